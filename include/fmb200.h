@@ -1,0 +1,114 @@
+/* fmb200.h -- C ABI of the B200-native libFM SGD hot path.
+ *
+ * The reference (srendle/libfm) has no plugin/FFI interface; its de-facto seam is
+ * the fm_learn vtable (src/libfm/src/fm_learn.h:31-60) and the per-row calls
+ * fm->predict / fm_SGD (src/libfm/src/fm_learn_sgd_element.h:57,66).  A per-row
+ * seam is useless for a GPU, so this ABI replaces the BODY OF THE EPOCH LOOP
+ * (fm_learn_sgd_element.h:56-67) and the evaluate / predict passes
+ * (fm_learn.h:93-153, fm_learn_sgd.h:76-90) at per-epoch granularity.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on error; the message is
+ *    available from fmb200_last_error() (thread-local static string).  Nothing
+ *    throws across the boundary (the reference throws std::string / const char*,
+ *    caught at libfm.cpp:436-440; the host learner converts codes back to that).
+ *  - plain pointers and sizes only.  Host pointers unless the name says device.
+ *  - one context == one GPU.  Not re-entrant per context (same as the reference,
+ *    whose fm_model carries mutable scratch, fm_model.h:65); distinct contexts
+ *    may be driven from distinct threads/processes.
+ *  - the library is CUDA-only: there is no CPU fallback.  fmb200_create fails
+ *    loudly when no sm_100 device is usable.
+ */
+#ifndef FMB200_H_
+#define FMB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fmb200_ctx fmb200_ctx;
+
+#define FMB200_TASK_REGRESSION 0     /* fm_learn.h:47 */
+#define FMB200_TASK_CLASSIFICATION 1 /* fm_learn.h:48 */
+
+/* execution modes of fmb200_sgd_epoch */
+#define FMB200_MODE_INORDER 0 /* sequential-equivalent: rows strictly in file order, fp64
+                                 state; bit-compatible with fm_learn_sgd_element::learn */
+#define FMB200_MODE_HOGWILD 1 /* throughput: rows in parallel, fp32 state, red.global.add
+                                 write-back, CTA-local bias carry */
+
+#define FMB200_MAX_SLOTS 8
+
+/* Replaces: fm_model construction, libfm.cpp:245-256 (num_attribute, k0, k1, num_factor).
+ * `device` is the CUDA ordinal. */
+int fmb200_create(fmb200_ctx** out, int device, uint32_t n_attr, int num_factor, int use_w0,
+                  int use_w);
+void fmb200_destroy(fmb200_ctx* ctx);
+const char* fmb200_last_error(void);
+
+/* Replaces: the learner fields set at libfm.cpp:294-309,366-404:
+ * task, learn_rate (scalar; fm_learn_sgd.h:67-69), reg0/regw/regv, min/max_target. */
+int fmb200_set_hparams(fmb200_ctx* ctx, int task, double learn_rate, double reg0, double regw,
+                       double regv, double min_target, double max_target);
+int fmb200_set_mode(fmb200_ctx* ctx, int mode);
+
+/* Replaces: the in-memory matrix Data::load builds (Data.h:180-290): upload a CSR
+ * copy of a data set into `slot` (0 = train, 1 = test, ...).  The context copies;
+ * the caller may free afterwards.  row_ptr has n_rows+1 entries, row_ptr[0]==0.
+ * Fails if any col >= n_attr (the reference's live assert, fm_model.h:112). */
+int fmb200_upload_data(fmb200_ctx* ctx, int slot, uint64_t n_rows, uint64_t nnz,
+                       const uint64_t* row_ptr, const uint32_t* col, const float* val,
+                       const float* target);
+/* Same, straight from the reference's AoS layout (util/fmatrix.h:34-42):
+ * `rows` points at n_rows sparse_row{sparse_entry* data; uint size;} records (16 B
+ * each on LP64), each entry {uint id; float value} (8 B). */
+int fmb200_upload_data_aos(fmb200_ctx* ctx, int slot, uint64_t n_rows, const void* rows,
+                           const float* target);
+int fmb200_free_data(fmb200_ctx* ctx, int slot);
+
+/* Replaces: reading / writing fm_model::w0, w, v (fm_model.h:46-48).  v is the
+ * reference's FACTOR-MAJOR double [num_factor][n_attr] (util/matrix.h:152-175). */
+int fmb200_set_params(fmb200_ctx* ctx, double w0, const double* w, const double* v_factor_major);
+int fmb200_get_params(fmb200_ctx* ctx, double* w0, double* w, double* v_factor_major);
+
+/* Replaces: the row loop of fm_learn_sgd_element::learn (fm_learn_sgd_element.h:56-67):
+ * predict + loss multiplier + fm_SGD over every row of `slot`.  Blocking; if
+ * device_seconds != NULL it receives the CUDA-event time of the epoch. */
+int fmb200_sgd_epoch(fmb200_ctx* ctx, int slot, double* device_seconds);
+/* enqueue only (no host sync); pair with fmb200_sync */
+int fmb200_sgd_epoch_async(fmb200_ctx* ctx, int slot);
+int fmb200_sync(fmb200_ctx* ctx);
+
+/* Replaces: fm_learn::evaluate_regression / evaluate_classification
+ * (fm_learn.h:113-153).  Regression fills sum_sq_err and sum_abs_err of
+ * clamp(p)-y; classification fills n_correct (sign agreement). */
+int fmb200_evaluate(fmb200_ctx* ctx, int slot, double* sum_sq_err, double* sum_abs_err,
+                    uint64_t* n_correct);
+
+/* Replaces: fm_learn_sgd::predict (fm_learn_sgd.h:76-90).  transform=1 applies
+ * the task transform (clamp / sigmoid) exactly as -out writes it; transform=0
+ * returns the raw score of fm_model::predict (fm_model.h:105-127). */
+int fmb200_predict(fmb200_ctx* ctx, int slot, int transform, double* out);
+
+/* Multi-GPU plumbing (row sharding + one all-reduce of w0|w|V per epoch; the
+ * reference has no equivalent).  The HOGWILD state is one packed fp32 device
+ * buffer [w0, pad x3 | w[n] padded to 4 | V[n][kp]]; the caller all-reduces it
+ * (NCCL) and calls fmb200_scale_params(1/G).  Both run on fmb200_stream(). */
+int fmb200_params_device(fmb200_ctx* ctx, void** device_ptr, uint64_t* n_floats);
+int fmb200_scale_params(fmb200_ctx* ctx, double factor);
+int fmb200_stream(fmb200_ctx* ctx, void** cuda_stream);
+
+/* Introspection for tests / bench */
+int fmb200_kernel_launches(fmb200_ctx* ctx, uint64_t* count); /* kernels launched so far */
+int fmb200_last_epoch_config(fmb200_ctx* ctx, int* lanes_per_row, int* slots, int* rows_per_tile,
+                             int* grid, int* block, int* smem_bytes);
+/* hogwild tuning knobs; 0 keeps the default.  ctas_per_sm bounds the number of
+ * rows in flight (the Hogwild staleness window). */
+int fmb200_set_tuning(fmb200_ctx* ctx, int ctas_per_sm, int rows_per_tile, int threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMB200_H_ */

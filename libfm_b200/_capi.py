@@ -1,0 +1,64 @@
+"""ctypes binding of include/fmb200.h (the C ABI of libfmb200.so).
+
+This is the same stub a maintainer of the reference would write to reach the
+library from Python; the C++ command line (host/) links the library directly.
+There is no fallback: if the shared object is missing, loading raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfmb200.so")
+
+# every symbol include/fmb200.h declares, with (restype, argtypes)
+_u64p = C.POINTER(C.c_uint64)
+_u32p = C.POINTER(C.c_uint32)
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+_intp = C.POINTER(C.c_int)
+_ctx = C.c_void_p
+
+SYMBOLS = {
+    "fmb200_create": (C.c_int, [C.POINTER(_ctx), C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int]),
+    "fmb200_destroy": (None, [_ctx]),
+    "fmb200_last_error": (C.c_char_p, []),
+    "fmb200_set_hparams": (C.c_int, [_ctx, C.c_int] + [C.c_double] * 6),
+    "fmb200_set_mode": (C.c_int, [_ctx, C.c_int]),
+    "fmb200_upload_data": (C.c_int, [_ctx, C.c_int, C.c_uint64, C.c_uint64, _u64p, _u32p, _f32p, _f32p]),
+    "fmb200_upload_data_aos": (C.c_int, [_ctx, C.c_int, C.c_uint64, C.c_void_p, _f32p]),
+    "fmb200_free_data": (C.c_int, [_ctx, C.c_int]),
+    "fmb200_set_params": (C.c_int, [_ctx, C.c_double, _f64p, _f64p]),
+    "fmb200_get_params": (C.c_int, [_ctx, _f64p, _f64p, _f64p]),
+    "fmb200_sgd_epoch": (C.c_int, [_ctx, C.c_int, _f64p]),
+    "fmb200_sgd_epoch_async": (C.c_int, [_ctx, C.c_int]),
+    "fmb200_sync": (C.c_int, [_ctx]),
+    "fmb200_evaluate": (C.c_int, [_ctx, C.c_int, _f64p, _f64p, _u64p]),
+    "fmb200_predict": (C.c_int, [_ctx, C.c_int, C.c_int, _f64p]),
+    "fmb200_params_device": (C.c_int, [_ctx, C.POINTER(C.c_void_p), _u64p]),
+    "fmb200_scale_params": (C.c_int, [_ctx, C.c_double]),
+    "fmb200_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),
+    "fmb200_kernel_launches": (C.c_int, [_ctx, _u64p]),
+    "fmb200_last_epoch_config": (C.c_int, [_ctx] + [_intp] * 6),
+    "fmb200_set_tuning": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen libfmb200.so and type every entry point.  Raises if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m libfm_b200.build` "
+                "(libfm_b200 has no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the export is missing
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

@@ -1,0 +1,497 @@
+// fm_context.cu -- the C ABI declared in include/fmb200.h: context lifetime,
+// host<->HBM layout conversion (bit-exact index/ordering work), epoch /
+// evaluate / predict entry points.  CUDA only: no CPU fallback exists.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "fmb200_internal.h"
+
+using namespace fmb;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+#define CK(expr)                                                                      \
+  do {                                                                                \
+    cudaError_t e__ = (expr);                                                         \
+    if (e__ != cudaSuccess)                                                           \
+      return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                  __LINE__);                                                          \
+  } while (0)
+
+#define NEED_CTX(c) \
+  if ((c) == nullptr) return fail("null context")
+
+int bind(fmb200_ctx* c) {
+  CK(cudaSetDevice(c->device));
+  return 0;
+}
+
+void free_slot(DataSlot& s) {
+  if (s.row_ptr) cudaFree(s.row_ptr);
+  if (s.col) cudaFree(s.col);
+  if (s.val) cudaFree(s.val);
+  if (s.target) cudaFree(s.target);
+  s = DataSlot();
+}
+
+// slack (in elements) behind every CSR array so that whole-tile TMA bulk copies
+// of the last tile stay inside the allocation
+constexpr uint64_t kRowSlack = 512 + 8;
+constexpr uint64_t kEntrySlack = 16;
+
+int upload_common(fmb200_ctx* c, int slot, uint64_t n_rows, uint64_t nnz, const uint64_t* row_ptr,
+                  const uint32_t* col, const float* val, const float* target) {
+  DataSlot& s = c->slots[slot];
+  free_slot(s);
+  // structural validation of the offsets (host side, O(n_rows))
+  if (row_ptr[0] != 0) return fail("row_ptr[0] must be 0");
+  uint32_t max_row = 0;
+  for (uint64_t r = 0; r < n_rows; r++) {
+    if (row_ptr[r + 1] < row_ptr[r]) return fail("row_ptr not monotone at row %llu", (unsigned long long)r);
+    uint64_t len = row_ptr[r + 1] - row_ptr[r];
+    if (len > 0xffffffffull) return fail("row %llu too long", (unsigned long long)r);
+    if (len > max_row) max_row = (uint32_t)len;
+  }
+  if (row_ptr[n_rows] != nnz) return fail("row_ptr[n_rows]=%llu != nnz=%llu",
+                                          (unsigned long long)row_ptr[n_rows], (unsigned long long)nnz);
+  for (int i = 0; i < 5; i++) {
+    const uint64_t TR = 32ull << i;
+    uint64_t worst = 0;
+    for (uint64_t r0 = 0; r0 < n_rows; r0 += TR) {
+      uint64_t r1 = r0 + TR < n_rows ? r0 + TR : n_rows;
+      uint64_t ab = row_ptr[r0] & ~3ull, ae = (row_ptr[r1] + 3ull) & ~3ull;
+      if (ae - ab > worst) worst = ae - ab;
+    }
+    if (worst > 0xffffffffull) return fail("tile too large");
+    s.tile_span[i] = (uint32_t)worst;
+  }
+  s.max_row_nnz = max_row;
+  s.n_rows = n_rows;
+  s.nnz = nnz;
+  CK(cudaMalloc(&s.row_ptr, (n_rows + 1 + kRowSlack) * sizeof(uint64_t)));
+  CK(cudaMalloc(&s.target, (n_rows + kRowSlack) * sizeof(float)));
+  CK(cudaMalloc(&s.col, (nnz + kEntrySlack) * sizeof(uint32_t)));
+  CK(cudaMalloc(&s.val, (nnz + kEntrySlack) * sizeof(float)));
+  CK(cudaMemsetAsync(s.row_ptr + n_rows + 1, 0, kRowSlack * sizeof(uint64_t), c->stream));
+  CK(cudaMemsetAsync(s.target + n_rows, 0, kRowSlack * sizeof(float), c->stream));
+  CK(cudaMemsetAsync(s.col + nnz, 0, kEntrySlack * sizeof(uint32_t), c->stream));
+  CK(cudaMemsetAsync(s.val + nnz, 0, kEntrySlack * sizeof(float), c->stream));
+  CK(cudaMemcpyAsync(s.row_ptr, row_ptr, (n_rows + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(s.target, target, n_rows * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(s.col, col, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(s.val, val, nnz * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  // the reference asserts id < num_attribute per access (fm_model.h:112);
+  // here the whole data set is checked once, on the device
+  if (nnz > 0) {
+    CK(cudaMemsetAsync(c->d_flag, 0, sizeof(unsigned int), c->stream));
+    CK(launch_max_col(c, s.col, nnz, c->d_flag));
+    unsigned int mx = 0;
+    CK(cudaMemcpyAsync(&mx, c->d_flag, sizeof(mx), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (mx >= c->n) {
+      free_slot(s);
+      return fail("feature id %u out of range (num_attribute=%u)", mx, c->n);
+    }
+  } else {
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  s.present = true;
+  return 0;
+}
+
+int need_slot(fmb200_ctx* c, int slot) {
+  if (slot < 0 || slot >= FMB200_MAX_SLOTS) return fail("slot %d out of range", slot);
+  if (!c->slots[slot].present) return fail("slot %d holds no data", slot);
+  return 0;
+}
+
+int ensure_partials(fmb200_ctx* c, int n_blocks) {
+  if (c->n_partials < n_blocks) {
+    if (c->d_partials) cudaFree(c->d_partials);
+    c->d_partials = nullptr;
+    CK(cudaMalloc(&c->d_partials, sizeof(double) * 3 * n_blocks));
+    c->n_partials = n_blocks;
+  }
+  return 0;
+}
+
+int metric_blocks(fmb200_ctx* c, const DataSlot& s) {
+  uint64_t want = (s.n_rows + 255) / 256;
+  uint64_t cap = (uint64_t)c->sm_count * 8;
+  uint64_t b = want < cap ? want : cap;
+  return (int)(b < 1 ? 1 : b);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fmb200_last_error(void) { return g_err; }
+
+int fmb200_create(fmb200_ctx** out, int device, uint32_t n_attr, int num_factor, int use_w0,
+                  int use_w) {
+  if (out == nullptr) return fail("null out pointer");
+  *out = nullptr;
+  if (num_factor < 0) return fail("num_factor must be >= 0");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail("no CUDA device available (%s): libfmb200 has no CPU path",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail("device %d out of range (count %d)", device, count);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail("device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major,
+                prop.minor);
+  fmb200_ctx* c = new (std::nothrow) fmb200_ctx();
+  if (!c) return fail("out of host memory");
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  c->n = n_attr;
+  c->k = num_factor;
+  c->kp = (num_factor + 3) & ~3;
+  c->k0 = use_w0 != 0;
+  c->k1 = use_w != 0;
+  CK(cudaSetDevice(device));
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&c->ev0));
+  CK(cudaEventCreate(&c->ev1));
+  const uint64_t n4 = ((uint64_t)n_attr + 3) & ~3ull;
+  c->p32.off_w = 4;
+  c->p32.off_v = 4 + n4;
+  c->p32.n_floats = 4 + n4 + (uint64_t)n_attr * c->kp;
+  c->p64.off_v = 1 + (uint64_t)n_attr;
+  c->p64.n_doubles = 1 + (uint64_t)n_attr + (uint64_t)n_attr * num_factor;
+  CK(cudaMalloc(&c->p32.base, c->p32.n_floats * sizeof(float)));
+  CK(cudaMalloc(&c->p64.base, c->p64.n_doubles * sizeof(double)));
+  CK(cudaMemsetAsync(c->p32.base, 0, c->p32.n_floats * sizeof(float), c->stream));
+  CK(cudaMemsetAsync(c->p64.base, 0, c->p64.n_doubles * sizeof(double), c->stream));
+  CK(cudaMalloc(&c->d_w0_accum, sizeof(float)));
+  CK(cudaMalloc(&c->d_done, sizeof(unsigned int)));
+  CK(cudaMalloc(&c->d_flag, sizeof(unsigned int)));
+  CK(cudaMemsetAsync(c->d_w0_accum, 0, sizeof(float), c->stream));
+  CK(cudaMemsetAsync(c->d_done, 0, sizeof(unsigned int), c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *out = c;
+  return 0;
+}
+
+void fmb200_destroy(fmb200_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < FMB200_MAX_SLOTS; i++) free_slot(c->slots[i]);
+  if (c->p32.base) cudaFree(c->p32.base);
+  if (c->p64.base) cudaFree(c->p64.base);
+  if (c->d_partials) cudaFree(c->d_partials);
+  if (c->d_pred) cudaFree(c->d_pred);
+  if (c->d_w0_accum) cudaFree(c->d_w0_accum);
+  if (c->d_done) cudaFree(c->d_done);
+  if (c->d_flag) cudaFree(c->d_flag);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int fmb200_set_hparams(fmb200_ctx* c, int task, double learn_rate, double reg0, double regw,
+                       double regv, double min_target, double max_target) {
+  NEED_CTX(c);
+  if (task != FMB200_TASK_REGRESSION && task != FMB200_TASK_CLASSIFICATION)
+    return fail("unknown task");  // fm_learn.h:99-101 throws "unknown task"
+  c->hp.task = task;
+  c->hp.lr = learn_rate;
+  c->hp.reg0 = reg0;
+  c->hp.regw = regw;
+  c->hp.regv = regv;
+  c->hp.min_target = min_target;
+  c->hp.max_target = max_target;
+  return 0;
+}
+
+int fmb200_set_mode(fmb200_ctx* c, int mode) {
+  NEED_CTX(c);
+  if (mode != FMB200_MODE_INORDER && mode != FMB200_MODE_HOGWILD) return fail("unknown mode %d", mode);
+  if (mode == c->mode) return 0;
+  if (bind(c)) return 1;
+  // carry the live state into the representation of the new mode
+  if (mode == FMB200_MODE_HOGWILD) {
+    CK(launch_p64_to_p32(c));
+  } else {
+    if (c->k > 256) return fail("num_factor > 256 is not supported in INORDER mode");
+    CK(launch_p32_to_p64(c));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  c->mode = mode;
+  return 0;
+}
+
+int fmb200_upload_data(fmb200_ctx* c, int slot, uint64_t n_rows, uint64_t nnz,
+                       const uint64_t* row_ptr, const uint32_t* col, const float* val,
+                       const float* target) {
+  NEED_CTX(c);
+  if (slot < 0 || slot >= FMB200_MAX_SLOTS) return fail("slot %d out of range", slot);
+  if (!row_ptr || (n_rows && !target) || (nnz && (!col || !val))) return fail("null data pointer");
+  if (n_rows > 0xffffffffull) return fail("row count exceeds the reference's uint range");
+  if (bind(c)) return 1;
+  return upload_common(c, slot, n_rows, nnz, row_ptr, col, val, target);
+}
+
+int fmb200_upload_data_aos(fmb200_ctx* c, int slot, uint64_t n_rows, const void* rows,
+                           const float* target) {
+  NEED_CTX(c);
+  if (slot < 0 || slot >= FMB200_MAX_SLOTS) return fail("slot %d out of range", slot);
+  if (n_rows && (!rows || !target)) return fail("null data pointer");
+  if (bind(c)) return 1;
+  // reference layout, util/fmatrix.h:34-42
+  struct Entry {
+    uint32_t id;
+    float value;
+  };
+  struct Row {
+    const Entry* data;
+    uint32_t size;
+  };
+  static_assert(sizeof(Row) == 16 && sizeof(Entry) == 8, "LP64 layout of sparse_row/sparse_entry");
+  const Row* r = static_cast<const Row*>(rows);
+  std::vector<uint64_t> rp(n_rows + 1);
+  rp[0] = 0;
+  for (uint64_t i = 0; i < n_rows; i++) rp[i + 1] = rp[i] + r[i].size;
+  const uint64_t nnz = rp[n_rows];
+  std::vector<uint32_t> col(nnz ? nnz : 1);
+  std::vector<float> val(nnz ? nnz : 1);
+  for (uint64_t i = 0; i < n_rows; i++) {
+    const Entry* e = r[i].data;
+    uint64_t o = rp[i];
+    for (uint32_t j = 0; j < r[i].size; j++) {
+      col[o + j] = e[j].id;
+      val[o + j] = e[j].value;
+    }
+  }
+  return upload_common(c, slot, n_rows, nnz, rp.data(), col.data(), val.data(), target);
+}
+
+int fmb200_free_data(fmb200_ctx* c, int slot) {
+  NEED_CTX(c);
+  if (slot < 0 || slot >= FMB200_MAX_SLOTS) return fail("slot %d out of range", slot);
+  if (bind(c)) return 1;
+  CK(cudaStreamSynchronize(c->stream));
+  free_slot(c->slots[slot]);
+  return 0;
+}
+
+int fmb200_set_params(fmb200_ctx* c, double w0, const double* w, const double* v) {
+  NEED_CTX(c);
+  if ((c->n && !w) || ((uint64_t)c->n * c->k && !v)) return fail("null parameter pointer");
+  if (bind(c)) return 1;
+  const uint32_t n = c->n;
+  const int k = c->k, kp = c->kp;
+  // fp64 image: [w0 | w | V attribute-major]
+  std::vector<double> h64(c->p64.n_doubles);
+  h64[0] = w0;
+  for (uint32_t i = 0; i < n; i++) h64[1 + i] = w[i];
+  double* hv = h64.data() + c->p64.off_v;
+  for (int f = 0; f < k; f++)
+    for (uint32_t i = 0; i < n; i++) hv[(size_t)i * k + f] = v[(size_t)f * n + i];
+  // fp32 packed image
+  std::vector<float> h32(c->p32.n_floats, 0.f);
+  h32[0] = (float)w0;
+  for (uint32_t i = 0; i < n; i++) h32[c->p32.off_w + i] = (float)w[i];
+  float* hv32 = h32.data() + c->p32.off_v;
+  for (int f = 0; f < k; f++)
+    for (uint32_t i = 0; i < n; i++) hv32[(size_t)i * kp + f] = (float)v[(size_t)f * n + i];
+  CK(cudaMemcpyAsync(c->p64.base, h64.data(), h64.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->p32.base, h32.data(), h32.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int fmb200_get_params(fmb200_ctx* c, double* w0, double* w, double* v) {
+  NEED_CTX(c);
+  if (!w0 || (c->n && !w) || ((uint64_t)c->n * c->k && !v)) return fail("null parameter pointer");
+  if (bind(c)) return 1;
+  const uint32_t n = c->n;
+  const int k = c->k, kp = c->kp;
+  if (c->mode == FMB200_MODE_INORDER) {
+    std::vector<double> h(c->p64.n_doubles);
+    CK(cudaMemcpyAsync(h.data(), c->p64.base, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *w0 = h[0];
+    for (uint32_t i = 0; i < n; i++) w[i] = h[1 + i];
+    const double* hv = h.data() + c->p64.off_v;
+    for (int f = 0; f < k; f++)
+      for (uint32_t i = 0; i < n; i++) v[(size_t)f * n + i] = hv[(size_t)i * k + f];
+  } else {
+    std::vector<float> h(c->p32.n_floats);
+    CK(cudaMemcpyAsync(h.data(), c->p32.base, h.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *w0 = h[0];
+    for (uint32_t i = 0; i < n; i++) w[i] = h[c->p32.off_w + i];
+    const float* hv = h.data() + c->p32.off_v;
+    for (int f = 0; f < k; f++)
+      for (uint32_t i = 0; i < n; i++) v[(size_t)f * n + i] = hv[(size_t)i * kp + f];
+  }
+  return 0;
+}
+
+int fmb200_sgd_epoch_async(fmb200_ctx* c, int slot) {
+  NEED_CTX(c);
+  if (need_slot(c, slot)) return 1;
+  if (bind(c)) return 1;
+  const DataSlot& d = c->slots[slot];
+  if (c->mode == FMB200_MODE_INORDER) {
+    if (c->k > 256) return fail("num_factor > 256 is not supported in INORDER mode");
+    CK(launch_sgd_inorder(c, d));
+  } else {
+    if (c->kp > 128) return fail("num_factor > 128 is not supported in HOGWILD mode");
+    CK(launch_sgd_hogwild(c, d));
+  }
+  return 0;
+}
+
+int fmb200_sync(fmb200_ctx* c) {
+  NEED_CTX(c);
+  if (bind(c)) return 1;
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int fmb200_sgd_epoch(fmb200_ctx* c, int slot, double* device_seconds) {
+  NEED_CTX(c);
+  if (bind(c)) return 1;
+  CK(cudaEventRecord(c->ev0, c->stream));
+  if (fmb200_sgd_epoch_async(c, slot)) return 1;
+  CK(cudaEventRecord(c->ev1, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (device_seconds) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    *device_seconds = (double)ms * 1e-3;
+  }
+  return 0;
+}
+
+int fmb200_evaluate(fmb200_ctx* c, int slot, double* sum_sq_err, double* sum_abs_err,
+                    uint64_t* n_correct) {
+  NEED_CTX(c);
+  if (need_slot(c, slot)) return 1;
+  if (bind(c)) return 1;
+  const DataSlot& d = c->slots[slot];
+  double sq = 0, ab = 0, ok = 0;
+  if (d.n_rows > 0) {
+    const int nb = metric_blocks(c, d);
+    if (ensure_partials(c, nb)) return 1;
+    if (c->mode == FMB200_MODE_INORDER) {
+      CK(launch_predict64(c, d, 0, nullptr, c->d_partials, nb));
+    } else {
+      CK(launch_predict32(c, d, 0, nullptr, c->d_partials, nb));
+    }
+    std::vector<double> h(3 * (size_t)nb);
+    CK(cudaMemcpyAsync(h.data(), c->d_partials, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int b = 0; b < nb; b++) {  // fixed order: deterministic result
+      sq += h[3 * b + 0];
+      ab += h[3 * b + 1];
+      ok += h[3 * b + 2];
+    }
+  }
+  if (sum_sq_err) *sum_sq_err = sq;
+  if (sum_abs_err) *sum_abs_err = ab;
+  if (n_correct) *n_correct = (uint64_t)llround(ok);
+  return 0;
+}
+
+int fmb200_predict(fmb200_ctx* c, int slot, int transform, double* out) {
+  NEED_CTX(c);
+  if (need_slot(c, slot)) return 1;
+  if (bind(c)) return 1;
+  const DataSlot& d = c->slots[slot];
+  if (d.n_rows == 0) return 0;
+  if (!out) return fail("null output pointer");
+  if (c->pred_cap < d.n_rows) {
+    if (c->d_pred) cudaFree(c->d_pred);
+    c->d_pred = nullptr;
+    c->pred_cap = 0;
+    CK(cudaMalloc(&c->d_pred, d.n_rows * sizeof(double)));
+    c->pred_cap = d.n_rows;
+  }
+  const int nb = metric_blocks(c, d);
+  if (c->mode == FMB200_MODE_INORDER) {
+    CK(launch_predict64(c, d, transform, c->d_pred, nullptr, nb));
+  } else {
+    CK(launch_predict32(c, d, transform, c->d_pred, nullptr, nb));
+  }
+  CK(cudaMemcpyAsync(out, c->d_pred, d.n_rows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int fmb200_params_device(fmb200_ctx* c, void** device_ptr, uint64_t* n_floats) {
+  NEED_CTX(c);
+  if (c->mode != FMB200_MODE_HOGWILD) return fail("packed fp32 state is live only in HOGWILD mode");
+  if (device_ptr) *device_ptr = c->p32.base;
+  if (n_floats) *n_floats = c->p32.n_floats;
+  return 0;
+}
+
+int fmb200_scale_params(fmb200_ctx* c, double factor) {
+  NEED_CTX(c);
+  if (c->mode != FMB200_MODE_HOGWILD) return fail("scale_params applies to the HOGWILD state");
+  if (bind(c)) return 1;
+  CK(launch_scale_p32(c, (float)factor));
+  return 0;
+}
+
+int fmb200_stream(fmb200_ctx* c, void** cuda_stream) {
+  NEED_CTX(c);
+  if (cuda_stream) *cuda_stream = (void*)c->stream;
+  return 0;
+}
+
+int fmb200_kernel_launches(fmb200_ctx* c, uint64_t* count) {
+  NEED_CTX(c);
+  if (count) *count = c->launches;
+  return 0;
+}
+
+int fmb200_last_epoch_config(fmb200_ctx* c, int* lanes_per_row, int* slots, int* rows_per_tile,
+                             int* grid, int* block, int* smem_bytes) {
+  NEED_CTX(c);
+  if (lanes_per_row) *lanes_per_row = c->last_cfg.lanes_per_row;
+  if (slots) *slots = c->last_cfg.slots;
+  if (rows_per_tile) *rows_per_tile = c->last_cfg.rows_per_tile;
+  if (grid) *grid = c->last_cfg.grid;
+  if (block) *block = c->last_cfg.block;
+  if (smem_bytes) *smem_bytes = c->last_cfg.smem;
+  return 0;
+}
+
+int fmb200_set_tuning(fmb200_ctx* c, int ctas_per_sm, int rows_per_tile, int threads) {
+  NEED_CTX(c);
+  if (threads && (threads % 32 != 0 || threads < 32 || threads > 256))
+    return fail("threads must be a multiple of 32 in [32,256]");
+  if (rows_per_tile && (rows_per_tile < 32 || rows_per_tile > 512))
+    return fail("rows_per_tile must be in [32,512]");
+  c->tune_ctas_per_sm = ctas_per_sm;
+  c->tune_rows_per_tile = rows_per_tile;
+  c->tune_threads = threads;
+  return 0;
+}
+
+}  // extern "C"

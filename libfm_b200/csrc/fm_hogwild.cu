@@ -1,0 +1,397 @@
+// fm_hogwild.cu -- the throughput SGD epoch (FMB200_MODE_HOGWILD), sm_100a.
+//
+// Replaces the row loop of fm_learn_sgd_element::learn (reference
+// src/libfm/src/fm_learn_sgd_element.h:56-67 = fm_model::predict, fm_model.h:105-127,
+// + loss multiplier + fm_SGD, fm_sgd.h:33-51) with ONE persistent kernel launch
+// per epoch.
+//
+// Structure
+//  * grid = (#SMs x CTAs/SM) persistent CTAs; CTA b takes row tiles b, b+grid, ...
+//    (tiles = rows_per_tile consecutive rows, so the set of rows in flight is a
+//    window sliding through the file in order).
+//  * CSR staging: thread 0 is the TMA producer.  Per tile it issues four 1-D bulk
+//    copies (cp.async.bulk global->shared, mbarrier complete_tx): row offsets,
+//    targets, column ids, values; NSTAGE tiles are in flight per CTA, marked
+//    L2 evict_first (the CSR is streamed once per epoch).
+//  * compute: every warp handles 32/E rows at a time with the RowGroup mapping
+//    (fm_rowgroup.cuh): V rows gathered as float4 with ld.global.cg (parameters
+//    are mutated by other SMs through L2, so L1 must not serve them), per-factor
+//    sums by segmented warp shuffles, write-back as fire-and-forget
+//    red.global.add.v4.f32 / red.global.add.f32 (Hogwild: no locks, no CAS).
+//  * bias w0: every example touches it (fm_sgd.h:34-37), so naive Hogwild
+//    (sum of B stale gradients) has gain lr*B and diverges for B >> 1/lr.  Each
+//    CTA therefore carries a LOCAL bias through its own tile sequence and applies,
+//    per tile of T rows, the closed-form solution of the reference's sequential
+//    recurrence w0 <- w0 - lr*(mult_t + reg0*w0) under a frozen-residual /
+//    mean-curvature linearisation:  dw0 = gamma * (-lr) * sum_t(mult_t + reg0*w0),
+//    gamma = (1 - a^T) / (T (1 - a)),  a = 1 - lr (h + reg0),  h = mean d mult/d w0
+//    (gamma == 1 for T == 1, i.e. exactly the reference's step).  At the end of the
+//    epoch the row-weighted mean of the CTA-local biases becomes the global w0.
+//
+// Algorithmic HBM traffic per example (roofline numerator, BASELINE.json):
+// 2*k*nnz*4 bytes (V rows read + written back).
+#include <algorithm>
+
+#include "fm_rowgroup.cuh"
+#include "fmb200_internal.h"
+
+namespace fmb {
+
+constexpr int HW_NSTAGE = 3;
+constexpr int HW_MAX_THREADS = 256;
+constexpr int HW_HDR_BYTES = 128;  // mbarriers + per-tile bias accumulators
+
+struct HogwildArgs {
+  const uint64_t* row_ptr;
+  const uint32_t* col;
+  const float* val;
+  const float* target;
+  uint64_t n_rows;
+  uint32_t n_tiles;
+  int tile_rows;       // TR (multiple of 32)
+  uint32_t tile_cap;   // max staged entries per tile (multiple of 4)
+  uint32_t stage_bytes;
+  float* w0;
+  float* w;
+  float* v;
+  int gp;  // float4 chunks per V row (kp / 4)
+  int use_w0, use_w, task;
+  float lr, reg0, regw, regv, min_target, max_target;
+  float* w0_accum;
+  unsigned int* done;
+};
+
+__device__ __forceinline__ unsigned char* stage_base(unsigned char* smem, const HogwildArgs& a,
+                                                     int stage) {
+  return smem + HW_HDR_BYTES + (size_t)stage * a.stage_bytes;
+}
+
+// TMA producer: stage one tile.  Called by a single thread.
+__device__ __forceinline__ void issue_tile(const HogwildArgs& a, unsigned char* smem,
+                                           uint64_t* bars, uint32_t tile, int stage,
+                                           uint64_t policy) {
+  const int TR = a.tile_rows;
+  const uint64_t r0 = (uint64_t)tile * TR;
+  const uint64_t r1 = min(r0 + (uint64_t)TR, a.n_rows);
+  const uint64_t nb = __ldg(a.row_ptr + r0);
+  const uint64_t ne = __ldg(a.row_ptr + r1);
+  const uint64_t ab = nb & ~3ull;
+  const uint64_t ae = (ne + 3ull) & ~3ull;
+  const uint32_t ebytes = (uint32_t)(ae - ab) * 4u;
+  const uint32_t rp_bytes = (uint32_t)(TR + 2) * 8u;
+  const uint32_t y_bytes = (uint32_t)TR * 4u;
+  unsigned char* sb = stage_base(smem, a, stage);
+  uint64_t* bar = bars + stage;
+  mbar_arrive_expect_tx(bar, rp_bytes + y_bytes + 2u * ebytes);
+  bulk_g2s_hint(sb, a.row_ptr + r0, rp_bytes, bar, policy);
+  bulk_g2s_hint(sb + rp_bytes, a.target + r0, y_bytes, bar, policy);
+  if (ebytes) {
+    unsigned char* cb = sb + rp_bytes + y_bytes;
+    bulk_g2s_hint(cb, a.col + ab, ebytes, bar, policy);
+    bulk_g2s_hint(cb + (size_t)a.tile_cap * 4u, a.val + ab, ebytes, bar, policy);
+  }
+}
+
+template <int G, int S, int R>
+__global__ void __launch_bounds__(HW_MAX_THREADS, (R <= 2 ? 4 : 2))
+    fm_sgd_hogwild_kernel(const HogwildArgs a) {
+  using RG = RowGroup<G, S, R>;
+  constexpr int E = RG::E;
+  constexpr int RPW = 32 / E;  // rows per warp per pass
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  float* s_acc = reinterpret_cast<float*>(smem + 64);  // [3][2]: sum mult, sum curvature
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int nwarp = blockDim.x >> 5;
+  const int rows_per_pass = nwarp * RPW;
+  const int lig = lane % E;  // lane in group
+  const int c = lig % G;
+  const int s = lig / G;
+  const int sub = lane / E;  // which of the warp's RPW rows
+  const int TR = a.tile_rows;
+
+  uint64_t policy = 0;
+  if (tid == 0) {
+    for (int i = 0; i < HW_NSTAGE; i++) mbar_init(bars + i, 1);
+    for (int i = 0; i < 6; i++) s_acc[i] = 0.f;
+    fence_mbar_init();
+    policy = policy_evict_first();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 0; i < HW_NSTAGE; i++) {
+      uint64_t t = (uint64_t)blockIdx.x + (uint64_t)i * gridDim.x;
+      if (t < a.n_tiles) issue_tile(a, smem, bars, (uint32_t)t, i, policy);
+    }
+  }
+
+  const float4* V4 = reinterpret_cast<const float4*>(a.v);
+  const bool use_w = a.use_w != 0;
+  const bool use_w0 = a.use_w0 != 0;
+  float w0 = use_w0 ? ld_cg_f(a.w0) : 0.f;
+  const float lr = a.lr;
+  uint64_t my_rows = 0;
+
+  int it = 0;
+  for (uint64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+    const int stage = it % HW_NSTAGE;
+    const uint32_t parity = (uint32_t)(it / HW_NSTAGE) & 1u;
+    mbar_wait(bars + stage, parity);
+
+    unsigned char* sb = stage_base(smem, a, stage);
+    const uint64_t* rp = reinterpret_cast<const uint64_t*>(sb);
+    const float* ys = reinterpret_cast<const float*>(sb + (size_t)(TR + 2) * 8);
+    const uint32_t* ids = reinterpret_cast<const uint32_t*>(sb + (size_t)(TR + 2) * 8 + (size_t)TR * 4);
+    const float* xs = reinterpret_cast<const float*>(ids + a.tile_cap);
+    const uint64_t row0 = tile * (uint64_t)TR;
+    const int rows_here = (int)min((uint64_t)TR, a.n_rows - row0);
+    const uint64_t ab = rp[0] & ~3ull;
+
+    float msum = 0.f, hsum = 0.f;
+    for (int rbase = warp * RPW; rbase < rows_here; rbase += rows_per_pass) {
+      const int r = rbase + sub;
+      const bool valid = r < rows_here;
+      int beg = 0, end = 0;
+      float y = 0.f;
+      if (valid) {
+        beg = (int)(rp[r] - ab);
+        end = (int)(rp[r + 1] - ab);
+        y = ys[r];
+      }
+      RG g;
+      const float part = g.score(V4, a.w, a.gp, use_w, ids, xs, beg, end, c, s);
+      float p = w0 + part;
+      float mult, curv;
+      if (a.task == FMB200_TASK_REGRESSION) {
+        // fm_learn_sgd_element.h:59-62
+        const float pc = fmaxf(a.min_target, fminf(a.max_target, p));
+        curv = (pc == p) ? 1.f : 0.f;
+        mult = pc - y;
+      } else {
+        // fm_learn_sgd_element.h:63-64 ; y in {-1,+1}
+        const float sg = 1.f / (1.f + __expf(-y * p));
+        mult = -y * (1.f - sg);
+        curv = sg * (1.f - sg);
+      }
+      if (valid && lig == 0) {
+        msum += mult;
+        hsum += curv;
+      }
+      // ---- fm_SGD write-back (fm_sgd.h:38-50) as L2 reductions ----
+      const float nlr_mult = -lr * mult;
+      const float nlr_regv = -lr * a.regv;
+      const float nlr_regw = -lr * a.regw;
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const int j = beg + s + q * S;
+        if (j < end) {
+          const float x = g.xc[q];
+          const uint32_t id = g.idc[q];
+          if (c < a.gp) {
+            const float4 v = g.vc[q];
+            const float x2 = x * x;
+            // -lr*(mult*(sum_f*x - v*x^2) + regv*v)
+            red_add_f4(a.v + ((size_t)id * a.gp + c) * 4,
+                       nlr_mult * (g.acc.x * x - v.x * x2) + nlr_regv * v.x,
+                       nlr_mult * (g.acc.y * x - v.y * x2) + nlr_regv * v.y,
+                       nlr_mult * (g.acc.z * x - v.z * x2) + nlr_regv * v.z,
+                       nlr_mult * (g.acc.w * x - v.w * x2) + nlr_regv * v.w);
+          }
+          if (use_w && c == 0) red_add_f(a.w + id, nlr_mult * x + nlr_regw * g.wc[q]);
+        }
+      }
+      for (int q = R; q < g.maxit; ++q) {
+        const int j = beg + s + q * S;
+        if (j < end) {
+          const float x = xs[j];
+          const uint32_t id = ids[j];
+          if (c < a.gp) {
+            const float4 v = ld_cg_f4(V4 + (size_t)id * a.gp + c);
+            const float x2 = x * x;
+            red_add_f4(a.v + ((size_t)id * a.gp + c) * 4,
+                       nlr_mult * (g.acc.x * x - v.x * x2) + nlr_regv * v.x,
+                       nlr_mult * (g.acc.y * x - v.y * x2) + nlr_regv * v.y,
+                       nlr_mult * (g.acc.z * x - v.z * x2) + nlr_regv * v.z,
+                       nlr_mult * (g.acc.w * x - v.w * x2) + nlr_regv * v.w);
+          }
+          if (use_w && c == 0) {
+            const float wv = ld_cg_f(a.w + id);
+            red_add_f(a.w + id, nlr_mult * x + nlr_regw * wv);
+          }
+        }
+      }
+    }
+
+    // ---- per-tile bias step (CTA-local carry) ----
+    const int slot = it % 3;
+    if (use_w0) {
+      msum = warp_sum(msum);
+      hsum = warp_sum(hsum);
+      if (lane == 0) {
+        atomicAdd(&s_acc[2 * slot + 0], msum);
+        atomicAdd(&s_acc[2 * slot + 1], hsum);
+      }
+    }
+    __syncthreads();  // tile consumed: stage is free, accumulators complete
+    if (tid == 0) {
+      const uint64_t nt = tile + (uint64_t)HW_NSTAGE * gridDim.x;
+      if (nt < a.n_tiles) issue_tile(a, smem, bars, (uint32_t)nt, stage, policy);
+      const int zs = (it + 2) % 3;  // last read before the previous barrier
+      s_acc[2 * zs + 0] = 0.f;
+      s_acc[2 * zs + 1] = 0.f;
+    }
+    if (use_w0) {
+      const float T = (float)rows_here;
+      const float M = s_acc[2 * slot + 0];
+      const float H = s_acc[2 * slot + 1];
+      const float q = lr * (H / T + a.reg0);  // 1 - a
+      float gamma = 1.f;
+      if (q * T > 1e-3f) {
+        const float aa = fmaxf(1.f - q, 0.f);
+        gamma = (1.f - __powf(aa, T)) / (T * q);
+      }
+      w0 += gamma * (-lr) * (M + T * a.reg0 * w0);
+    }
+    my_rows += rows_here;
+  }
+
+  // ---- merge the CTA-local biases: row-weighted mean ----
+  if (use_w0 && tid == 0) {
+    if (my_rows > 0) atomicAdd(a.w0_accum, w0 * (float)((double)my_rows / (double)a.n_rows));
+    __threadfence();
+    const unsigned int ticket = atomicAdd(a.done, 1u);
+    if (ticket == gridDim.x - 1) {
+      __threadfence();
+      const float merged = atomicExch(a.w0_accum, 0.f);
+      *a.w0 = merged;
+      *a.done = 0u;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+using KernelFn = void (*)(const HogwildArgs);
+
+template <int G, int S>
+KernelFn pick_r(int R) {
+  switch (R) {
+    case 1: return fm_sgd_hogwild_kernel<G, S, 1>;
+    case 2: return fm_sgd_hogwild_kernel<G, S, 2>;
+    default: return fm_sgd_hogwild_kernel<G, S, 8>;
+  }
+}
+
+template <int G>
+KernelFn pick_s(int S, int R) {
+  if constexpr (G <= 4) {
+    if (S >= 8) return pick_r<G, 8>(R);
+  }
+  if constexpr (G <= 8) {
+    if (S >= 4) return pick_r<G, 4>(R);
+  }
+  if constexpr (G <= 16) {
+    if (S >= 2) return pick_r<G, 2>(R);
+  }
+  return pick_r<G, 1>(R);
+}
+
+static KernelFn pick_kernel(int G, int S, int R) {
+  switch (G) {
+    case 1: return pick_s<1>(S, R);
+    case 2: return pick_s<2>(S, R);
+    case 4: return pick_s<4>(S, R);
+    case 8: return pick_s<8>(S, R);
+    case 16: return pick_s<16>(S, R);
+    default: return pick_s<32>(S, R);
+  }
+}
+
+void pick_geometry(int kp, uint64_t n_rows, uint64_t nnz, int* G, int* S) {
+  int gp = kp / 4;
+  int g = 1;
+  while (g < gp) g <<= 1;
+  if (g > 32) g = 32;
+  double avg = n_rows ? (double)nnz / (double)n_rows : 1.0;
+  int s = 1;
+  while (s < avg && s < 8) s <<= 1;
+  while (g * s > 32) s >>= 1;
+  if (s < 1) s = 1;
+  *G = g;
+  *S = s;
+}
+
+cudaError_t launch_sgd_hogwild(fmb200_ctx* c, const DataSlot& d) {
+  if (c->kp / 4 > 32) return cudaErrorInvalidValue;  // num_factor <= 128 in this mode
+  if (d.n_rows == 0) return cudaSuccess;
+  int G, S;
+  pick_geometry(c->kp, d.n_rows, d.nnz, &G, &S);
+  const double avg = (double)d.nnz / (double)d.n_rows;
+  const int iters = (int)((avg + S - 1) / S);
+  const int R = iters <= 1 ? 1 : (iters <= 2 ? 2 : 8);
+  const int threads = c->tune_threads > 0 ? std::min(c->tune_threads, HW_MAX_THREADS) : 256;
+
+  // tile geometry: largest tile (<= 256 rows by default) whose worst-case
+  // staged entry count keeps NSTAGE stages within a quarter of the SM's smem
+  const int budget = (c->max_smem_optin - 1024) / (R <= 2 ? 4 : 2);
+  int tr_idx = 3;  // 256 rows
+  if (c->tune_rows_per_tile > 0) {
+    tr_idx = 0;
+    while (tr_idx < 4 && (32 << (tr_idx + 1)) <= c->tune_rows_per_tile) tr_idx++;
+  }
+  auto stage_bytes_for = [&](int idx) {
+    const int TR = 32 << idx;
+    const uint32_t cap = (d.tile_span[idx] + 3u) & ~3u;
+    return (uint32_t)((TR + 2) * 8 + TR * 4 + 2 * cap * 4 + 15) & ~15u;
+  };
+  while (tr_idx > 0 && HW_HDR_BYTES + HW_NSTAGE * (int)stage_bytes_for(tr_idx) > budget) tr_idx--;
+  const int TR = 32 << tr_idx;
+  const uint32_t sbytes = stage_bytes_for(tr_idx);
+  const int smem = HW_HDR_BYTES + HW_NSTAGE * (int)sbytes;
+  if (smem > c->max_smem_optin) return cudaErrorInvalidConfiguration;  // one row longer than smem
+
+  KernelFn fn = pick_kernel(G, S, R);
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorInvalidConfiguration;
+  int per_sm = c->tune_ctas_per_sm > 0 ? std::min(c->tune_ctas_per_sm, occ) : occ;
+  const uint64_t n_tiles = (d.n_rows + TR - 1) / TR;
+  const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)c->sm_count * per_sm);
+
+  HogwildArgs a;
+  a.row_ptr = d.row_ptr;
+  a.col = d.col;
+  a.val = d.val;
+  a.target = d.target;
+  a.n_rows = d.n_rows;
+  a.n_tiles = (uint32_t)n_tiles;
+  a.tile_rows = TR;
+  a.tile_cap = (d.tile_span[tr_idx] + 3u) & ~3u;
+  a.stage_bytes = sbytes;
+  a.w0 = c->p32.w0();
+  a.w = c->p32.w();
+  a.v = c->p32.v();
+  a.gp = c->kp / 4;
+  a.use_w0 = c->k0;
+  a.use_w = c->k1;
+  a.task = c->hp.task;
+  a.lr = (float)c->hp.lr;
+  a.reg0 = (float)c->hp.reg0;
+  a.regw = (float)c->hp.regw;
+  a.regv = (float)c->hp.regv;
+  a.min_target = (float)c->hp.min_target;
+  a.max_target = (float)c->hp.max_target;
+  a.w0_accum = c->d_w0_accum;
+  a.done = c->d_done;
+  fn<<<grid, threads, smem, c->stream>>>(a);
+  c->launches++;
+  c->last_cfg = EpochConfig{G, S, TR, grid, threads, smem};
+  return cudaGetLastError();
+}
+
+}  // namespace fmb

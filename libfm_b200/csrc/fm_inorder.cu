@@ -1,0 +1,242 @@
+// fm_inorder.cu -- sequential-equivalent fp64 path (FMB200_MODE_INORDER).
+//
+// This translation unit is compiled with --fmad=false: the reference is built
+// by g++ -O3 for baseline x86-64 (no FMA contraction), and the parity gate for
+// this mode is bit-level agreement of w0/w/V with fm_learn_sgd_element::learn
+// (reference src/libfm/src/fm_learn_sgd_element.h:56-67) for regression.
+//
+// Mapping: ONE warp walks the rows strictly in file order (example t must see
+// every update of examples < t, including the bias w0 that every example
+// touches -- fm_sgd.h:34-37 -- so the epoch is one serial dependency chain and
+// no parallel schedule is sequentially equivalent).  Within a row the warp
+// parallelises across factors: lane l owns factors l, l+32, ...  All
+// floating-point sums are formed in the reference's order:
+//   result = w0 ; += w[id_i]*x_i (i ascending) ; += 0.5*(sum_f^2 - sumsq_f) (f ascending)
+//   sum_f  = ((0 + d_0) + d_1) + ...                       (fm_model.h:105-127)
+// V is attribute-major fp64 [n][k] here (lane-contiguous, coalesced), versus
+// the reference's factor-major layout; only the addressing differs.
+#include "fm_device.cuh"
+#include "fmb200_internal.h"
+
+namespace fmb {
+
+constexpr int KF_MAX = 8;  // factors per lane -> num_factor <= 256 in this mode
+
+struct RowCtx {
+  int k;
+  bool k0, k1;
+  const double* w;
+  const double* v;
+};
+
+// Exact fm_model::predict for one row, executed by a full warp.  Returns the
+// score in every lane; sum[j] holds sum_f for f = lane + 32*j.
+__device__ __forceinline__ double predict_row_exact(const RowCtx& m, double w0,
+                                                    const uint32_t* __restrict__ col,
+                                                    const float* __restrict__ val, uint32_t size,
+                                                    double (&sum)[KF_MAX], int lane) {
+  double result = 0;
+  if (lane == 0) {
+    if (m.k0) result += w0;
+    if (m.k1) {
+      for (uint32_t i = 0; i < size; i++) {
+        result += m.w[col[i]] * (double)val[i];
+      }
+    }
+  }
+  result = __shfl_sync(0xffffffffu, result, 0);
+  double term[KF_MAX];
+#pragma unroll
+  for (int j = 0; j < KF_MAX; j++) {
+    int f = lane + 32 * j;
+    double s = 0, ss = 0;
+    if (f < m.k) {
+      for (uint32_t i = 0; i < size; i++) {
+        double d = m.v[(size_t)col[i] * m.k + f] * (double)val[i];
+        s += d;
+        ss += d * d;
+      }
+    }
+    sum[j] = s;
+    term[j] = 0.5 * (s * s - ss);
+  }
+  // ordered accumulation over f = 0..k-1 (all lanes redundantly, same ops)
+#pragma unroll
+  for (int j = 0; j < KF_MAX; j++) {
+    int fbase = 32 * j;
+    if (fbase < m.k) {
+      int cnt = min(32, m.k - fbase);
+      for (int l = 0; l < cnt; l++) {
+        double t = __shfl_sync(0xffffffffu, term[j], l);
+        result += t;
+      }
+    }
+  }
+  return result;
+}
+
+__global__ void __launch_bounds__(32, 1)
+    fm_sgd_inorder_kernel(Params64 p, int n_factor, int use_w0, int use_w, HParams hp,
+                          uint64_t n_rows, const uint64_t* __restrict__ row_ptr,
+                          const uint32_t* __restrict__ col, const float* __restrict__ val,
+                          const float* __restrict__ target) {
+  const int lane = threadIdx.x;
+  RowCtx m;
+  m.k = n_factor;
+  m.k0 = use_w0 != 0;
+  m.k1 = use_w != 0;
+  m.w = p.w();
+  m.v = p.v();
+  double* w = p.w();
+  double* v = p.v();
+  double w0 = *p.w0();
+  const double lr = hp.lr, reg0 = hp.reg0, regw = hp.regw, regv = hp.regv;
+  double sum[KF_MAX];
+
+  for (uint64_t r0 = 0; r0 < n_rows; r0 += 32) {
+    // the CSR is immutable: fetch 32 rows' bounds and targets at once
+    uint64_t rr = r0 + lane;
+    uint64_t my_beg = 0, my_end = 0;
+    float my_y = 0.f;
+    if (rr < n_rows) {
+      my_beg = row_ptr[rr];
+      my_end = row_ptr[rr + 1];
+      my_y = target[rr];
+    }
+    int cnt = (int)min((uint64_t)32, n_rows - r0);
+    for (int q = 0; q < cnt; q++) {
+      uint64_t beg = __shfl_sync(0xffffffffu, my_beg, q);
+      uint64_t end = __shfl_sync(0xffffffffu, my_end, q);
+      double y = (double)__shfl_sync(0xffffffffu, my_y, q);
+      uint32_t size = (uint32_t)(end - beg);
+      const uint32_t* c = col + beg;
+      const float* x = val + beg;
+
+      double pr = predict_row_exact(m, w0, c, x, size, sum, lane);
+      // fm_learn_sgd_element.h:58-65
+      double mult = 0;
+      if (hp.task == FMB200_TASK_REGRESSION) {
+        pr = fmin(hp.max_target, pr);
+        pr = fmax(hp.min_target, pr);
+        mult = -(y - pr);
+      } else {
+        mult = -y * (1.0 - 1.0 / (1.0 + exp(-y * pr)));
+      }
+      // fm_sgd.h:34-37 (replicated in every lane, identical arithmetic)
+      if (m.k0) w0 -= lr * (mult + reg0 * w0);
+      // fm_sgd.h:38-43 (lane 0 is the only reader/writer of w)
+      if (m.k1 && lane == 0) {
+        for (uint32_t i = 0; i < size; i++) {
+          double* wi = &w[c[i]];
+          double cur = *wi;
+          cur -= lr * (mult * (double)x[i] + regw * cur);
+          *wi = cur;
+        }
+      }
+      // fm_sgd.h:44-50 (lane f%32 is the only reader/writer of V[:, f])
+#pragma unroll
+      for (int j = 0; j < KF_MAX; j++) {
+        int f = lane + 32 * j;
+        if (f < m.k) {
+          for (uint32_t i = 0; i < size; i++) {
+            double* vp = &v[(size_t)c[i] * m.k + f];
+            double xv = (double)x[i];
+            double cur = *vp;
+            double grad = sum[j] * xv - cur * xv * xv;
+            cur -= lr * (mult * grad + regv * cur);
+            *vp = cur;
+          }
+        }
+      }
+    }
+  }
+  if (lane == 0 && m.k0) *p.w0() = w0;
+}
+
+// Exact fp64 scores: one warp per row; optional metric partials per block in
+// fixed (deterministic) order: each block reduces its warps in warp order.
+__global__ void __launch_bounds__(256)
+    fm_predict64_kernel(Params64 p, int n_factor, int use_w0, int use_w, HParams hp, int transform,
+                        uint64_t n_rows, const uint64_t* __restrict__ row_ptr,
+                        const uint32_t* __restrict__ col, const float* __restrict__ val,
+                        const float* __restrict__ target, double* __restrict__ out_pred,
+                        double* __restrict__ partials) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarp = blockDim.x >> 5;
+  RowCtx m;
+  m.k = n_factor;
+  m.k0 = use_w0 != 0;
+  m.k1 = use_w != 0;
+  m.w = p.w();
+  m.v = p.v();
+  const double w0 = *p.w0();
+  double sum[KF_MAX];
+  double sq = 0, ab = 0, ok = 0;
+  // contiguous row ranges per warp keep the reduction order a pure function of
+  // (n_rows, grid, block)
+  uint64_t total_warps = (uint64_t)gridDim.x * nwarp;
+  uint64_t gw = (uint64_t)blockIdx.x * nwarp + warp;
+  uint64_t per = (n_rows + total_warps - 1) / total_warps;
+  uint64_t rbeg = gw * per, rend = min(n_rows, rbeg + per);
+  for (uint64_t r = rbeg; r < rend; r++) {
+    uint64_t beg = row_ptr[r], end = row_ptr[r + 1];
+    double pr = predict_row_exact(m, w0, col + beg, val + beg, (uint32_t)(end - beg), sum, lane);
+    double y = (double)target[r];
+    if (hp.task == FMB200_TASK_REGRESSION) {
+      // fm_learn.h:138-142
+      double pc = fmin(hp.max_target, pr);
+      pc = fmax(hp.min_target, pc);
+      double err = pc - y;
+      sq += err * err;
+      ab += fabs(err);
+      if (transform) pr = pc;
+    } else {
+      // fm_learn.h:118-120
+      if (((pr >= 0) && (y >= 0)) || ((pr < 0) && (y < 0))) ok += 1;
+      if (transform) pr = 1.0 / (1.0 + exp(-pr));  // fm_learn_sgd.h:84
+    }
+    if (out_pred != nullptr && lane == 0) out_pred[r] = pr;
+  }
+  if (partials != nullptr) {
+    __shared__ double s_part[8][3];
+    if (lane == 0) {
+      s_part[warp][0] = sq;
+      s_part[warp][1] = ab;
+      s_part[warp][2] = ok;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0, b = 0, c = 0;
+      for (int i = 0; i < nwarp; i++) {
+        a += s_part[i][0];
+        b += s_part[i][1];
+        c += s_part[i][2];
+      }
+      partials[3 * blockIdx.x + 0] = a;
+      partials[3 * blockIdx.x + 1] = b;
+      partials[3 * blockIdx.x + 2] = c;
+    }
+  }
+}
+
+cudaError_t launch_sgd_inorder(fmb200_ctx* c, const DataSlot& d) {
+  if (c->k > 32 * KF_MAX) return cudaErrorInvalidValue;
+  fm_sgd_inorder_kernel<<<1, 32, 0, c->stream>>>(c->p64, c->k, c->k0, c->k1, c->hp, d.n_rows,
+                                                 d.row_ptr, d.col, d.val, d.target);
+  c->launches++;
+  c->last_cfg = EpochConfig{32, 1, 1, 1, 32, 0};
+  return cudaGetLastError();
+}
+
+cudaError_t launch_predict64(fmb200_ctx* c, const DataSlot& d, int transform, double* out_pred,
+                             double* partials, int n_blocks) {
+  if (c->k > 32 * KF_MAX) return cudaErrorInvalidValue;
+  fm_predict64_kernel<<<n_blocks, 256, 0, c->stream>>>(c->p64, c->k, c->k0, c->k1, c->hp, transform,
+                                                       d.n_rows, d.row_ptr, d.col, d.val, d.target,
+                                                       out_pred, partials);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+}  // namespace fmb

@@ -1,0 +1,232 @@
+// fm_predict.cu -- fp32 scoring / metric pass and small state kernels.
+//
+// fm_predict32_kernel replaces fm_learn::evaluate_regression / _classification
+// (reference src/libfm/src/fm_learn.h:113-153) and fm_learn_sgd::predict
+// (fm_learn_sgd.h:76-90) for the fp32 (HOGWILD) state: the same RowGroup score
+// as the training kernel, metric sums accumulated in fp64 per block, per-block
+// partials written in a fixed order (the host adds them in block order, so the
+// result is a deterministic function of the launch geometry).
+#include <algorithm>
+
+#include "fm_rowgroup.cuh"
+#include "fmb200_internal.h"
+
+namespace fmb {
+
+struct PredictArgs {
+  const uint64_t* row_ptr;
+  const uint32_t* col;
+  const float* val;
+  const float* target;
+  uint64_t n_rows;
+  const float* w0;
+  const float* w;
+  const float* v;
+  int gp, use_w0, use_w, task, transform;
+  float min_target, max_target;
+  double* out_pred;
+  double* partials;
+};
+
+template <int G, int S>
+__global__ void __launch_bounds__(256) fm_predict32_kernel(const PredictArgs a) {
+  using RG = RowGroup<G, S, 1>;
+  constexpr int E = RG::E;
+  constexpr int RPW = 32 / E;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarp = blockDim.x >> 5;
+  const int lig = lane % E, c = lig % G, s = lig / G, sub = lane / E;
+  const float4* V4 = reinterpret_cast<const float4*>(a.v);
+  const float w0 = a.use_w0 ? *a.w0 : 0.f;
+  double sq = 0, ab = 0, ok = 0;
+
+  // contiguous chunk of rows per block, walked RPW rows per warp at a time
+  const uint64_t per_block = (a.n_rows + gridDim.x - 1) / gridDim.x;
+  const uint64_t b0 = (uint64_t)blockIdx.x * per_block;
+  const uint64_t b1 = min(a.n_rows, b0 + per_block);
+  for (uint64_t rbase = b0 + (uint64_t)warp * RPW; rbase < b1; rbase += (uint64_t)nwarp * RPW) {
+    const uint64_t r = rbase + sub;
+    const bool valid = r < b1;
+    uint64_t beg = 0, end = 0;
+    float y = 0.f;
+    if (valid) {
+      beg = __ldg(a.row_ptr + r);
+      end = __ldg(a.row_ptr + r + 1);
+      y = __ldg(a.target + r);
+    }
+    RG g;
+    const float part = g.score(V4, a.w, a.gp, a.use_w != 0, a.col + beg, a.val + beg, 0,
+                               (int)(end - beg), c, s);
+    float p = w0 + part;
+    if (valid && lig == 0) {
+      if (a.task == FMB200_TASK_REGRESSION) {
+        const float pc = fmaxf(a.min_target, fminf(a.max_target, p));
+        const double err = (double)pc - (double)y;
+        sq += err * err;
+        ab += fabs(err);
+        if (a.transform) p = pc;
+      } else {
+        if (((p >= 0.f) && (y >= 0.f)) || ((p < 0.f) && (y < 0.f))) ok += 1;
+        if (a.transform) p = 1.f / (1.f + expf(-p));
+      }
+      if (a.out_pred != nullptr) a.out_pred[r] = (double)p;
+    }
+  }
+  if (a.partials != nullptr) {
+    sq = warp_sum_d(sq);
+    ab = warp_sum_d(ab);
+    ok = warp_sum_d(ok);
+    __shared__ double s_part[8][3];
+    if (lane == 0) {
+      s_part[warp][0] = sq;
+      s_part[warp][1] = ab;
+      s_part[warp][2] = ok;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double x0 = 0, x1 = 0, x2 = 0;
+      for (int i = 0; i < nwarp; i++) {
+        x0 += s_part[i][0];
+        x1 += s_part[i][1];
+        x2 += s_part[i][2];
+      }
+      a.partials[3 * blockIdx.x + 0] = x0;
+      a.partials[3 * blockIdx.x + 1] = x1;
+      a.partials[3 * blockIdx.x + 2] = x2;
+    }
+  }
+}
+
+using PredictFn = void (*)(const PredictArgs);
+
+template <int G>
+static PredictFn pick_predict_s(int S) {
+  if constexpr (G <= 4) {
+    if (S >= 8) return fm_predict32_kernel<G, 8>;
+  }
+  if constexpr (G <= 8) {
+    if (S >= 4) return fm_predict32_kernel<G, 4>;
+  }
+  if constexpr (G <= 16) {
+    if (S >= 2) return fm_predict32_kernel<G, 2>;
+  }
+  return fm_predict32_kernel<G, 1>;
+}
+
+cudaError_t launch_predict32(fmb200_ctx* c, const DataSlot& d, int transform, double* out_pred,
+                             double* partials, int n_blocks) {
+  if (c->kp / 4 > 32) return cudaErrorInvalidValue;
+  int G, S;
+  pick_geometry(c->kp, d.n_rows, d.nnz, &G, &S);
+  PredictFn fn;
+  switch (G) {
+    case 1: fn = pick_predict_s<1>(S); break;
+    case 2: fn = pick_predict_s<2>(S); break;
+    case 4: fn = pick_predict_s<4>(S); break;
+    case 8: fn = pick_predict_s<8>(S); break;
+    case 16: fn = pick_predict_s<16>(S); break;
+    default: fn = pick_predict_s<32>(S); break;
+  }
+  PredictArgs a;
+  a.row_ptr = d.row_ptr;
+  a.col = d.col;
+  a.val = d.val;
+  a.target = d.target;
+  a.n_rows = d.n_rows;
+  a.w0 = c->p32.w0();
+  a.w = c->p32.w();
+  a.v = c->p32.v();
+  a.gp = c->kp / 4;
+  a.use_w0 = c->k0;
+  a.use_w = c->k1;
+  a.task = c->hp.task;
+  a.transform = transform;
+  a.min_target = (float)c->hp.min_target;
+  a.max_target = (float)c->hp.max_target;
+  a.out_pred = out_pred;
+  a.partials = partials;
+  fn<<<n_blocks, 256, 0, c->stream>>>(a);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+// ---- state conversion --------------------------------------------------------
+__global__ void p64_to_p32_kernel(Params64 s, Params32 d, uint32_t n, int k, int kp) {
+  const uint64_t total = (uint64_t)n * kp;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t row = i / kp;
+    const int f = (int)(i % kp);
+    d.v()[i] = f < k ? (float)s.v()[row * k + f] : 0.f;
+  }
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    d.w()[i] = (float)s.w()[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) d.w0()[0] = (float)s.w0()[0];
+}
+
+__global__ void p32_to_p64_kernel(Params32 s, Params64 d, uint32_t n, int k, int kp) {
+  const uint64_t total = (uint64_t)n * k;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t row = i / k;
+    const int f = (int)(i % k);
+    d.v()[i] = (double)s.v()[row * kp + f];
+  }
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    d.w()[i] = (double)s.w()[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) d.w0()[0] = (double)s.w0()[0];
+}
+
+__global__ void scale_kernel(float* p, uint64_t n, float f) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    p[i] *= f;
+}
+
+__global__ void max_col_kernel(const uint32_t* __restrict__ col, uint64_t nnz,
+                               unsigned int* out_max) {
+  unsigned int m = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nnz;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    m = max(m, col[i]);
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0) atomicMax(out_max, m);
+}
+
+static int grid_for(fmb200_ctx* c, uint64_t work) {
+  uint64_t blocks = (work + 255) / 256;
+  return (int)std::max<uint64_t>(1, std::min<uint64_t>(blocks, (uint64_t)c->sm_count * 8));
+}
+
+cudaError_t launch_p64_to_p32(fmb200_ctx* c) {
+  p64_to_p32_kernel<<<grid_for(c, (uint64_t)c->n * (c->kp + 1)), 256, 0, c->stream>>>(c->p64, c->p32,
+                                                                               c->n, c->k, c->kp);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_p32_to_p64(fmb200_ctx* c) {
+  p32_to_p64_kernel<<<grid_for(c, (uint64_t)c->n * (c->k + 1)), 256, 0, c->stream>>>(c->p32, c->p64,
+                                                                              c->n, c->k, c->kp);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scale_p32(fmb200_ctx* c, float factor) {
+  scale_kernel<<<grid_for(c, c->p32.n_floats), 256, 0, c->stream>>>(c->p32.base, c->p32.n_floats,
+                                                                   factor);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_max_col(fmb200_ctx* c, const uint32_t* col, uint64_t nnz,
+                           unsigned int* out_max) {
+  max_col_kernel<<<grid_for(c, nnz), 256, 0, c->stream>>>(col, nnz, out_max);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+}  // namespace fmb

@@ -1,0 +1,110 @@
+// fmb200_internal.h -- context layout and kernel launch entry points shared by
+// the translation units of libfmb200.so.  Not part of the public ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fmb200.h"
+
+namespace fmb {
+
+// One uploaded data set, SoA CSR in HBM.  Arrays are over-allocated so that
+// 16-byte-granular TMA bulk copies may read past the logical end.
+struct DataSlot {
+  bool present = false;
+  uint64_t n_rows = 0;
+  uint64_t nnz = 0;
+  uint64_t* row_ptr = nullptr;  // [n_rows + 1] (+ padding)
+  uint32_t* col = nullptr;      // [nnz] (+ padding)
+  float* val = nullptr;         // [nnz] (+ padding)
+  float* target = nullptr;      // [n_rows] (+ padding)
+  uint32_t max_row_nnz = 0;
+  // worst-case 4-element-aligned nnz span of any tile of 2^(5+i) rows
+  // (i = 0..4 -> 32, 64, 128, 256, 512 rows); sizes the smem staging buffers
+  uint32_t tile_span[5] = {0, 0, 0, 0, 0};
+};
+
+// Packed fp32 state: [w0, 0, 0, 0 | w[n] padded to a multiple of 4 | V[n][kp]]
+struct Params32 {
+  float* base = nullptr;
+  uint64_t n_floats = 0;
+  uint64_t off_w = 4;
+  uint64_t off_v = 0;
+  __host__ __device__ float* w0() const { return base; }
+  __host__ __device__ float* w() const { return base + off_w; }
+  __host__ __device__ float* v() const { return base + off_v; }
+};
+
+// fp64 state: [w0 | w[n] | V[n][k]] attribute-major, unpadded
+struct Params64 {
+  double* base = nullptr;
+  uint64_t n_doubles = 0;
+  uint64_t off_v = 0;
+  __host__ __device__ double* w0() const { return base; }
+  __host__ __device__ double* w() const { return base + 1; }
+  __host__ __device__ double* v() const { return base + off_v; }
+};
+
+struct HParams {
+  int task = 0;
+  double lr = 0, reg0 = 0, regw = 0, regv = 0;
+  double min_target = 0, max_target = 0;
+};
+
+struct EpochConfig {
+  int lanes_per_row = 0, slots = 0, rows_per_tile = 0, grid = 0, block = 0, smem = 0;
+};
+
+}  // namespace fmb
+
+struct fmb200_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  uint32_t n = 0;
+  int k = 0, kp = 0;
+  bool k0 = true, k1 = true;
+  int mode = FMB200_MODE_HOGWILD;
+  fmb::HParams hp;
+  fmb::Params32 p32;
+  fmb::Params64 p64;
+  fmb::DataSlot slots[FMB200_MAX_SLOTS];
+  // scratch
+  double* d_partials = nullptr;  // evaluate: per-block partial sums
+  int n_partials = 0;
+  double* d_pred = nullptr;  // predict output staging
+  uint64_t pred_cap = 0;
+  float* d_w0_accum = nullptr;       // hogwild: row-weighted sum of CTA-local biases
+  unsigned int* d_done = nullptr;    // hogwild: CTAs finished
+  unsigned int* d_flag = nullptr;    // generic device flag (column range check)
+  uint64_t launches = 0;
+  fmb::EpochConfig last_cfg;
+  int tune_ctas_per_sm = 0, tune_rows_per_tile = 0, tune_threads = 0;
+};
+
+namespace fmb {
+
+// fm_inorder.cu: sequential-equivalent fp64 epoch (one warp, rows in order)
+cudaError_t launch_sgd_inorder(fmb200_ctx* c, const DataSlot& d);
+// fm_inorder.cu: exact fp64 scores, one warp per row.  out_pred may be null;
+// partials (3 doubles per block: sq, abs, correct) may be null.
+cudaError_t launch_predict64(fmb200_ctx* c, const DataSlot& d, int transform, double* out_pred,
+                             double* partials, int n_blocks);
+// fm_hogwild.cu: throughput epoch
+cudaError_t launch_sgd_hogwild(fmb200_ctx* c, const DataSlot& d);
+// fm_predict.cu: fp32 scores / metrics with sub-warp row groups
+cudaError_t launch_predict32(fmb200_ctx* c, const DataSlot& d, int transform, double* out_pred,
+                             double* partials, int n_blocks);
+// fm_predict.cu: state conversion and scaling
+cudaError_t launch_p64_to_p32(fmb200_ctx* c);
+cudaError_t launch_p32_to_p64(fmb200_ctx* c);
+cudaError_t launch_scale_p32(fmb200_ctx* c, float factor);
+cudaError_t launch_max_col(fmb200_ctx* c, const uint32_t* col, uint64_t nnz, unsigned int* out_max);
+
+// pick the sub-warp geometry for a data set: G lanes per V row (power of two
+// covering kp/4 float4 chunks), S entry slots per row group
+void pick_geometry(int kp, uint64_t n_rows, uint64_t nnz, int* G, int* S);
+
+}  // namespace fmb
