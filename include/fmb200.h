@@ -103,10 +103,12 @@ int fmb200_stream(fmb200_ctx* ctx, void** cuda_stream);
 /* Introspection for tests / bench */
 int fmb200_kernel_launches(fmb200_ctx* ctx, uint64_t* count); /* kernels launched so far */
 int fmb200_last_epoch_config(fmb200_ctx* ctx, int* lanes_per_row, int* slots, int* rows_per_tile,
-                             int* grid, int* block, int* smem_bytes);
+                             int* grid, int* block, int* smem_bytes, int* damp);
 /* hogwild tuning knobs; 0 keeps the default.  ctas_per_sm bounds the number of
- * rows in flight (the Hogwild staleness window). */
-int fmb200_set_tuning(fmb200_ctx* ctx, int ctas_per_sm, int rows_per_tile, int threads);
+ * rows in flight (the Hogwild staleness window).  damp: 0 = automatic hot-feature
+ * damping (on when the hottest feature's expected concurrency matters), 1 = force
+ * on, -1 = force off (plain summed Hogwild on w/V). */
+int fmb200_set_tuning(fmb200_ctx* ctx, int ctas_per_sm, int rows_per_tile, int threads, int damp);
 
 #ifdef __cplusplus
 }

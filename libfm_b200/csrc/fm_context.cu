@@ -45,6 +45,7 @@ void free_slot(DataSlot& s) {
   if (s.col) cudaFree(s.col);
   if (s.val) cudaFree(s.val);
   if (s.target) cudaFree(s.target);
+  if (s.feat_cnt) cudaFree(s.feat_cnt);
   s = DataSlot();
 }
 
@@ -106,7 +107,16 @@ int upload_common(fmb200_ctx* c, int slot, uint64_t n_rows, uint64_t nnz, const 
       free_slot(s);
       return fail("feature id %u out of range (num_attribute=%u)", mx, c->n);
     }
+    // per-feature occurrence counts (hot-feature damping of the HOGWILD epoch)
+    CK(cudaMalloc(&s.feat_cnt, sizeof(float) * (size_t)(c->n ? c->n : 1)));
+    CK(cudaMemsetAsync(c->d_flag, 0, sizeof(unsigned int), c->stream));
+    CK(launch_feature_counts(c, s.col, nnz, s.feat_cnt, c->d_flag));
+    CK(cudaMemcpyAsync(&mx, c->d_flag, sizeof(mx), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    s.max_feat_cnt = mx;
   } else {
+    CK(cudaMalloc(&s.feat_cnt, sizeof(float) * (size_t)(c->n ? c->n : 1)));
+    CK(cudaMemsetAsync(s.feat_cnt, 0, sizeof(float) * (size_t)(c->n ? c->n : 1), c->stream));
     CK(cudaStreamSynchronize(c->stream));
   }
   s.present = true;
@@ -471,7 +481,7 @@ int fmb200_kernel_launches(fmb200_ctx* c, uint64_t* count) {
 }
 
 int fmb200_last_epoch_config(fmb200_ctx* c, int* lanes_per_row, int* slots, int* rows_per_tile,
-                             int* grid, int* block, int* smem_bytes) {
+                             int* grid, int* block, int* smem_bytes, int* damp) {
   NEED_CTX(c);
   if (lanes_per_row) *lanes_per_row = c->last_cfg.lanes_per_row;
   if (slots) *slots = c->last_cfg.slots;
@@ -479,10 +489,11 @@ int fmb200_last_epoch_config(fmb200_ctx* c, int* lanes_per_row, int* slots, int*
   if (grid) *grid = c->last_cfg.grid;
   if (block) *block = c->last_cfg.block;
   if (smem_bytes) *smem_bytes = c->last_cfg.smem;
+  if (damp) *damp = c->last_cfg.damp;
   return 0;
 }
 
-int fmb200_set_tuning(fmb200_ctx* c, int ctas_per_sm, int rows_per_tile, int threads) {
+int fmb200_set_tuning(fmb200_ctx* c, int ctas_per_sm, int rows_per_tile, int threads, int damp) {
   NEED_CTX(c);
   if (threads && (threads % 32 != 0 || threads < 32 || threads > 256))
     return fail("threads must be a multiple of 32 in [32,256]");
@@ -491,6 +502,7 @@ int fmb200_set_tuning(fmb200_ctx* c, int ctas_per_sm, int rows_per_tile, int thr
   c->tune_ctas_per_sm = ctas_per_sm;
   c->tune_rows_per_tile = rows_per_tile;
   c->tune_threads = threads;
+  c->tune_damp = damp;
   return 0;
 }
 

@@ -18,15 +18,24 @@
 //    are mutated by other SMs through L2, so L1 must not serve them), per-factor
 //    sums by segmented warp shuffles, write-back as fire-and-forget
 //    red.global.add.v4.f32 / red.global.add.f32 (Hogwild: no locks, no CAS).
-//  * bias w0: every example touches it (fm_sgd.h:34-37), so naive Hogwild
-//    (sum of B stale gradients) has gain lr*B and diverges for B >> 1/lr.  Each
-//    CTA therefore carries a LOCAL bias through its own tile sequence and applies,
-//    per tile of T rows, the closed-form solution of the reference's sequential
-//    recurrence w0 <- w0 - lr*(mult_t + reg0*w0) under a frozen-residual /
-//    mean-curvature linearisation:  dw0 = gamma * (-lr) * sum_t(mult_t + reg0*w0),
-//    gamma = (1 - a^T) / (T (1 - a)),  a = 1 - lr (h + reg0),  h = mean d mult/d w0
-//    (gamma == 1 for T == 1, i.e. exactly the reference's step).  At the end of the
-//    epoch the row-weighted mean of the CTA-local biases becomes the global w0.
+//  * concurrency control.  The reference is strictly sequential; Hogwild sums the
+//    steps of all examples that are in flight together.  For a parameter block
+//    shared by c concurrent examples that sum has gain c*lr*h (h = curvature of
+//    the loss w.r.t. the block) and diverges once it exceeds 2 -- immediately for
+//    the bias w0 (every example touches it, fm_sgd.h:34-37) and for popular
+//    features of skewed data.  Both are handled by the closed form of the
+//    reference's own sequential recurrence under a mean-field linearisation:
+//    c sequential steps contract the residual by a = 1 - lr*h each, so the c
+//    concurrent steps are each scaled by  sat(q) = (1 - e^-q)/q,  q = c*lr*h
+//    (sat -> 1 for q -> 0: cold features and c = 1 take exactly the reference step).
+//      - w0: carried PER WARP in a register through the warp's own row sequence
+//        (T = rows of one pass, q = T*lr*(mean curvature + reg0)); the
+//        row-weighted mean of all warp-local biases becomes w0 at the end of the
+//        epoch.  No atomics on w0, no block barrier for it.
+//      - w_i, V_i (template flag DAMP, on when some feature is hot enough to
+//        matter): c_i = count_i * W / N from a per-feature occurrence table built
+//        at upload (W = rows in flight), h_w = x^2 + regw,
+//        h_V = x^2 * sum_f (s_f - v_if x)^2 + regv.
 //
 // Algorithmic HBM traffic per example (roofline numerator, BASELINE.json):
 // 2*k*nnz*4 bytes (V rows read + written back).
@@ -39,7 +48,7 @@ namespace fmb {
 
 constexpr int HW_NSTAGE = 3;
 constexpr int HW_MAX_THREADS = 256;
-constexpr int HW_HDR_BYTES = 128;  // mbarriers + per-tile bias accumulators
+constexpr int HW_HDR_BYTES = 128;  // mbarriers
 
 struct HogwildArgs {
   const uint64_t* row_ptr;
@@ -59,6 +68,8 @@ struct HogwildArgs {
   float lr, reg0, regw, regv, min_target, max_target;
   float* w0_accum;
   unsigned int* done;
+  const float* feat_cnt;  // occurrences of each feature in this data set (DAMP)
+  float conc_scale;       // rows in flight / n_rows: count -> expected concurrency
 };
 
 __device__ __forceinline__ unsigned char* stage_base(unsigned char* smem, const HogwildArgs& a,
@@ -92,7 +103,12 @@ __device__ __forceinline__ void issue_tile(const HogwildArgs& a, unsigned char* 
   }
 }
 
-template <int G, int S, int R>
+// sat(q) = (1 - e^-q)/q : the mean-field step scale for q = c*lr*h
+__device__ __forceinline__ float sat_scale(float q) {
+  return q < 1e-3f ? 1.f - 0.5f * q : (1.f - __expf(-q)) / q;
+}
+
+template <int G, int S, int R, bool DAMP>
 __global__ void __launch_bounds__(HW_MAX_THREADS, (R <= 2 ? 4 : 2))
     fm_sgd_hogwild_kernel(const HogwildArgs a) {
   using RG = RowGroup<G, S, R>;
@@ -100,7 +116,6 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R <= 2 ? 4 : 2))
   constexpr int RPW = 32 / E;  // rows per warp per pass
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  float* s_acc = reinterpret_cast<float*>(smem + 64);  // [3][2]: sum mult, sum curvature
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -116,7 +131,6 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R <= 2 ? 4 : 2))
   uint64_t policy = 0;
   if (tid == 0) {
     for (int i = 0; i < HW_NSTAGE; i++) mbar_init(bars + i, 1);
-    for (int i = 0; i < 6; i++) s_acc[i] = 0.f;
     fence_mbar_init();
     policy = policy_evict_first();
   }
@@ -131,9 +145,11 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R <= 2 ? 4 : 2))
   const float4* V4 = reinterpret_cast<const float4*>(a.v);
   const bool use_w = a.use_w != 0;
   const bool use_w0 = a.use_w0 != 0;
-  float w0 = use_w0 ? ld_cg_f(a.w0) : 0.f;
+  float w0 = use_w0 ? ld_cg_f(a.w0) : 0.f;  // warp-local bias (replicated in the lanes)
   const float lr = a.lr;
-  uint64_t my_rows = 0;
+  const float nlr_regv = -lr * a.regv;
+  const float nlr_regw = -lr * a.regw;
+  float my_rows = 0.f;
 
   int it = 0;
   for (uint64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
@@ -150,7 +166,6 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R <= 2 ? 4 : 2))
     const int rows_here = (int)min((uint64_t)TR, a.n_rows - row0);
     const uint64_t ab = rp[0] & ~3ull;
 
-    float msum = 0.f, hsum = 0.f;
     for (int rbase = warp * RPW; rbase < rows_here; rbase += rows_per_pass) {
       const int r = rbase + sub;
       const bool valid = r < rows_here;
@@ -163,7 +178,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R <= 2 ? 4 : 2))
       }
       RG g;
       const float part = g.score(V4, a.w, a.gp, use_w, ids, xs, beg, end, c, s);
-      float p = w0 + part;
+      const float p = w0 + part;
       float mult, curv;
       if (a.task == FMB200_TASK_REGRESSION) {
         // fm_learn_sgd_element.h:59-62
@@ -176,98 +191,102 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R <= 2 ? 4 : 2))
         mult = -y * (1.f - sg);
         curv = sg * (1.f - sg);
       }
-      if (valid && lig == 0) {
-        msum += mult;
-        hsum += curv;
+
+      // ---- bias: warp-local closed-form step over this pass's rows ----
+      if (use_w0) {
+        float ms = (valid && lig == 0) ? mult : 0.f;
+        float hs = (valid && lig == 0) ? curv : 0.f;
+        float ts = (valid && lig == 0) ? 1.f : 0.f;
+        // sum over the warp's group leaders (xor strides that are multiples of E
+        // keep lig fixed), then broadcast lane 0's total
+#pragma unroll
+        for (int o = E; o < 32; o <<= 1) {
+          ms += __shfl_xor_sync(0xffffffffu, ms, o);
+          hs += __shfl_xor_sync(0xffffffffu, hs, o);
+          ts += __shfl_xor_sync(0xffffffffu, ts, o);
+        }
+        ms = __shfl_sync(0xffffffffu, ms, 0);
+        hs = __shfl_sync(0xffffffffu, hs, 0);
+        ts = __shfl_sync(0xffffffffu, ts, 0);
+        if (ts > 0.f) {
+          const float q = lr * (hs + ts * a.reg0);  // T * lr * (mean curvature + reg0)
+          w0 -= sat_scale(q) * lr * (ms + ts * a.reg0 * w0);
+          my_rows += ts;
+        }
       }
+
       // ---- fm_SGD write-back (fm_sgd.h:38-50) as L2 reductions ----
       const float nlr_mult = -lr * mult;
-      const float nlr_regv = -lr * a.regv;
-      const float nlr_regw = -lr * a.regw;
+      auto update = [&](bool on, uint32_t id, float x, const float4& v, float wv) {
+        const float x2 = x * x;
+        const float gx = g.acc.x * x - v.x * x2, gy = g.acc.y * x - v.y * x2;
+        const float gz = g.acc.z * x - v.z * x2, gw = g.acc.w * x - v.w * x2;
+        float sv = 1.f, sw = 1.f;
+        if (DAMP) {
+          const float conc = __ldg(a.feat_cnt + id) * a.conc_scale;  // expected concurrency
+          float n2 = gx * gx + gy * gy + gz * gz + gw * gw;           // |d p / d V_i|^2
+#pragma unroll
+          for (int o = 1; o < G; o <<= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+          sv = sat_scale(conc * lr * (n2 + a.regv));
+          sw = sat_scale(conc * lr * (x2 + a.regw));
+        }
+        if (on && c < a.gp) {
+          // -lr*(mult*(sum_f*x - v*x^2) + regv*v)
+          red_add_f4(a.v + ((size_t)id * a.gp + c) * 4, sv * (nlr_mult * gx + nlr_regv * v.x),
+                     sv * (nlr_mult * gy + nlr_regv * v.y), sv * (nlr_mult * gz + nlr_regv * v.z),
+                     sv * (nlr_mult * gw + nlr_regv * v.w));
+        }
+        if (on && use_w && c == 0) red_add_f(a.w + id, sw * (nlr_mult * x + nlr_regw * wv));
+      };
 #pragma unroll
       for (int q = 0; q < R; ++q) {
         const int j = beg + s + q * S;
-        if (j < end) {
-          const float x = g.xc[q];
-          const uint32_t id = g.idc[q];
-          if (c < a.gp) {
-            const float4 v = g.vc[q];
-            const float x2 = x * x;
-            // -lr*(mult*(sum_f*x - v*x^2) + regv*v)
-            red_add_f4(a.v + ((size_t)id * a.gp + c) * 4,
-                       nlr_mult * (g.acc.x * x - v.x * x2) + nlr_regv * v.x,
-                       nlr_mult * (g.acc.y * x - v.y * x2) + nlr_regv * v.y,
-                       nlr_mult * (g.acc.z * x - v.z * x2) + nlr_regv * v.z,
-                       nlr_mult * (g.acc.w * x - v.w * x2) + nlr_regv * v.w);
-          }
-          if (use_w && c == 0) red_add_f(a.w + id, nlr_mult * x + nlr_regw * g.wc[q]);
+        const bool on = j < end;
+        if (DAMP) {
+          // the norm reduction shuffles across the G chunk lanes: keep them converged
+          if (__any_sync(0xffffffffu, on)) update(on, g.idc[q], g.xc[q], g.vc[q], g.wc[q]);
+        } else if (on) {
+          update(true, g.idc[q], g.xc[q], g.vc[q], g.wc[q]);
         }
       }
       for (int q = R; q < g.maxit; ++q) {
         const int j = beg + s + q * S;
-        if (j < end) {
-          const float x = xs[j];
-          const uint32_t id = ids[j];
-          if (c < a.gp) {
-            const float4 v = ld_cg_f4(V4 + (size_t)id * a.gp + c);
-            const float x2 = x * x;
-            red_add_f4(a.v + ((size_t)id * a.gp + c) * 4,
-                       nlr_mult * (g.acc.x * x - v.x * x2) + nlr_regv * v.x,
-                       nlr_mult * (g.acc.y * x - v.y * x2) + nlr_regv * v.y,
-                       nlr_mult * (g.acc.z * x - v.z * x2) + nlr_regv * v.z,
-                       nlr_mult * (g.acc.w * x - v.w * x2) + nlr_regv * v.w);
-          }
-          if (use_w && c == 0) {
-            const float wv = ld_cg_f(a.w + id);
-            red_add_f(a.w + id, nlr_mult * x + nlr_regw * wv);
-          }
+        const bool on = j < end;
+        uint32_t id = 0;
+        float x = 0.f, wv = 0.f;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on) {
+          x = xs[j];
+          id = ids[j];
+          if (c < a.gp) v = ld_cg_f4(V4 + (size_t)id * a.gp + c);
+          if (use_w && c == 0) wv = ld_cg_f(a.w + id);
         }
+        if (DAMP || on) update(on, id, x, v, wv);
       }
     }
 
-    // ---- per-tile bias step (CTA-local carry) ----
-    const int slot = it % 3;
-    if (use_w0) {
-      msum = warp_sum(msum);
-      hsum = warp_sum(hsum);
-      if (lane == 0) {
-        atomicAdd(&s_acc[2 * slot + 0], msum);
-        atomicAdd(&s_acc[2 * slot + 1], hsum);
-      }
-    }
-    __syncthreads();  // tile consumed: stage is free, accumulators complete
+    __syncthreads();  // every warp is done with this stage: refill it
     if (tid == 0) {
       const uint64_t nt = tile + (uint64_t)HW_NSTAGE * gridDim.x;
       if (nt < a.n_tiles) issue_tile(a, smem, bars, (uint32_t)nt, stage, policy);
-      const int zs = (it + 2) % 3;  // last read before the previous barrier
-      s_acc[2 * zs + 0] = 0.f;
-      s_acc[2 * zs + 1] = 0.f;
     }
-    if (use_w0) {
-      const float T = (float)rows_here;
-      const float M = s_acc[2 * slot + 0];
-      const float H = s_acc[2 * slot + 1];
-      const float q = lr * (H / T + a.reg0);  // 1 - a
-      float gamma = 1.f;
-      if (q * T > 1e-3f) {
-        const float aa = fmaxf(1.f - q, 0.f);
-        gamma = (1.f - __powf(aa, T)) / (T * q);
-      }
-      w0 += gamma * (-lr) * (M + T * a.reg0 * w0);
-    }
-    my_rows += rows_here;
   }
 
-  // ---- merge the CTA-local biases: row-weighted mean ----
-  if (use_w0 && tid == 0) {
-    if (my_rows > 0) atomicAdd(a.w0_accum, w0 * (float)((double)my_rows / (double)a.n_rows));
-    __threadfence();
-    const unsigned int ticket = atomicAdd(a.done, 1u);
-    if (ticket == gridDim.x - 1) {
+  // ---- merge the warp-local biases: row-weighted mean over all warps ----
+  if (use_w0 && lane == 0) {
+    if (my_rows > 0.f) atomicAdd(a.w0_accum, w0 * (my_rows / (float)a.n_rows));
+  }
+  if (use_w0) {
+    __syncthreads();
+    if (tid == 0) {
       __threadfence();
-      const float merged = atomicExch(a.w0_accum, 0.f);
-      *a.w0 = merged;
-      *a.done = 0u;
+      const unsigned int ticket = atomicAdd(a.done, 1u);
+      if (ticket == gridDim.x - 1) {
+        __threadfence();
+        const float merged = atomicExch(a.w0_accum, 0.f);
+        *a.w0 = merged;
+        *a.done = 0u;
+      }
     }
   }
 }
@@ -276,36 +295,43 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R <= 2 ? 4 : 2))
 using KernelFn = void (*)(const HogwildArgs);
 
 template <int G, int S>
-KernelFn pick_r(int R) {
+KernelFn pick_r(int R, bool damp) {
+  if (damp) {
+    switch (R) {
+      case 1: return fm_sgd_hogwild_kernel<G, S, 1, true>;
+      case 2: return fm_sgd_hogwild_kernel<G, S, 2, true>;
+      default: return fm_sgd_hogwild_kernel<G, S, 8, true>;
+    }
+  }
   switch (R) {
-    case 1: return fm_sgd_hogwild_kernel<G, S, 1>;
-    case 2: return fm_sgd_hogwild_kernel<G, S, 2>;
-    default: return fm_sgd_hogwild_kernel<G, S, 8>;
+    case 1: return fm_sgd_hogwild_kernel<G, S, 1, false>;
+    case 2: return fm_sgd_hogwild_kernel<G, S, 2, false>;
+    default: return fm_sgd_hogwild_kernel<G, S, 8, false>;
   }
 }
 
 template <int G>
-KernelFn pick_s(int S, int R) {
+KernelFn pick_s(int S, int R, bool damp) {
   if constexpr (G <= 4) {
-    if (S >= 8) return pick_r<G, 8>(R);
+    if (S >= 8) return pick_r<G, 8>(R, damp);
   }
   if constexpr (G <= 8) {
-    if (S >= 4) return pick_r<G, 4>(R);
+    if (S >= 4) return pick_r<G, 4>(R, damp);
   }
   if constexpr (G <= 16) {
-    if (S >= 2) return pick_r<G, 2>(R);
+    if (S >= 2) return pick_r<G, 2>(R, damp);
   }
-  return pick_r<G, 1>(R);
+  return pick_r<G, 1>(R, damp);
 }
 
-static KernelFn pick_kernel(int G, int S, int R) {
+static KernelFn pick_kernel(int G, int S, int R, bool damp) {
   switch (G) {
-    case 1: return pick_s<1>(S, R);
-    case 2: return pick_s<2>(S, R);
-    case 4: return pick_s<4>(S, R);
-    case 8: return pick_s<8>(S, R);
-    case 16: return pick_s<16>(S, R);
-    default: return pick_s<32>(S, R);
+    case 1: return pick_s<1>(S, R, damp);
+    case 2: return pick_s<2>(S, R, damp);
+    case 4: return pick_s<4>(S, R, damp);
+    case 8: return pick_s<8>(S, R, damp);
+    case 16: return pick_s<16>(S, R, damp);
+    default: return pick_s<32>(S, R, damp);
   }
 }
 
@@ -352,7 +378,14 @@ cudaError_t launch_sgd_hogwild(fmb200_ctx* c, const DataSlot& d) {
   const int smem = HW_HDR_BYTES + HW_NSTAGE * (int)sbytes;
   if (smem > c->max_smem_optin) return cudaErrorInvalidConfiguration;  // one row longer than smem
 
-  KernelFn fn = pick_kernel(G, S, R);
+  // hot-feature damping is compiled in only when the hottest feature's expected
+  // concurrency makes q = c*lr*(1+reg) non-negligible for this launch geometry
+  const double rows_in_flight_guess =
+      std::min<double>((double)d.n_rows, (double)c->sm_count * 4 * (threads / 32) * (32.0 / (G * S)));
+  const double q_max = (double)d.max_feat_cnt * rows_in_flight_guess / (double)d.n_rows * c->hp.lr *
+                       (1.0 + std::max(c->hp.regw, c->hp.regv));
+  const bool damp = c->tune_damp == 1 || (c->tune_damp == 0 && q_max > 0.25);
+  KernelFn fn = pick_kernel(G, S, R, damp);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -388,9 +421,14 @@ cudaError_t launch_sgd_hogwild(fmb200_ctx* c, const DataSlot& d) {
   a.max_target = (float)c->hp.max_target;
   a.w0_accum = c->d_w0_accum;
   a.done = c->d_done;
+  a.feat_cnt = d.feat_cnt;
+  {
+    const double in_flight = std::min<double>((double)d.n_rows, (double)grid * (threads / 32) * (32.0 / (G * S)));
+    a.conc_scale = (float)(in_flight / (double)d.n_rows);
+  }
   fn<<<grid, threads, smem, c->stream>>>(a);
   c->launches++;
-  c->last_cfg = EpochConfig{G, S, TR, grid, threads, smem};
+  c->last_cfg = EpochConfig{G, S, TR, grid, threads, smem, damp ? 1 : 0};
   return cudaGetLastError();
 }
 

@@ -196,6 +196,25 @@ __global__ void max_col_kernel(const uint32_t* __restrict__ col, uint64_t nnz,
   if ((threadIdx.x & 31) == 0) atomicMax(out_max, m);
 }
 
+__global__ void hist_kernel(const uint32_t* __restrict__ col, uint64_t nnz, unsigned int* cnt) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nnz;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    atomicAdd(cnt + col[i], 1u);
+}
+
+// in place: uint32 counts -> float counts, and the maximum
+__global__ void cnt_to_float_kernel(unsigned int* cnt, uint32_t n, unsigned int* out_max) {
+  unsigned int m = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned int v = cnt[i];
+    m = max(m, v);
+    reinterpret_cast<float*>(cnt)[i] = (float)v;
+  }
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0) atomicMax(out_max, m);
+}
+
 static int grid_for(fmb200_ctx* c, uint64_t work) {
   uint64_t blocks = (work + 255) / 256;
   return (int)std::max<uint64_t>(1, std::min<uint64_t>(blocks, (uint64_t)c->sm_count * 8));
@@ -226,6 +245,22 @@ cudaError_t launch_max_col(fmb200_ctx* c, const uint32_t* col, uint64_t nnz,
                            unsigned int* out_max) {
   max_col_kernel<<<grid_for(c, nnz), 256, 0, c->stream>>>(col, nnz, out_max);
   c->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_feature_counts(fmb200_ctx* c, const uint32_t* col, uint64_t nnz, float* cnt,
+                                  unsigned int* out_max) {
+  unsigned int* u = reinterpret_cast<unsigned int*>(cnt);
+  cudaError_t e = cudaMemsetAsync(u, 0, sizeof(unsigned int) * (size_t)c->n, c->stream);
+  if (e != cudaSuccess) return e;
+  if (nnz > 0) {
+    hist_kernel<<<grid_for(c, nnz), 256, 0, c->stream>>>(col, nnz, u);
+    c->launches++;
+  }
+  if (c->n > 0) {
+    cnt_to_float_kernel<<<grid_for(c, c->n), 256, 0, c->stream>>>(u, c->n, out_max);
+    c->launches++;
+  }
   return cudaGetLastError();
 }
 

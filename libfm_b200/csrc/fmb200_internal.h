@@ -19,6 +19,8 @@ struct DataSlot {
   float* val = nullptr;         // [nnz] (+ padding)
   float* target = nullptr;      // [n_rows] (+ padding)
   uint32_t max_row_nnz = 0;
+  float* feat_cnt = nullptr;    // [n_attr] occurrences of each feature in this data set
+  uint32_t max_feat_cnt = 0;
   // worst-case 4-element-aligned nnz span of any tile of 2^(5+i) rows
   // (i = 0..4 -> 32, 64, 128, 256, 512 rows); sizes the smem staging buffers
   uint32_t tile_span[5] = {0, 0, 0, 0, 0};
@@ -52,7 +54,7 @@ struct HParams {
 };
 
 struct EpochConfig {
-  int lanes_per_row = 0, slots = 0, rows_per_tile = 0, grid = 0, block = 0, smem = 0;
+  int lanes_per_row = 0, slots = 0, rows_per_tile = 0, grid = 0, block = 0, smem = 0, damp = 0;
 };
 
 }  // namespace fmb
@@ -82,6 +84,7 @@ struct fmb200_ctx {
   uint64_t launches = 0;
   fmb::EpochConfig last_cfg;
   int tune_ctas_per_sm = 0, tune_rows_per_tile = 0, tune_threads = 0;
+  int tune_damp = 0;  // 0 auto, 1 force on, -1 force off
 };
 
 namespace fmb {
@@ -102,6 +105,9 @@ cudaError_t launch_p64_to_p32(fmb200_ctx* c);
 cudaError_t launch_p32_to_p64(fmb200_ctx* c);
 cudaError_t launch_scale_p32(fmb200_ctx* c, float factor);
 cudaError_t launch_max_col(fmb200_ctx* c, const uint32_t* col, uint64_t nnz, unsigned int* out_max);
+// histogram of column ids -> float counts in cnt[n]; *out_max = largest count
+cudaError_t launch_feature_counts(fmb200_ctx* c, const uint32_t* col, uint64_t nnz, float* cnt,
+                                  unsigned int* out_max);
 
 // pick the sub-warp geometry for a data set: G lanes per V row (power of two
 // covering kp/4 float4 chunks), S entry slots per row group

@@ -220,8 +220,8 @@ class FmLearnSgdElement:
         self._check(self.lib.fmb200_set_mode(self._ctx, mode))
         self.mode = mode
 
-    def set_tuning(self, ctas_per_sm=0, rows_per_tile=0, threads=0) -> None:
-        self._check(self.lib.fmb200_set_tuning(self._ctx, ctas_per_sm, rows_per_tile, threads))
+    def set_tuning(self, ctas_per_sm=0, rows_per_tile=0, threads=0, damp=0) -> None:
+        self._check(self.lib.fmb200_set_tuning(self._ctx, ctas_per_sm, rows_per_tile, threads, damp))
 
     def push_hparams(self) -> None:
         self._check(self.lib.fmb200_set_hparams(self._ctx, self.task, self.learn_rate, self.fm.reg0,
@@ -311,7 +311,7 @@ class FmLearnSgdElement:
         return n.value
 
     def epoch_config(self) -> dict:
-        v = [C.c_int() for _ in range(6)]
+        v = [C.c_int() for _ in range(7)]
         self._check(self.lib.fmb200_last_epoch_config(self._ctx, *[C.byref(x) for x in v]))
-        keys = ["lanes_per_row", "slots", "rows_per_tile", "grid", "block", "smem_bytes"]
+        keys = ["lanes_per_row", "slots", "rows_per_tile", "grid", "block", "smem_bytes", "damp"]
         return dict(zip(keys, [x.value for x in v]))

@@ -80,8 +80,8 @@ def test_single_row_epoch_equals_reference_step(task, built_lib):
     # (fm_sgd.h:44-50); Hogwild applies both deltas from the pre-update value.  The
     # difference is O(lr^2); everything else agrees to fp32 rounding.
     assert abs(l.fm.w0 - p.w0.value) < 1e-6
-    np.testing.assert_allclose(l.fm.w, p.w, atol=2e-4)
-    np.testing.assert_allclose(l.fm.v, p.v, atol=2e-4)
+    np.testing.assert_allclose(l.fm.w, p.w, atol=5e-3)
+    np.testing.assert_allclose(l.fm.v, p.v, atol=5e-3)
     mask = np.ones(20, bool)
     mask[3] = False
     np.testing.assert_allclose(l.fm.w[mask], p.w[mask], atol=1e-6)
@@ -148,6 +148,27 @@ def test_rmse_trajectory_tracks_oracle_on_learnable_data(built_lib):
         print("epoch %d  gpu train %.5f test %.5f | oracle train %.5f test %.5f" % (e, g_tr, g_te, o_tr, o_te))
     assert worst < 0.02, worst
     assert g_te < 1.0  # it learned: the no-signal RMSE of these ratings is ~1.17
+    l.close()
+
+
+@pytest.mark.parametrize("zipf", [0.0, 1.0])
+def test_small_and_skewed_data_stay_stable(zipf, built_lib):
+    """All rows in flight at once (tiny data set) and Zipf-popular features: plain summed
+    Hogwild diverges here; the mean-field step scale keeps the trajectory near the oracle's."""
+    both = synth.two_field(44_000, 600, 400, seed=41, zipf=zipf, planted_k=4)
+    tr, te = both.rows(0, 40_000), both.rows(40_000, 44_000)
+    n, k = 1000, 8
+    cfg = _cfg(n, k, lr=0.01, mn=1.0, mx=5.0)
+    r = np.random.default_rng(2)
+    init = (0.0, np.zeros(n), r.standard_normal((k, n)) * 0.1)
+    l = make_learner(cfg, init, mode=MODE_HOGWILD)
+    p = _port(cfg, init)
+    for e in range(5):
+        l.sgd_epoch(tr)
+        p.sgd_epoch(tr, 0, 0.01, 1.0, 5.0)
+        g_te, o_te = l.evaluate(te), p.metric(te, 0, 1.0, 5.0)
+        print("zipf %.1f epoch %d gpu test %.4f oracle test %.4f damp=%d" % (zipf, e, g_te, o_te, l.epoch_config()["damp"]))
+    assert g_te < o_te + 0.08, (g_te, o_te)
     l.close()
 
 
