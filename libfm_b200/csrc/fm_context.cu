@@ -57,68 +57,52 @@ constexpr uint64_t kEntrySlack = 16;
 int upload_common(fmb200_ctx* c, int slot, uint64_t n_rows, uint64_t nnz, const uint64_t* row_ptr,
                   const uint32_t* col, const float* val, const float* target) {
   DataSlot& s = c->slots[slot];
-  free_slot(s);
-  // structural validation of the offsets (host side, O(n_rows))
-  if (row_ptr[0] != 0) return fail("row_ptr[0] must be 0");
-  uint32_t max_row = 0;
-  for (uint64_t r = 0; r < n_rows; r++) {
-    if (row_ptr[r + 1] < row_ptr[r]) return fail("row_ptr not monotone at row %llu", (unsigned long long)r);
-    uint64_t len = row_ptr[r + 1] - row_ptr[r];
-    if (len > 0xffffffffull) return fail("row %llu too long", (unsigned long long)r);
-    if (len > max_row) max_row = (uint32_t)len;
+  // re-uploads into a slot reuse its buffers when they are large enough
+  if (!(s.row_ptr && s.cap_rows >= n_rows && s.cap_nnz >= nnz)) {
+    free_slot(s);
+    CK(cudaMalloc(&s.row_ptr, (n_rows + 1 + kRowSlack) * sizeof(uint64_t)));
+    CK(cudaMalloc(&s.target, (n_rows + kRowSlack) * sizeof(float)));
+    CK(cudaMalloc(&s.col, (nnz + kEntrySlack) * sizeof(uint32_t)));
+    CK(cudaMalloc(&s.val, (nnz + kEntrySlack) * sizeof(float)));
+    CK(cudaMalloc(&s.feat_cnt, sizeof(float) * (size_t)(c->n ? c->n : 1)));
+    // the slack is only ever read by whole-tile bulk copies and never used
+    CK(cudaMemsetAsync(s.row_ptr, 0, (n_rows + 1 + kRowSlack) * sizeof(uint64_t), c->stream));
+    CK(cudaMemsetAsync(s.target, 0, (n_rows + kRowSlack) * sizeof(float), c->stream));
+    CK(cudaMemsetAsync(s.col, 0, (nnz + kEntrySlack) * sizeof(uint32_t), c->stream));
+    CK(cudaMemsetAsync(s.val, 0, (nnz + kEntrySlack) * sizeof(float), c->stream));
+    s.cap_rows = n_rows;
+    s.cap_nnz = nnz;
   }
-  if (row_ptr[n_rows] != nnz) return fail("row_ptr[n_rows]=%llu != nnz=%llu",
-                                          (unsigned long long)row_ptr[n_rows], (unsigned long long)nnz);
-  for (int i = 0; i < 5; i++) {
-    const uint64_t TR = 32ull << i;
-    uint64_t worst = 0;
-    for (uint64_t r0 = 0; r0 < n_rows; r0 += TR) {
-      uint64_t r1 = r0 + TR < n_rows ? r0 + TR : n_rows;
-      uint64_t ab = row_ptr[r0] & ~3ull, ae = (row_ptr[r1] + 3ull) & ~3ull;
-      if (ae - ab > worst) worst = ae - ab;
-    }
-    if (worst > 0xffffffffull) return fail("tile too large");
-    s.tile_span[i] = (uint32_t)worst;
-  }
-  s.max_row_nnz = max_row;
+  s.present = false;
   s.n_rows = n_rows;
   s.nnz = nnz;
-  CK(cudaMalloc(&s.row_ptr, (n_rows + 1 + kRowSlack) * sizeof(uint64_t)));
-  CK(cudaMalloc(&s.target, (n_rows + kRowSlack) * sizeof(float)));
-  CK(cudaMalloc(&s.col, (nnz + kEntrySlack) * sizeof(uint32_t)));
-  CK(cudaMalloc(&s.val, (nnz + kEntrySlack) * sizeof(float)));
-  CK(cudaMemsetAsync(s.row_ptr + n_rows + 1, 0, kRowSlack * sizeof(uint64_t), c->stream));
-  CK(cudaMemsetAsync(s.target + n_rows, 0, kRowSlack * sizeof(float), c->stream));
-  CK(cudaMemsetAsync(s.col + nnz, 0, kEntrySlack * sizeof(uint32_t), c->stream));
-  CK(cudaMemsetAsync(s.val + nnz, 0, kEntrySlack * sizeof(float), c->stream));
   CK(cudaMemcpyAsync(s.row_ptr, row_ptr, (n_rows + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(s.target, target, n_rows * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(s.col, col, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(s.val, val, nnz * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  // the reference asserts id < num_attribute per access (fm_model.h:112);
-  // here the whole data set is checked once, on the device
-  if (nnz > 0) {
-    CK(cudaMemsetAsync(c->d_flag, 0, sizeof(unsigned int), c->stream));
-    CK(launch_max_col(c, s.col, nnz, c->d_flag));
-    unsigned int mx = 0;
-    CK(cudaMemcpyAsync(&mx, c->d_flag, sizeof(mx), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    if (mx >= c->n) {
-      free_slot(s);
-      return fail("feature id %u out of range (num_attribute=%u)", mx, c->n);
-    }
-    // per-feature occurrence counts (hot-feature damping of the HOGWILD epoch)
-    CK(cudaMalloc(&s.feat_cnt, sizeof(float) * (size_t)(c->n ? c->n : 1)));
-    CK(cudaMemsetAsync(c->d_flag, 0, sizeof(unsigned int), c->stream));
-    CK(launch_feature_counts(c, s.col, nnz, s.feat_cnt, c->d_flag));
-    CK(cudaMemcpyAsync(&mx, c->d_flag, sizeof(mx), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    s.max_feat_cnt = mx;
-  } else {
-    CK(cudaMalloc(&s.feat_cnt, sizeof(float) * (size_t)(c->n ? c->n : 1)));
-    CK(cudaMemsetAsync(s.feat_cnt, 0, sizeof(float) * (size_t)(c->n ? c->n : 1), c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-  }
+  // Inspection runs on the device, in the shadow of nothing but itself: offsets
+  // monotone and consistent, longest row, tile spans, largest column id (the
+  // reference asserts id < num_attribute per access, fm_model.h:112), and the
+  // per-feature occurrence counts used by the HOGWILD damping.
+  CK(cudaMemsetAsync(c->d_flag, 0, 16 * sizeof(unsigned int), c->stream));
+  CK(launch_csr_inspect(c, s.row_ptr, n_rows, nnz, c->d_flag));
+  if (nnz > 0) CK(launch_max_col(c, s.col, nnz, c->d_flag + 8));
+  unsigned int h[16];
+  CK(cudaMemcpyAsync(h, c->d_flag, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (h[0] & 1u) return fail("row_ptr[0] must be 0");
+  if (h[0] & 2u) return fail("row_ptr is not monotone");
+  if (h[0] & 4u) return fail("row_ptr[n_rows] != nnz");
+  if (h[0] & 8u) return fail("a row is longer than 2^32-1 entries");
+  if (nnz > 0 && h[8] >= c->n)
+    return fail("feature id %u out of range (num_attribute=%u)", h[8], c->n);
+  s.max_row_nnz = h[1];
+  for (int i = 0; i < 5; i++) s.tile_span[i] = h[2 + i];
+  // counts only after the ids are known to be in range (the histogram indexes by id)
+  CK(launch_feature_counts(c, s.col, nnz, s.feat_cnt, c->d_flag + 9));
+  CK(cudaMemcpyAsync(h, c->d_flag + 9, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  s.max_feat_cnt = h[0];
   s.present = true;
   return 0;
 }
@@ -194,7 +178,7 @@ int fmb200_create(fmb200_ctx** out, int device, uint32_t n_attr, int num_factor,
   CK(cudaMemsetAsync(c->p64.base, 0, c->p64.n_doubles * sizeof(double), c->stream));
   CK(cudaMalloc(&c->d_w0_accum, sizeof(float)));
   CK(cudaMalloc(&c->d_done, sizeof(unsigned int)));
-  CK(cudaMalloc(&c->d_flag, sizeof(unsigned int)));
+  CK(cudaMalloc(&c->d_flag, 16 * sizeof(unsigned int)));
   CK(cudaMemsetAsync(c->d_w0_accum, 0, sizeof(float), c->stream));
   CK(cudaMemsetAsync(c->d_done, 0, sizeof(unsigned int), c->stream));
   CK(cudaStreamSynchronize(c->stream));

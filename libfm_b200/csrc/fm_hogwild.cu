@@ -13,10 +13,11 @@
 //    copies (cp.async.bulk global->shared, mbarrier complete_tx): row offsets,
 //    targets, column ids, values; NSTAGE tiles are in flight per CTA, marked
 //    L2 evict_first (the CSR is streamed once per epoch).
-//  * compute: every warp handles 32/E rows at a time with the RowGroup mapping
-//    (fm_rowgroup.cuh): V rows gathered as float4 with ld.global.cg (parameters
-//    are mutated by other SMs through L2, so L1 must not serve them), per-factor
-//    sums by segmented warp shuffles, write-back as fire-and-forget
+//  * compute: every warp handles U x 32/E rows at a time with the RowGroup mapping
+//    (fm_rowgroup.cuh): the gathers of all U row sets are issued before any is
+//    consumed (memory-level parallelism), V rows as float4 with ld.global.cg
+//    (parameters are mutated by other SMs through L2, so L1 must not serve them),
+//    per-factor sums by segmented warp shuffles, write-back as fire-and-forget
 //    red.global.add.v4.f32 / red.global.add.f32 (Hogwild: no locks, no CAS).
 //  * concurrency control.  The reference is strictly sequential; Hogwild sums the
 //    steps of all examples that are in flight together.  For a parameter block
@@ -25,17 +26,19 @@
 //    the bias w0 (every example touches it, fm_sgd.h:34-37) and for popular
 //    features of skewed data.  Both are handled by the closed form of the
 //    reference's own sequential recurrence under a mean-field linearisation:
-//    c sequential steps contract the residual by a = 1 - lr*h each, so the c
-//    concurrent steps are each scaled by  sat(q) = (1 - e^-q)/q,  q = c*lr*h
-//    (sat -> 1 for q -> 0: cold features and c = 1 take exactly the reference step).
-//      - w0: carried PER WARP in a register through the warp's own row sequence
-//        (T = rows of one pass, q = T*lr*(mean curvature + reg0)); the
-//        row-weighted mean of all warp-local biases becomes w0 at the end of the
-//        epoch.  No atomics on w0, no block barrier for it.
+//    c sequential steps contract the residual by a = 1 - lr*h each, so each of
+//    the c concurrent steps is scaled by
+//        gamma(c, lr*h) = (1 - a^c) / (c * (1 - a))        (== 1 for c == 1)
+//    which reproduces the reference step for cold features / a single row.
+//      - w0: every CTA accumulates sum(mult + reg0*w0) and the mean SECANT curvature
+//        h_t = mult_t / (p_raw_t - y_t) of a tile (1 where the score is unclamped,
+//        < 1 where fm_learn_sgd_element.h:60-61 clamps it; logistic: s(1-s)) and
+//        applies ONE damped reduction to the global w0 per tile, with
+//        c = rows in flight = min(N, grid * rows_per_tile).
 //      - w_i, V_i (template flag DAMP, on when some feature is hot enough to
-//        matter): c_i = count_i * W / N from a per-feature occurrence table built
-//        at upload (W = rows in flight), h_w = x^2 + regw,
-//        h_V = x^2 * sum_f (s_f - v_if x)^2 + regv.
+//        matter): c_i = max(1, count_i * W / N) from a per-feature occurrence table
+//        built at upload (W = rows being processed concurrently),
+//        h_w = x^2 + regw,  h_V = x^2 * sum_f (s_f - v_if x)^2 + regv.
 //
 // Algorithmic HBM traffic per example (roofline numerator, BASELINE.json):
 // 2*k*nnz*4 bytes (V rows read + written back).
@@ -48,7 +51,7 @@ namespace fmb {
 
 constexpr int HW_NSTAGE = 3;
 constexpr int HW_MAX_THREADS = 256;
-constexpr int HW_HDR_BYTES = 128;  // mbarriers
+constexpr int HW_HDR_BYTES = 128;  // mbarriers [0,64) + per-tile bias accumulators [64,128)
 
 struct HogwildArgs {
   const uint64_t* row_ptr;
@@ -66,10 +69,9 @@ struct HogwildArgs {
   int gp;  // float4 chunks per V row (kp / 4)
   int use_w0, use_w, task;
   float lr, reg0, regw, regv, min_target, max_target;
-  float* w0_accum;
-  unsigned int* done;
   const float* feat_cnt;  // occurrences of each feature in this data set (DAMP)
-  float conc_scale;       // rows in flight / n_rows: count -> expected concurrency
+  float conc_scale;       // rows processed concurrently / n_rows: count -> concurrency
+  float w0_conc;          // rows in flight w.r.t. the bias (tile granularity)
 };
 
 __device__ __forceinline__ unsigned char* stage_base(unsigned char* smem, const HogwildArgs& a,
@@ -77,15 +79,12 @@ __device__ __forceinline__ unsigned char* stage_base(unsigned char* smem, const 
   return smem + HW_HDR_BYTES + (size_t)stage * a.stage_bytes;
 }
 
-// TMA producer: stage one tile.  Called by a single thread.
+// TMA producer: stage one tile whose entry range [nb, ne) is already known.
 __device__ __forceinline__ void issue_tile(const HogwildArgs& a, unsigned char* smem,
                                            uint64_t* bars, uint32_t tile, int stage,
-                                           uint64_t policy) {
+                                           uint64_t policy, uint64_t nb, uint64_t ne) {
   const int TR = a.tile_rows;
   const uint64_t r0 = (uint64_t)tile * TR;
-  const uint64_t r1 = min(r0 + (uint64_t)TR, a.n_rows);
-  const uint64_t nb = __ldg(a.row_ptr + r0);
-  const uint64_t ne = __ldg(a.row_ptr + r1);
   const uint64_t ab = nb & ~3ull;
   const uint64_t ae = (ne + 3ull) & ~3ull;
   const uint32_t ebytes = (uint32_t)(ae - ab) * 4u;
@@ -103,25 +102,32 @@ __device__ __forceinline__ void issue_tile(const HogwildArgs& a, unsigned char* 
   }
 }
 
-// sat(q) = (1 - e^-q)/q : the mean-field step scale for q = c*lr*h
-__device__ __forceinline__ float sat_scale(float q) {
-  return q < 1e-3f ? 1.f - 0.5f * q : (1.f - __expf(-q)) / q;
+// gamma(c, u) = (1 - (1-u)^c) / (c*u): scale of each of c concurrent steps whose
+// sequential execution would contract the residual by (1-u) per step
+__device__ __forceinline__ float gamma_scale(float c, float u) {
+  if (c <= 1.f || u <= 0.f) return 1.f;
+  const float q = c * u;
+  if (q < 1e-3f) return 1.f;
+  const float a = fmaxf(1.f - u, 0.f);
+  const float ac = a > 0.f ? __expf(c * __logf(a)) : 0.f;
+  return fminf(1.f, (1.f - ac) / q);
 }
 
-template <int G, int S, int R, bool DAMP>
-__global__ void __launch_bounds__(HW_MAX_THREADS, (R <= 2 ? 4 : 2))
+template <int G, int S, int R, int U, bool DAMP>
+__global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
     fm_sgd_hogwild_kernel(const HogwildArgs a) {
   using RG = RowGroup<G, S, R>;
   constexpr int E = RG::E;
-  constexpr int RPW = 32 / E;  // rows per warp per pass
+  constexpr int RPW = 32 / E;  // rows per warp per row set
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  float* s_acc = reinterpret_cast<float*>(smem + 64);  // [3][4]: sum grad, sum curvature
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
   const int nwarp = blockDim.x >> 5;
-  const int rows_per_pass = nwarp * RPW;
+  const int rows_per_set = nwarp * RPW;
   const int lig = lane % E;  // lane in group
   const int c = lig % G;
   const int s = lig / G;
@@ -131,30 +137,43 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R <= 2 ? 4 : 2))
   uint64_t policy = 0;
   if (tid == 0) {
     for (int i = 0; i < HW_NSTAGE; i++) mbar_init(bars + i, 1);
+    for (int i = 0; i < 12; i++) s_acc[i] = 0.f;
     fence_mbar_init();
     policy = policy_evict_first();
   }
   __syncthreads();
   if (tid == 0) {
     for (int i = 0; i < HW_NSTAGE; i++) {
-      uint64_t t = (uint64_t)blockIdx.x + (uint64_t)i * gridDim.x;
-      if (t < a.n_tiles) issue_tile(a, smem, bars, (uint32_t)t, i, policy);
+      const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)i * gridDim.x;
+      if (t < a.n_tiles) {
+        const uint64_t r0 = t * TR, r1 = min(r0 + (uint64_t)TR, a.n_rows);
+        issue_tile(a, smem, bars, (uint32_t)t, i, policy, __ldg(a.row_ptr + r0),
+                   __ldg(a.row_ptr + r1));
+      }
     }
   }
 
   const float4* V4 = reinterpret_cast<const float4*>(a.v);
   const bool use_w = a.use_w != 0;
   const bool use_w0 = a.use_w0 != 0;
-  float w0 = use_w0 ? ld_cg_f(a.w0) : 0.f;  // warp-local bias (replicated in the lanes)
   const float lr = a.lr;
   const float nlr_regv = -lr * a.regv;
   const float nlr_regw = -lr * a.regw;
-  float my_rows = 0.f;
 
   int it = 0;
   for (uint64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
     const int stage = it % HW_NSTAGE;
     const uint32_t parity = (uint32_t)(it / HW_NSTAGE) & 1u;
+    // producer: fetch the entry range of the tile that will refill this stage now,
+    // so the two dependent global loads overlap this tile's compute
+    const uint64_t nt = tile + (uint64_t)HW_NSTAGE * gridDim.x;
+    uint64_t nt_nb = 0, nt_ne = 0;
+    if (tid == 0 && nt < a.n_tiles) {
+      const uint64_t r0 = nt * TR, r1 = min(r0 + (uint64_t)TR, a.n_rows);
+      nt_nb = __ldg(a.row_ptr + r0);
+      nt_ne = __ldg(a.row_ptr + r1);
+    }
+    const float w0 = use_w0 ? ld_cg_f(a.w0) : 0.f;  // tile-start bias
     mbar_wait(bars + stage, parity);
 
     unsigned char* sb = stage_base(smem, a, stage);
@@ -166,126 +185,123 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R <= 2 ? 4 : 2))
     const int rows_here = (int)min((uint64_t)TR, a.n_rows - row0);
     const uint64_t ab = rp[0] & ~3ull;
 
-    for (int rbase = warp * RPW; rbase < rows_here; rbase += rows_per_pass) {
-      const int r = rbase + sub;
-      const bool valid = r < rows_here;
-      int beg = 0, end = 0;
-      float y = 0.f;
-      if (valid) {
-        beg = (int)(rp[r] - ab);
-        end = (int)(rp[r + 1] - ab);
-        y = ys[r];
+    float msum = 0.f, hsum = 0.f;
+    for (int rbase = warp * RPW; rbase < rows_here; rbase += U * rows_per_set) {
+      RG g[U];
+      float y[U];
+      bool valid[U];
+      // ---- phase 1: put the gathers of all U row sets in flight ----
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = rbase + u * rows_per_set + sub;
+        valid[u] = r < rows_here;
+        int beg = 0, end = 0;
+        y[u] = 0.f;
+        if (valid[u]) {
+          beg = (int)(rp[r] - ab);
+          end = (int)(rp[r + 1] - ab);
+          y[u] = ys[r];
+        }
+        g[u].gather(V4, a.w, a.gp, use_w, ids, xs, beg, end, c, s);
       }
-      RG g;
-      const float part = g.score(V4, a.w, a.gp, use_w, ids, xs, beg, end, c, s);
-      const float p = w0 + part;
-      float mult, curv;
-      if (a.task == FMB200_TASK_REGRESSION) {
-        // fm_learn_sgd_element.h:59-62
-        const float pc = fmaxf(a.min_target, fminf(a.max_target, p));
-        curv = (pc == p) ? 1.f : 0.f;
-        mult = pc - y;
-      } else {
-        // fm_learn_sgd_element.h:63-64 ; y in {-1,+1}
-        const float sg = 1.f / (1.f + __expf(-y * p));
-        mult = -y * (1.f - sg);
-        curv = sg * (1.f - sg);
-      }
+      // ---- phase 2: score, multiplier, write-back, one row set at a time ----
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (U > 1 && rbase + u * rows_per_set >= rows_here) break;  // warp-uniform
+        RG& gu = g[u];
+        const float part = gu.reduce(V4, a.w, a.gp, use_w, ids, xs, c, s);
+        const float p = w0 + part;
+        float mult, curv;
+        if (a.task == FMB200_TASK_REGRESSION) {
+          // fm_learn_sgd_element.h:59-62
+          const float pc = fmaxf(a.min_target, fminf(a.max_target, p));
+          mult = pc - y[u];
+          // secant curvature of the clamped loss w.r.t. the raw score
+          const float den = p - y[u];
+          curv = (pc == p) ? 1.f : (fabsf(den) > 1e-12f ? fminf(fmaxf(mult / den, 0.f), 1.f) : 0.f);
+        } else {
+          // fm_learn_sgd_element.h:63-64 ; y in {-1,+1}
+          const float sg = 1.f / (1.f + __expf(-y[u] * p));
+          mult = -y[u] * (1.f - sg);
+          curv = sg * (1.f - sg);
+        }
+        if (valid[u] && lig == 0) {
+          msum += mult;
+          hsum += curv;
+        }
 
-      // ---- bias: warp-local closed-form step over this pass's rows ----
+        // ---- fm_SGD write-back (fm_sgd.h:38-50) as L2 reductions ----
+        const float nlr_mult = -lr * mult;
+        auto update = [&](bool on, uint32_t id, float x, const float4& v, float wv) {
+          const float x2 = x * x;
+          const float gx = gu.acc.x * x - v.x * x2, gy = gu.acc.y * x - v.y * x2;
+          const float gz = gu.acc.z * x - v.z * x2, gw = gu.acc.w * x - v.w * x2;
+          float sv = 1.f, sw = 1.f;
+          if (DAMP) {
+            const float conc = __ldg(a.feat_cnt + id) * a.conc_scale;  // expected concurrency
+            float n2 = gx * gx + gy * gy + gz * gz + gw * gw;           // |d p / d V_i|^2
+#pragma unroll
+            for (int o = 1; o < G; o <<= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+            sv = gamma_scale(conc, lr * (n2 + a.regv));
+            sw = gamma_scale(conc, lr * (x2 + a.regw));
+          }
+          if (on && c < a.gp) {
+            // -lr*(mult*(sum_f*x - v*x^2) + regv*v)
+            red_add_f4(a.v + ((size_t)id * a.gp + c) * 4, sv * (nlr_mult * gx + nlr_regv * v.x),
+                       sv * (nlr_mult * gy + nlr_regv * v.y), sv * (nlr_mult * gz + nlr_regv * v.z),
+                       sv * (nlr_mult * gw + nlr_regv * v.w));
+          }
+          if (on && use_w && c == 0) red_add_f(a.w + id, sw * (nlr_mult * x + nlr_regw * wv));
+        };
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          const int j = gu.beg + s + q * S;
+          const bool on = j < gu.end;
+          if (DAMP) {
+            // the norm reduction shuffles across the G chunk lanes: keep the warp converged
+            if (__any_sync(0xffffffffu, on)) update(on, gu.idc[q], gu.xc[q], gu.vc[q], gu.wc[q]);
+          } else if (on) {
+            update(true, gu.idc[q], gu.xc[q], gu.vc[q], gu.wc[q]);
+          }
+        }
+        for (int q = R; q < gu.maxit; ++q) {
+          const int j = gu.beg + s + q * S;
+          const bool on = j < gu.end;
+          uint32_t id = 0;
+          float x = 0.f, wv = 0.f;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (on) {
+            x = xs[j];
+            id = ids[j];
+            if (c < a.gp) v = ld_cg_f4(V4 + (size_t)id * a.gp + c);
+            if (use_w && c == 0) wv = ld_cg_f(a.w + id);
+          }
+          if (DAMP || on) update(on, id, x, v, wv);
+        }
+      }
+    }
+
+    // ---- bias: one damped reduction into the global w0 per tile ----
+    const int slot = it % 3;
+    if (use_w0) {
+      msum = warp_sum(msum);
+      hsum = warp_sum(hsum);
+      if (lane == 0) {
+        atomicAdd(&s_acc[4 * slot + 0], msum);
+        atomicAdd(&s_acc[4 * slot + 1], hsum);
+      }
+    }
+    __syncthreads();  // every warp is done with this stage; accumulators complete
+    if (tid == 0) {
+      if (nt < a.n_tiles) issue_tile(a, smem, bars, (uint32_t)nt, stage, policy, nt_nb, nt_ne);
       if (use_w0) {
-        float ms = (valid && lig == 0) ? mult : 0.f;
-        float hs = (valid && lig == 0) ? curv : 0.f;
-        float ts = (valid && lig == 0) ? 1.f : 0.f;
-        // sum over the warp's group leaders (xor strides that are multiples of E
-        // keep lig fixed), then broadcast lane 0's total
-#pragma unroll
-        for (int o = E; o < 32; o <<= 1) {
-          ms += __shfl_xor_sync(0xffffffffu, ms, o);
-          hs += __shfl_xor_sync(0xffffffffu, hs, o);
-          ts += __shfl_xor_sync(0xffffffffu, ts, o);
-        }
-        ms = __shfl_sync(0xffffffffu, ms, 0);
-        hs = __shfl_sync(0xffffffffu, hs, 0);
-        ts = __shfl_sync(0xffffffffu, ts, 0);
-        if (ts > 0.f) {
-          const float q = lr * (hs + ts * a.reg0);  // T * lr * (mean curvature + reg0)
-          w0 -= sat_scale(q) * lr * (ms + ts * a.reg0 * w0);
-          my_rows += ts;
-        }
-      }
-
-      // ---- fm_SGD write-back (fm_sgd.h:38-50) as L2 reductions ----
-      const float nlr_mult = -lr * mult;
-      auto update = [&](bool on, uint32_t id, float x, const float4& v, float wv) {
-        const float x2 = x * x;
-        const float gx = g.acc.x * x - v.x * x2, gy = g.acc.y * x - v.y * x2;
-        const float gz = g.acc.z * x - v.z * x2, gw = g.acc.w * x - v.w * x2;
-        float sv = 1.f, sw = 1.f;
-        if (DAMP) {
-          const float conc = __ldg(a.feat_cnt + id) * a.conc_scale;  // expected concurrency
-          float n2 = gx * gx + gy * gy + gz * gz + gw * gw;           // |d p / d V_i|^2
-#pragma unroll
-          for (int o = 1; o < G; o <<= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
-          sv = sat_scale(conc * lr * (n2 + a.regv));
-          sw = sat_scale(conc * lr * (x2 + a.regw));
-        }
-        if (on && c < a.gp) {
-          // -lr*(mult*(sum_f*x - v*x^2) + regv*v)
-          red_add_f4(a.v + ((size_t)id * a.gp + c) * 4, sv * (nlr_mult * gx + nlr_regv * v.x),
-                     sv * (nlr_mult * gy + nlr_regv * v.y), sv * (nlr_mult * gz + nlr_regv * v.z),
-                     sv * (nlr_mult * gw + nlr_regv * v.w));
-        }
-        if (on && use_w && c == 0) red_add_f(a.w + id, sw * (nlr_mult * x + nlr_regw * wv));
-      };
-#pragma unroll
-      for (int q = 0; q < R; ++q) {
-        const int j = beg + s + q * S;
-        const bool on = j < end;
-        if (DAMP) {
-          // the norm reduction shuffles across the G chunk lanes: keep them converged
-          if (__any_sync(0xffffffffu, on)) update(on, g.idc[q], g.xc[q], g.vc[q], g.wc[q]);
-        } else if (on) {
-          update(true, g.idc[q], g.xc[q], g.vc[q], g.wc[q]);
-        }
-      }
-      for (int q = R; q < g.maxit; ++q) {
-        const int j = beg + s + q * S;
-        const bool on = j < end;
-        uint32_t id = 0;
-        float x = 0.f, wv = 0.f;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (on) {
-          x = xs[j];
-          id = ids[j];
-          if (c < a.gp) v = ld_cg_f4(V4 + (size_t)id * a.gp + c);
-          if (use_w && c == 0) wv = ld_cg_f(a.w + id);
-        }
-        if (DAMP || on) update(on, id, x, v, wv);
-      }
-    }
-
-    __syncthreads();  // every warp is done with this stage: refill it
-    if (tid == 0) {
-      const uint64_t nt = tile + (uint64_t)HW_NSTAGE * gridDim.x;
-      if (nt < a.n_tiles) issue_tile(a, smem, bars, (uint32_t)nt, stage, policy);
-    }
-  }
-
-  // ---- merge the warp-local biases: row-weighted mean over all warps ----
-  if (use_w0 && lane == 0) {
-    if (my_rows > 0.f) atomicAdd(a.w0_accum, w0 * (my_rows / (float)a.n_rows));
-  }
-  if (use_w0) {
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      const unsigned int ticket = atomicAdd(a.done, 1u);
-      if (ticket == gridDim.x - 1) {
-        __threadfence();
-        const float merged = atomicExch(a.w0_accum, 0.f);
-        *a.w0 = merged;
-        *a.done = 0u;
+        const float T = (float)rows_here;
+        const float M = s_acc[4 * slot + 0] + T * a.reg0 * w0;  // sum_t (mult_t + reg0*w0)
+        const float hbar = s_acc[4 * slot + 1] / T;
+        const float gsc = gamma_scale(fmaxf(a.w0_conc, 1.f), lr * (hbar + a.reg0));
+        red_add_f(a.w0, -lr * gsc * M);
+        s_acc[4 * slot + 0] = 0.f;  // next written after two more barriers
+        s_acc[4 * slot + 1] = 0.f;
       }
     }
   }
@@ -294,19 +310,19 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R <= 2 ? 4 : 2))
 // ---------------------------------------------------------------------------
 using KernelFn = void (*)(const HogwildArgs);
 
+template <int G, int S, int R, int U>
+KernelFn pick_damp(bool damp) {
+  return damp ? fm_sgd_hogwild_kernel<G, S, R, U, true> : fm_sgd_hogwild_kernel<G, S, R, U, false>;
+}
+
+// R entries cached per lane, U row sets in flight: (1,4) short one-hot rows,
+// (2,2), and (8,1) for long rows
 template <int G, int S>
 KernelFn pick_r(int R, bool damp) {
-  if (damp) {
-    switch (R) {
-      case 1: return fm_sgd_hogwild_kernel<G, S, 1, true>;
-      case 2: return fm_sgd_hogwild_kernel<G, S, 2, true>;
-      default: return fm_sgd_hogwild_kernel<G, S, 8, true>;
-    }
-  }
   switch (R) {
-    case 1: return fm_sgd_hogwild_kernel<G, S, 1, false>;
-    case 2: return fm_sgd_hogwild_kernel<G, S, 2, false>;
-    default: return fm_sgd_hogwild_kernel<G, S, 8, false>;
+    case 1: return pick_damp<G, S, 1, 4>(damp);
+    case 2: return pick_damp<G, S, 2, 2>(damp);
+    default: return pick_damp<G, S, 8, 1>(damp);
   }
 }
 
@@ -357,11 +373,13 @@ cudaError_t launch_sgd_hogwild(fmb200_ctx* c, const DataSlot& d) {
   const double avg = (double)d.nnz / (double)d.n_rows;
   const int iters = (int)((avg + S - 1) / S);
   const int R = iters <= 1 ? 1 : (iters <= 2 ? 2 : 8);
+  const int U = R == 1 ? 4 : (R == 2 ? 2 : 1);
   const int threads = c->tune_threads > 0 ? std::min(c->tune_threads, HW_MAX_THREADS) : 256;
+  const int ctas_target = (R * U <= 4) ? 3 : 2;
 
   // tile geometry: largest tile (<= 256 rows by default) whose worst-case
-  // staged entry count keeps NSTAGE stages within a quarter of the SM's smem
-  const int budget = (c->max_smem_optin - 1024) / (R <= 2 ? 4 : 2);
+  // staged entry count keeps NSTAGE stages within the CTA's share of the SM's smem
+  const int budget = (c->max_smem_optin - 1024) / ctas_target;
   int tr_idx = 3;  // 256 rows
   if (c->tune_rows_per_tile > 0) {
     tr_idx = 0;
@@ -380,11 +398,13 @@ cudaError_t launch_sgd_hogwild(fmb200_ctx* c, const DataSlot& d) {
 
   // hot-feature damping is compiled in only when the hottest feature's expected
   // concurrency makes q = c*lr*(1+reg) non-negligible for this launch geometry
-  const double rows_in_flight_guess =
-      std::min<double>((double)d.n_rows, (double)c->sm_count * 4 * (threads / 32) * (32.0 / (G * S)));
-  const double q_max = (double)d.max_feat_cnt * rows_in_flight_guess / (double)d.n_rows * c->hp.lr *
+  const double rows_per_cta_step = (double)(threads / 32) * (32.0 / (G * S)) * U;
+  const double flight_guess =
+      std::min<double>((double)d.n_rows, (double)c->sm_count * ctas_target * rows_per_cta_step);
+  const double q_max = (double)d.max_feat_cnt * flight_guess / (double)d.n_rows * c->hp.lr *
                        (1.0 + std::max(c->hp.regw, c->hp.regv));
   const bool damp = c->tune_damp == 1 || (c->tune_damp == 0 && q_max > 0.25);
+
   KernelFn fn = pick_kernel(G, S, R, damp);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
@@ -419,13 +439,10 @@ cudaError_t launch_sgd_hogwild(fmb200_ctx* c, const DataSlot& d) {
   a.regv = (float)c->hp.regv;
   a.min_target = (float)c->hp.min_target;
   a.max_target = (float)c->hp.max_target;
-  a.w0_accum = c->d_w0_accum;
-  a.done = c->d_done;
   a.feat_cnt = d.feat_cnt;
-  {
-    const double in_flight = std::min<double>((double)d.n_rows, (double)grid * (threads / 32) * (32.0 / (G * S)));
-    a.conc_scale = (float)(in_flight / (double)d.n_rows);
-  }
+  a.conc_scale = (float)(std::min<double>((double)d.n_rows, (double)grid * rows_per_cta_step) /
+                         (double)d.n_rows);
+  a.w0_conc = (float)std::min<double>((double)d.n_rows, (double)grid * TR);
   fn<<<grid, threads, smem, c->stream>>>(a);
   c->launches++;
   c->last_cfg = EpochConfig{G, S, TR, grid, threads, smem, damp ? 1 : 0};

@@ -215,6 +215,46 @@ __global__ void cnt_to_float_kernel(unsigned int* cnt, uint32_t n, unsigned int*
   if ((threadIdx.x & 31) == 0) atomicMax(out_max, m);
 }
 
+// Structural check of the row offsets + the numbers the epoch launcher needs.
+// out[0] = error bits (1: row_ptr[0] != 0, 2: not monotone, 4: row_ptr[n] != nnz, 8: row too long)
+// out[1] = longest row; out[2..6] = worst 4-aligned entry span of any 32<<i row tile
+__global__ void csr_inspect_kernel(const uint64_t* __restrict__ rp, uint64_t n_rows, uint64_t nnz,
+                                   unsigned int* out) {
+  unsigned int err = 0, longest = 0;
+  unsigned int span[5] = {0, 0, 0, 0, 0};
+  for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n_rows;
+       r += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t a = rp[r], b = rp[r + 1];
+    if (b < a) err |= 2u;
+    else if (b - a > 0xffffffffull) err |= 8u;
+    else longest = max(longest, (unsigned int)(b - a));
+    if ((r & 31) == 0) {
+#pragma unroll
+      for (int i = 0; i < 5; i++) {
+        const uint64_t TR = 32ull << i;
+        if ((r & (TR - 1)) == 0) {
+          const uint64_t r1 = min(r + TR, n_rows);
+          const uint64_t ab = a & ~3ull, ae = (rp[r1] + 3ull) & ~3ull;
+          const uint64_t sp = ae >= ab ? ae - ab : 0;
+          span[i] = max(span[i], sp > 0xffffffffull ? 0xffffffffu : (unsigned int)sp);
+        }
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (rp[0] != 0) err |= 1u;
+    if (rp[n_rows] != nnz) err |= 4u;
+  }
+  if (err) atomicOr(out + 0, err);
+  longest = __reduce_max_sync(0xffffffffu, longest);
+  if ((threadIdx.x & 31) == 0 && longest) atomicMax(out + 1, longest);
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    const unsigned int m = __reduce_max_sync(0xffffffffu, span[i]);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out + 2 + i, m);
+  }
+}
+
 static int grid_for(fmb200_ctx* c, uint64_t work) {
   uint64_t blocks = (work + 255) / 256;
   return (int)std::max<uint64_t>(1, std::min<uint64_t>(blocks, (uint64_t)c->sm_count * 8));
@@ -244,6 +284,13 @@ cudaError_t launch_scale_p32(fmb200_ctx* c, float factor) {
 cudaError_t launch_max_col(fmb200_ctx* c, const uint32_t* col, uint64_t nnz,
                            unsigned int* out_max) {
   max_col_kernel<<<grid_for(c, nnz), 256, 0, c->stream>>>(col, nnz, out_max);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_csr_inspect(fmb200_ctx* c, const uint64_t* rp, uint64_t n_rows, uint64_t nnz,
+                               unsigned int* out8) {
+  csr_inspect_kernel<<<grid_for(c, n_rows ? n_rows : 1), 256, 0, c->stream>>>(rp, n_rows, nnz, out8);
   c->launches++;
   return cudaGetLastError();
 }

