@@ -37,12 +37,15 @@
 //        c = rows in flight = min(N, grid * rows_per_tile).
 //      - w_i, V_i (template flag DAMP, on when some feature is hot enough to
 //        matter): c_i = max(1, count_i * W / N) from a per-feature occurrence table
-//        built at upload (W = rows being processed concurrently),
-//        h_w = x^2 + regw,  h_V = x^2 * sum_f (s_f - v_if x)^2 + regv.
+//        built at upload (W = rows being processed concurrently).
+//      - every block a row touches contracts the SAME residual, so all of them use
+//        the row's JOINT curvature h = h_loss * (1 + sum_i x_i^2 + sum_i |d p/d V_i|^2)
+//        (+ the block's own regulariser) as their contraction rate.
 //
 // Algorithmic HBM traffic per example (roofline numerator, BASELINE.json):
 // 2*k*nnz*4 bytes (V rows read + written back).
 #include <algorithm>
+#include <cstdlib>
 
 #include "fm_rowgroup.cuh"
 #include "fmb200_internal.h"
@@ -72,6 +75,7 @@ struct HogwildArgs {
   const float* feat_cnt;  // occurrences of each feature in this data set (DAMP)
   float conc_scale;       // rows processed concurrently / n_rows: count -> concurrency
   float w0_conc;          // rows in flight w.r.t. the bias (tile granularity)
+  int dbg;                // development only (FMB200_DEBUG): 1 = skip V reductions, 2 = skip w reductions
 };
 
 __device__ __forceinline__ unsigned char* stage_base(unsigned char* smem, const HogwildArgs& a,
@@ -209,7 +213,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
       for (int u = 0; u < U; ++u) {
         if (U > 1 && rbase + u * rows_per_set >= rows_here) break;  // warp-uniform
         RG& gu = g[u];
-        const float part = gu.reduce(V4, a.w, a.gp, use_w, ids, xs, c, s);
+        const float part = gu.template reduce<DAMP>(V4, a.w, a.gp, use_w, ids, xs, c, s);
         const float p = w0 + part;
         float mult, curv;
         if (a.task == FMB200_TASK_REGRESSION) {
@@ -225,9 +229,12 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
           mult = -y[u] * (1.f - sg);
           curv = sg * (1.f - sg);
         }
+        // curvature of the loss along this row's whole parameter set: every block the
+        // row touches contracts the SAME residual, so they share one contraction rate
+        const float hjoint = DAMP ? curv * ((use_w0 ? 1.f : 0.f) + gu.hrow) : curv;
         if (valid[u] && lig == 0) {
           msum += mult;
-          hsum += curv;
+          hsum += hjoint;
         }
 
         // ---- fm_SGD write-back (fm_sgd.h:38-50) as L2 reductions ----
@@ -239,30 +246,24 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
           float sv = 1.f, sw = 1.f;
           if (DAMP) {
             const float conc = __ldg(a.feat_cnt + id) * a.conc_scale;  // expected concurrency
-            float n2 = gx * gx + gy * gy + gz * gz + gw * gw;           // |d p / d V_i|^2
-#pragma unroll
-            for (int o = 1; o < G; o <<= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
-            sv = gamma_scale(conc, lr * (n2 + a.regv));
-            sw = gamma_scale(conc, lr * (x2 + a.regw));
+            if (conc > 1.f) {
+              sv = gamma_scale(conc, lr * (hjoint + a.regv));
+              sw = gamma_scale(conc, lr * (hjoint + a.regw));
+            }
           }
-          if (on && c < a.gp) {
+          if (on && c < a.gp && !(a.dbg & 1)) {
             // -lr*(mult*(sum_f*x - v*x^2) + regv*v)
             red_add_f4(a.v + ((size_t)id * a.gp + c) * 4, sv * (nlr_mult * gx + nlr_regv * v.x),
                        sv * (nlr_mult * gy + nlr_regv * v.y), sv * (nlr_mult * gz + nlr_regv * v.z),
                        sv * (nlr_mult * gw + nlr_regv * v.w));
           }
-          if (on && use_w && c == 0) red_add_f(a.w + id, sw * (nlr_mult * x + nlr_regw * wv));
+          if (on && use_w && c == 0 && !(a.dbg & 2)) red_add_f(a.w + id, sw * (nlr_mult * x + nlr_regw * wv));
         };
 #pragma unroll
         for (int q = 0; q < R; ++q) {
           const int j = gu.beg + s + q * S;
           const bool on = j < gu.end;
-          if (DAMP) {
-            // the norm reduction shuffles across the G chunk lanes: keep the warp converged
-            if (__any_sync(0xffffffffu, on)) update(on, gu.idc[q], gu.xc[q], gu.vc[q], gu.wc[q]);
-          } else if (on) {
-            update(true, gu.idc[q], gu.xc[q], gu.vc[q], gu.wc[q]);
-          }
+          if (on) update(true, gu.idc[q], gu.xc[q], gu.vc[q], gu.wc[q]);
         }
         for (int q = R; q < gu.maxit; ++q) {
           const int j = gu.beg + s + q * S;
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
             if (c < a.gp) v = ld_cg_f4(V4 + (size_t)id * a.gp + c);
             if (use_w && c == 0) wv = ld_cg_f(a.w + id);
           }
-          if (DAMP || on) update(on, id, x, v, wv);
+          if (on) update(true, id, x, v, wv);
         }
       }
     }
@@ -443,6 +444,10 @@ cudaError_t launch_sgd_hogwild(fmb200_ctx* c, const DataSlot& d) {
   a.conc_scale = (float)(std::min<double>((double)d.n_rows, (double)grid * rows_per_cta_step) /
                          (double)d.n_rows);
   a.w0_conc = (float)std::min<double>((double)d.n_rows, (double)grid * TR);
+  {
+    const char* dbg = getenv("FMB200_DEBUG");
+    a.dbg = dbg ? atoi(dbg) : 0;
+  }
   fn<<<grid, threads, smem, c->stream>>>(a);
   c->launches++;
   c->last_cfg = EpochConfig{G, S, TR, grid, threads, smem, damp ? 1 : 0};

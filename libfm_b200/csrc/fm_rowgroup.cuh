@@ -33,6 +33,7 @@ struct RowGroup {
   uint32_t idc[R];  // cached feature ids
   int beg, end;     // this row's entries: [beg, end) in the id / value arrays
   int maxit;        // warp-uniform iteration count of the entry loop
+  float hrow;       // (WANT_H) curvature of the score w.r.t. all of this row's w/V blocks
 
   template <typename IdPtr, typename ValPtr>
   __device__ __forceinline__ void gather(const float4* __restrict__ V4,
@@ -63,16 +64,22 @@ struct RowGroup {
   }
 
   // Returns the score WITHOUT the bias term, replicated in all E lanes.
-  template <typename IdPtr, typename ValPtr>
+  // WANT_H additionally fills hrow = sum_i |d score / d (w_i, V_i)|^2, evaluated with
+  // the one-hot identity  A*k1 + (A-2)*sum_f s_f^2 + sum_f sum_i (v_if x_i)^2,
+  // A = sum_i x_i^2  (exact for x in {0,1}, a damping heuristic otherwise).
+  template <bool WANT_H, typename IdPtr, typename ValPtr>
   __device__ __forceinline__ float reduce(const float4* __restrict__ V4,
                                           const float* __restrict__ w, int gp, bool use_w,
                                           IdPtr ids, ValPtr xs, int c, int s) {
     acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float sq = 0.f, lin = 0.f;
+    float sq = 0.f, lin = 0.f, xx = 0.f;
     const int iters = (end - beg + S - 1) / S;
     maxit = __reduce_max_sync(0xffffffffu, iters);
 #pragma unroll
-    for (int it = 0; it < R; ++it) accumulate(vc[it], xc[it], wc[it], sq, lin);
+    for (int it = 0; it < R; ++it) {
+      accumulate(vc[it], xc[it], wc[it], sq, lin);
+      if (WANT_H && c == 0) xx += xc[it] * xc[it];
+    }
     const bool chunk_on = c < gp;
     for (int it = R; it < maxit; ++it) {
       const int j = beg + s + it * S;
@@ -84,6 +91,7 @@ struct RowGroup {
         if (chunk_on) v = ld_cg_f4(V4 + (size_t)id * gp + c);
         if (use_w && c == 0) wv = ld_cg_f(w + id);
         accumulate(v, x, wv, sq, lin);
+        if (WANT_H && c == 0) xx += x * x;
       }
     }
     // per-factor sums: reduce over the slot bits (lane strides G, 2G, ... < E)
@@ -97,9 +105,22 @@ struct RowGroup {
     // 0.5*(sum_f^2 - sumsq_f): the square term once per chunk (slot 0), the
     // rest from every lane; then reduce the scalar over the whole group
     float part = lin - 0.5f * sq;
-    if (s == 0) part += 0.5f * (acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w);
+    float s2 = 0.f;
+    if (s == 0) {
+      s2 = acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+      part += 0.5f * s2;
+    }
 #pragma unroll
     for (int o = 1; o < E; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (WANT_H) {
+#pragma unroll
+      for (int o = 1; o < E; o <<= 1) {
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        xx += __shfl_xor_sync(0xffffffffu, xx, o);
+      }
+      hrow = (use_w ? xx : 0.f) + fmaxf((xx - 2.f) * s2 + sq, 0.f);
+    }
     return part;
   }
 
@@ -109,7 +130,7 @@ struct RowGroup {
                                          const float* __restrict__ w, int gp, bool use_w,
                                          IdPtr ids, ValPtr xs, int beg_, int end_, int c, int s) {
     gather(V4, w, gp, use_w, ids, xs, beg_, end_, c, s);
-    return reduce(V4, w, gp, use_w, ids, xs, c, s);
+    return reduce<false>(V4, w, gp, use_w, ids, xs, c, s);
   }
 
   __device__ __forceinline__ void accumulate(const float4& v, float x, float wv, float& sq,

@@ -1,0 +1,109 @@
+"""GPU: the drop-in command line (bin/libFM, C++ host over the C ABI) against the
+stock reference binary (oracle/_ref/libFM, built from /root/reference in place and
+shipped to the GPU box) on BASELINE config C1: same flags -> same stdout lines,
+same -out / -save_model / -rlog files."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from libfm_b200 import synth
+from oracle.binding import REF_CLI, REF_CONVERT
+
+pytestmark = pytest.mark.gpu
+CLI = os.path.join(ROOT, "bin", "libFM")
+
+
+def _run(binary, args, cwd):
+    r = subprocess.run([binary] + args, capture_output=True, text=True, cwd=cwd, timeout=600)
+    return r
+
+
+@pytest.fixture(scope="module")
+def c1_files(tmp_path_factory):
+    d = tmp_path_factory.mktemp("c1")
+    synth.to_libfm_text(synth.plumbing_10k(), str(d / "train.libfm"))
+    synth.to_libfm_text(synth.plumbing_10k(seed=99, n_rows=2000), str(d / "test.libfm"))
+    return d
+
+
+def _need():
+    if not (os.path.exists(CLI) and os.path.exists(REF_CLI)):
+        pytest.skip("CLI binaries not built")
+
+
+def _iters(stdout):
+    return [l for l in stdout.splitlines() if l.startswith("#Iter=") or l.startswith("Final")]
+
+
+@pytest.mark.parametrize("task,extra", [("r", []), ("r", ["-regular", "0,0,0.01"]), ("c", ["-dim", "1,1,4"])])
+def test_cli_inorder_equals_reference_cli(c1_files, task, extra):
+    _need()
+    base = ["-task", task, "-train", "train.libfm", "-test", "test.libfm", "-method", "sgd",
+            "-dim", "1,1,8", "-iter", "3", "-learn_rate", "0.01", "-init_stdev", "0.1", "-seed", "42"]
+    if "-dim" in extra:
+        base = [a for i, a in enumerate(base) if not (a == "-dim" or (i > 0 and base[i - 1] == "-dim"))]
+    base += extra
+    ref = _run(REF_CLI, base + ["-out", "ref_pred.txt", "-save_model", "ref_model.txt", "-rlog", "ref_log.tsv"], c1_files)
+    ours = _run(CLI, base + ["-mode", "inorder", "-out", "our_pred.txt", "-save_model", "our_model.txt",
+                             "-rlog", "our_log.tsv"], c1_files)
+    assert ours.returncode == 0, ours.stderr
+    assert _iters(ours.stdout) == _iters(ref.stdout) and len(_iters(ref.stdout)) == 4
+    rd = lambda f: open(os.path.join(c1_files, f)).read()  # noqa: E731
+    if task == "r":
+        assert rd("our_pred.txt") == rd("ref_pred.txt")
+        assert rd("our_model.txt") == rd("ref_model.txt")
+    else:
+        a = np.loadtxt(os.path.join(c1_files, "our_pred.txt"))
+        b = np.loadtxt(os.path.join(c1_files, "ref_pred.txt"))
+        np.testing.assert_allclose(a, b, atol=2e-6)
+    # rlog: same header, same metric columns (time columns differ by construction)
+    lo, lr = rd("our_log.tsv").splitlines(), rd("ref_log.tsv").splitlines()
+    assert lo[0] == lr[0] and len(lo) == len(lr) == 4
+    hdr = lo[0].split("\t")
+    for a, b in zip(lo[1:], lr[1:]):
+        fa, fb = a.split("\t"), b.split("\t")
+        for name, x, y in zip(hdr, fa, fb):
+            if not name.startswith("time"):
+                assert x == y, (name, x, y)
+
+
+def test_cli_binary_input_equals_text_input(c1_files):
+    _need()
+    if not os.path.exists(REF_CONVERT):
+        pytest.skip("convert not built")
+    for stem in ("train", "test"):
+        r = _run(REF_CONVERT, ["--ifile", stem + ".libfm", "--ofilex", stem + ".bin.x", "--ofiley", stem + ".bin.y"], c1_files)
+        assert os.path.exists(os.path.join(c1_files, stem + ".bin.x")), r.stdout + r.stderr
+    base = ["-task", "r", "-method", "sgd", "-iter", "2", "-learn_rate", "0.01", "-seed", "7", "-mode", "inorder"]
+    t = _run(CLI, base + ["-train", "train.libfm", "-test", "test.libfm"], c1_files)
+    b = _run(CLI, base + ["-train", "train.bin", "-test", "test.bin"], c1_files)
+    assert t.returncode == 0 and b.returncode == 0, t.stderr + b.stderr
+    assert _iters(t.stdout) == _iters(b.stdout) and len(_iters(t.stdout)) == 3
+
+
+def test_cli_hogwild_tracks_reference(c1_files):
+    _need()
+    base = ["-task", "r", "-train", "train.libfm", "-test", "test.libfm", "-method", "sgd",
+            "-iter", "5", "-learn_rate", "0.01", "-seed", "42"]
+    ref = _run(REF_CLI, base, c1_files)
+    ours = _run(CLI, base, c1_files)  # default mode: hogwild
+    assert ours.returncode == 0, ours.stderr
+    val = lambda l: [float(t.split("=")[1]) for t in l.split("\t") if t.startswith(("Train", "Test"))]  # noqa: E731
+    a, b = val(_iters(ours.stdout)[-1]), val(_iters(ref.stdout)[-1])
+    assert abs(a[0] - b[0]) < 0.05 and abs(a[1] - b[1]) < 0.05, (a, b)
+
+
+def test_cli_load_model_roundtrip(c1_files):
+    _need()
+    base = ["-task", "r", "-train", "train.libfm", "-test", "test.libfm", "-method", "sgd",
+            "-learn_rate", "0.01", "-seed", "42", "-mode", "inorder"]
+    a = _run(CLI, base + ["-iter", "2", "-save_model", "m2.txt"], c1_files)
+    assert a.returncode == 0, a.stderr
+    # 0 further epochs from the checkpoint: Final must equal the 6-digit-rounded model's metrics
+    b = _run(CLI, base + ["-iter", "0", "-load_model", "m2.txt"], c1_files)
+    r = _run(REF_CLI, [x for x in base if x not in ("-mode", "inorder")] + ["-iter", "0", "-load_model", "m2.txt"], c1_files)
+    assert b.returncode == 0, b.stderr
+    assert _iters(b.stdout) == _iters(r.stdout)

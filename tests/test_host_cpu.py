@@ -1,0 +1,154 @@
+"""CPU: host-side logic -- loaders, model init/IO, sharding, gloo all-reduce."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from libfm_b200 import Data, FmError, FmModel, synth
+from libfm_b200 import dist as fdist
+from oracle import Ref, have_ref
+from oracle.binding import REF_CLI
+
+TRICKY = """# a comment line
+5 0:1 7:0.5
+
+   3.5\t2:1e-1   9:2   # trailing comment
+-1
++2 4:-3.25 4:1
+0 11:0
+"""
+
+
+@pytest.fixture()
+def tricky_file(tmp_path):
+    p = tmp_path / "tricky.libfm"
+    p.write_text(TRICKY)
+    return str(p)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_python_loader_matches_reference_loader(tricky_file):
+    rp, col, val, tgt, nf, mn, mx = Ref.load_data(tricky_file)
+    d = Data.load(tricky_file)
+    assert np.array_equal(d.row_ptr, rp) and np.array_equal(d.col, col)
+    assert np.array_equal(d.val, val) and np.array_equal(d.target, tgt)
+    assert d.num_feature == nf and d.min_target == mn and d.max_target == mx
+
+
+def test_python_loader_rejects_garbage(tmp_path):
+    p = tmp_path / "bad.libfm"
+    p.write_text("1 3:1 oops\n")
+    with pytest.raises(FmError, match="cannot parse line"):
+        Data.load(str(p))
+    with pytest.raises(FmError, match="unable to open"):
+        Data.load(str(tmp_path / "missing"))
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_model_init_draw_order_bit_exact():
+    fm = FmModel(37, 5)
+    fm.init_stdev = 0.1
+    fm.init(seed=42)
+    ref = Ref(37, 5, seed=42, init_stdev=0.1)
+    w0, w, v = ref.get_params()
+    assert fm.w0 == w0 and np.array_equal(fm.w, w) and np.array_equal(fm.v, v)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_model_text_checkpoint_readable_by_reference(tmp_path):
+    fm = FmModel(12, 3)
+    fm.init_stdev = 0.1
+    fm.init(seed=3)
+    fm.w0, fm.w[:] = 0.125, np.linspace(-1, 1, 12)
+    path = str(tmp_path / "m.txt")
+    fm.saveModel(path)
+    ref = Ref(12, 3, seed=1)
+    assert ref.load_model(path) == 1
+    w0, w, v = ref.get_params()
+    g6 = lambda a: np.array([float("%g" % x) for x in np.ravel(a)]).reshape(np.shape(a))  # noqa: E731
+    assert w0 == 0.125 and np.array_equal(w, g6(fm.w)) and np.array_equal(v, g6(fm.v))
+    ref_path = str(tmp_path / "ref.txt")
+    ref.save_model(ref_path)
+    assert open(ref_path).read() == open(path).read()  # idempotent text form
+
+
+def test_cli_loader_lines_match_reference(tricky_file, tmp_path):
+    """bin/libFM parses its inputs before it needs a GPU: its loader summary lines must
+    equal the reference CLI's, byte for byte."""
+    cli = os.path.join(ROOT, "bin", "libFM")
+    if not (os.path.exists(cli) and os.path.exists(REF_CLI)):
+        pytest.skip("CLI binaries not built")
+    args = ["-task", "r", "-train", tricky_file, "-test", tricky_file, "-method", "sgd",
+            "-iter", "0", "-learn_rate", "0.01", "-seed", "1"]
+    ours = subprocess.run([cli] + args, capture_output=True, text=True)
+    ref = subprocess.run([REF_CLI] + args, capture_output=True, text=True)
+    pick = lambda s: [l for l in s.splitlines() if l.startswith("num_rows=") or l.startswith("has x")]  # noqa: E731
+    assert pick(ours.stdout) == pick(ref.stdout) and len(pick(ref.stdout)) == 6
+    import torch
+    if not torch.cuda.is_available():
+        assert ours.returncode != 0 and "no CPU path" in ours.stderr
+
+
+def test_cli_flag_errors_match_reference_text(tmp_path):
+    cli = os.path.join(ROOT, "bin", "libFM")
+    if not os.path.exists(cli):
+        pytest.skip("CLI not built")
+    r = subprocess.run([cli, "-task", "r", "-bogus", "1"], capture_output=True, text=True)
+    assert "ERROR: the parameter bogus does not exist" in r.stderr
+    r = subprocess.run([cli, "-task", "r", "-task", "c"], capture_output=True, text=True)
+    assert "ERROR: the parameter task is already specified" in r.stderr
+    r = subprocess.run([cli, "-task", "r", "-train", "x", "-test", "y"], capture_output=True, text=True)
+    assert "outside the libfm_b200 scope" in r.stderr  # default method is mcmc (libfm.cpp:118)
+
+
+def test_shard_bounds_partition_rows():
+    for n in (0, 1, 7, 1000, 1_000_209):
+        for world in (1, 2, 3, 8):
+            b = [fdist.shard_bounds(n, world, r) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+    d = synth.ragged(101, 30, 5, seed=1)
+    parts = [fdist.shard(d, 4, r) for r in range(4)]
+    assert sum(p.num_cases for p in parts) == d.num_cases
+    assert np.array_equal(np.concatenate([p.col for p in parts]), d.col)
+    assert np.array_equal(np.concatenate([p.target for p in parts]), d.target)
+    assert all(p.row_ptr[0] == 0 for p in parts)
+
+
+_WORKER = r"""
+import os, sys, json
+sys.path.insert(0, %(root)r)
+import torch, torch.distributed as dist
+from libfm_b200 import dist as fdist, synth
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
+world, rank = 2, int(sys.argv[1])
+# each rank holds a different replica; after the epoch's all-reduce both hold the mean
+p = torch.arange(10, dtype=torch.float32) * (rank + 1)
+fdist.allreduce_mean_(p, world)
+assert torch.allclose(p, torch.arange(10, dtype=torch.float32) * 1.5), p
+d = synth.ragged(101, 30, 5, seed=1)
+mine = fdist.shard(d, world, rank)
+sq, ab, ok, n = fdist.sum_metrics(float(mine.num_cases), 2.0, mine.num_cases, mine.num_cases, world)
+assert n == d.num_cases and ok == d.num_cases and sq == float(d.num_cases) and ab == 4.0
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_world_size_2_gloo_allreduce_and_shards(tmp_path):
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER % {"root": ROOT, "port": port})
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
