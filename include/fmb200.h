@@ -37,7 +37,7 @@ typedef struct fmb200_ctx fmb200_ctx;
 #define FMB200_MODE_INORDER 0 /* sequential-equivalent: rows strictly in file order, fp64
                                  state; bit-compatible with fm_learn_sgd_element::learn */
 #define FMB200_MODE_HOGWILD 1 /* throughput: rows in parallel, fp32 state, red.global.add
-                                 write-back, CTA-local bias carry */
+                                 write-back, damped per-tile bias step */
 
 #define FMB200_MAX_SLOTS 8
 
@@ -107,8 +107,11 @@ int fmb200_last_epoch_config(fmb200_ctx* ctx, int* lanes_per_row, int* slots, in
 /* hogwild tuning knobs; 0 keeps the default.  ctas_per_sm bounds the number of
  * rows in flight (the Hogwild staleness window).  damp: 0 = automatic hot-feature
  * damping (on when the hottest feature's expected concurrency matters), 1 = force
- * on, -1 = force off (plain summed Hogwild on w/V). */
-int fmb200_set_tuning(fmb200_ctx* ctx, int ctas_per_sm, int rows_per_tile, int threads, int damp);
+ * on, -1 = force off (plain summed Hogwild on w/V).  variant: 0 = automatic choice
+ * of the epoch kernel, 1 = sub-warp row-group kernel, 2 = one-lane-per-row kernel
+ * (k <= 8, rows of <= 4 entries; ignored when not applicable). */
+int fmb200_set_tuning(fmb200_ctx* ctx, int ctas_per_sm, int rows_per_tile, int threads, int damp,
+                      int variant);
 
 #ifdef __cplusplus
 }

@@ -41,7 +41,7 @@ SYMBOLS = {
     "fmb200_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),
     "fmb200_kernel_launches": (C.c_int, [_ctx, _u64p]),
     "fmb200_last_epoch_config": (C.c_int, [_ctx] + [_intp] * 7),
-    "fmb200_set_tuning": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "fmb200_set_tuning": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
 }
 
 _lib = None

@@ -30,10 +30,11 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-
 CU_SOURCES = {
     "fm_context.cu": [],
     "fm_hogwild.cu": [],
+    "fm_rowlane.cu": [],
     "fm_predict.cu": [],
     "fm_inorder.cu": ["--fmad=false"],
 }
-CU_HEADERS = ["fm_device.cuh", "fm_rowgroup.cuh", "fmb200_internal.h"]
+CU_HEADERS = ["fm_device.cuh", "fm_rowgroup.cuh", "fm_hogwild_common.cuh", "fmb200_internal.h"]
 
 
 def _newer(target: str, deps: list[str]) -> bool:

@@ -477,7 +477,8 @@ int fmb200_last_epoch_config(fmb200_ctx* c, int* lanes_per_row, int* slots, int*
   return 0;
 }
 
-int fmb200_set_tuning(fmb200_ctx* c, int ctas_per_sm, int rows_per_tile, int threads, int damp) {
+int fmb200_set_tuning(fmb200_ctx* c, int ctas_per_sm, int rows_per_tile, int threads, int damp,
+                      int variant) {
   NEED_CTX(c);
   if (threads && (threads % 32 != 0 || threads < 32 || threads > 256))
     return fail("threads must be a multiple of 32 in [32,256]");
@@ -487,6 +488,7 @@ int fmb200_set_tuning(fmb200_ctx* c, int ctas_per_sm, int rows_per_tile, int thr
   c->tune_rows_per_tile = rows_per_tile;
   c->tune_threads = threads;
   c->tune_damp = damp;
+  c->tune_variant = variant;
   return 0;
 }
 

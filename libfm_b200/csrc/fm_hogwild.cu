@@ -47,75 +47,10 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include "fm_hogwild_common.cuh"
 #include "fm_rowgroup.cuh"
-#include "fmb200_internal.h"
 
 namespace fmb {
-
-constexpr int HW_NSTAGE = 3;
-constexpr int HW_MAX_THREADS = 256;
-constexpr int HW_HDR_BYTES = 128;  // mbarriers [0,64) + per-tile bias accumulators [64,128)
-
-struct HogwildArgs {
-  const uint64_t* row_ptr;
-  const uint32_t* col;
-  const float* val;
-  const float* target;
-  uint64_t n_rows;
-  uint32_t n_tiles;
-  int tile_rows;       // TR (multiple of 32)
-  uint32_t tile_cap;   // max staged entries per tile (multiple of 4)
-  uint32_t stage_bytes;
-  float* w0;
-  float* w;
-  float* v;
-  int gp;  // float4 chunks per V row (kp / 4)
-  int use_w0, use_w, task;
-  float lr, reg0, regw, regv, min_target, max_target;
-  const float* feat_cnt;  // occurrences of each feature in this data set (DAMP)
-  float conc_scale;       // rows processed concurrently / n_rows: count -> concurrency
-  float w0_conc;          // rows in flight w.r.t. the bias (tile granularity)
-  int dbg;                // development only (FMB200_DEBUG): 1 = skip V reductions, 2 = skip w reductions
-};
-
-__device__ __forceinline__ unsigned char* stage_base(unsigned char* smem, const HogwildArgs& a,
-                                                     int stage) {
-  return smem + HW_HDR_BYTES + (size_t)stage * a.stage_bytes;
-}
-
-// TMA producer: stage one tile whose entry range [nb, ne) is already known.
-__device__ __forceinline__ void issue_tile(const HogwildArgs& a, unsigned char* smem,
-                                           uint64_t* bars, uint32_t tile, int stage,
-                                           uint64_t policy, uint64_t nb, uint64_t ne) {
-  const int TR = a.tile_rows;
-  const uint64_t r0 = (uint64_t)tile * TR;
-  const uint64_t ab = nb & ~3ull;
-  const uint64_t ae = (ne + 3ull) & ~3ull;
-  const uint32_t ebytes = (uint32_t)(ae - ab) * 4u;
-  const uint32_t rp_bytes = (uint32_t)(TR + 2) * 8u;
-  const uint32_t y_bytes = (uint32_t)TR * 4u;
-  unsigned char* sb = stage_base(smem, a, stage);
-  uint64_t* bar = bars + stage;
-  mbar_arrive_expect_tx(bar, rp_bytes + y_bytes + 2u * ebytes);
-  bulk_g2s_hint(sb, a.row_ptr + r0, rp_bytes, bar, policy);
-  bulk_g2s_hint(sb + rp_bytes, a.target + r0, y_bytes, bar, policy);
-  if (ebytes) {
-    unsigned char* cb = sb + rp_bytes + y_bytes;
-    bulk_g2s_hint(cb, a.col + ab, ebytes, bar, policy);
-    bulk_g2s_hint(cb + (size_t)a.tile_cap * 4u, a.val + ab, ebytes, bar, policy);
-  }
-}
-
-// gamma(c, u) = (1 - (1-u)^c) / (c*u): scale of each of c concurrent steps whose
-// sequential execution would contract the residual by (1-u) per step
-__device__ __forceinline__ float gamma_scale(float c, float u) {
-  if (c <= 1.f || u <= 0.f) return 1.f;
-  const float q = c * u;
-  if (q < 1e-3f) return 1.f;
-  const float a = fmaxf(1.f - u, 0.f);
-  const float ac = a > 0.f ? __expf(c * __logf(a)) : 0.f;
-  return fminf(1.f, (1.f - ac) / q);
-}
 
 template <int G, int S, int R, int U, bool DAMP>
 __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
@@ -309,7 +244,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
 }
 
 // ---------------------------------------------------------------------------
-using KernelFn = void (*)(const HogwildArgs);
+using KernelFn = HogwildKernelFn;
 
 template <int G, int S, int R, int U>
 KernelFn pick_damp(bool damp) {
@@ -366,9 +301,85 @@ void pick_geometry(int kp, uint64_t n_rows, uint64_t nnz, int* G, int* S) {
   *S = s;
 }
 
+static HogwildArgs make_args(fmb200_ctx* c, const DataSlot& d, uint64_t n_tiles, int TR,
+                             uint32_t tile_cap, uint32_t sbytes) {
+  HogwildArgs a;
+  a.row_ptr = d.row_ptr;
+  a.col = d.col;
+  a.val = d.val;
+  a.target = d.target;
+  a.n_rows = d.n_rows;
+  a.n_tiles = (uint32_t)n_tiles;
+  a.tile_rows = TR;
+  a.tile_cap = tile_cap;
+  a.stage_bytes = sbytes;
+  a.w0 = c->p32.w0();
+  a.w = c->p32.w();
+  a.v = c->p32.v();
+  a.gp = c->kp / 4;
+  a.use_w0 = c->k0;
+  a.use_w = c->k1;
+  a.task = c->hp.task;
+  a.lr = (float)c->hp.lr;
+  a.reg0 = (float)c->hp.reg0;
+  a.regw = (float)c->hp.regw;
+  a.regv = (float)c->hp.regv;
+  a.min_target = (float)c->hp.min_target;
+  a.max_target = (float)c->hp.max_target;
+  a.feat_cnt = d.feat_cnt;
+  a.conc_scale = 1.f;
+  a.w0_conc = 1.f;
+  const char* dbg = getenv("FMB200_DEBUG");
+  a.dbg = dbg ? atoi(dbg) : 0;
+  return a;
+}
+
+// one-lane-per-row variant (fm_rowlane.cu) for k <= 8 and rows of at most 4 entries
+static cudaError_t launch_rowlane(fmb200_ctx* c, const DataSlot& d, bool* handled) {
+  *handled = false;
+  const int gp = c->kp / 4;
+  if (gp < 1 || gp > 2 || d.max_row_nnz > 4 || c->tune_variant == 1) return cudaSuccess;
+  int threads = c->tune_threads > 0 ? std::min(c->tune_threads, HW_MAX_THREADS) : 256;
+  int tr_idx = 0;
+  while ((32 << (tr_idx + 1)) <= threads) tr_idx++;
+  threads = 32 << tr_idx;  // rows_per_tile == threads: lane t owns row t of the tile
+  const int TR = threads;
+  const uint32_t cap = (d.tile_span[tr_idx] + 3u) & ~3u;
+  const uint32_t sbytes = (uint32_t)((TR + 2) * 8 + TR * 4 + 2 * cap * 4 + 15) & ~15u;
+  const int smem = HW_HDR_BYTES + HW_NSTAGE * (int)sbytes;
+  const double flight_guess = std::min<double>((double)d.n_rows, (double)c->sm_count * 3 * TR);
+  const double q_max = (double)d.max_feat_cnt * flight_guess / (double)d.n_rows * c->hp.lr *
+                       (1.0 + std::max(c->hp.regw, c->hp.regv));
+  const bool damp = c->tune_damp == 1 || (c->tune_damp == 0 && q_max > 0.25);
+  HogwildKernelFn fn = pick_rowlane_kernel(gp, (int)d.max_row_nnz, damp);
+  if (fn == nullptr) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorInvalidConfiguration;
+  const int per_sm = c->tune_ctas_per_sm > 0 ? std::min(c->tune_ctas_per_sm, occ) : occ;
+  const uint64_t n_tiles = (d.n_rows + TR - 1) / TR;
+  const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)c->sm_count * per_sm);
+  HogwildArgs a = make_args(c, d, n_tiles, TR, cap, sbytes);
+  a.conc_scale = (float)(std::min<double>((double)d.n_rows, (double)grid * TR) / (double)d.n_rows);
+  a.w0_conc = (float)std::min<double>((double)d.n_rows, (double)grid * TR);
+  fn<<<grid, threads, smem, c->stream>>>(a);
+  c->launches++;
+  c->last_cfg = EpochConfig{1, (int)std::max<uint32_t>(1, d.max_row_nnz), TR, grid, threads, smem, damp ? 1 : 0};
+  *handled = true;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_sgd_hogwild(fmb200_ctx* c, const DataSlot& d) {
   if (c->kp / 4 > 32) return cudaErrorInvalidValue;  // num_factor <= 128 in this mode
   if (d.n_rows == 0) return cudaSuccess;
+  {
+    bool handled = false;
+    cudaError_t e = launch_rowlane(c, d, &handled);
+    if (e != cudaSuccess || handled) return e;
+  }
   int G, S;
   pick_geometry(c->kp, d.n_rows, d.nnz, &G, &S);
   const double avg = (double)d.nnz / (double)d.n_rows;
@@ -417,37 +428,10 @@ cudaError_t launch_sgd_hogwild(fmb200_ctx* c, const DataSlot& d) {
   const uint64_t n_tiles = (d.n_rows + TR - 1) / TR;
   const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)c->sm_count * per_sm);
 
-  HogwildArgs a;
-  a.row_ptr = d.row_ptr;
-  a.col = d.col;
-  a.val = d.val;
-  a.target = d.target;
-  a.n_rows = d.n_rows;
-  a.n_tiles = (uint32_t)n_tiles;
-  a.tile_rows = TR;
-  a.tile_cap = (d.tile_span[tr_idx] + 3u) & ~3u;
-  a.stage_bytes = sbytes;
-  a.w0 = c->p32.w0();
-  a.w = c->p32.w();
-  a.v = c->p32.v();
-  a.gp = c->kp / 4;
-  a.use_w0 = c->k0;
-  a.use_w = c->k1;
-  a.task = c->hp.task;
-  a.lr = (float)c->hp.lr;
-  a.reg0 = (float)c->hp.reg0;
-  a.regw = (float)c->hp.regw;
-  a.regv = (float)c->hp.regv;
-  a.min_target = (float)c->hp.min_target;
-  a.max_target = (float)c->hp.max_target;
-  a.feat_cnt = d.feat_cnt;
+  HogwildArgs a = make_args(c, d, n_tiles, TR, (d.tile_span[tr_idx] + 3u) & ~3u, sbytes);
   a.conc_scale = (float)(std::min<double>((double)d.n_rows, (double)grid * rows_per_cta_step) /
                          (double)d.n_rows);
   a.w0_conc = (float)std::min<double>((double)d.n_rows, (double)grid * TR);
-  {
-    const char* dbg = getenv("FMB200_DEBUG");
-    a.dbg = dbg ? atoi(dbg) : 0;
-  }
   fn<<<grid, threads, smem, c->stream>>>(a);
   c->launches++;
   c->last_cfg = EpochConfig{G, S, TR, grid, threads, smem, damp ? 1 : 0};

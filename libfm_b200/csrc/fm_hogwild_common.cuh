@@ -1,0 +1,82 @@
+// fm_hogwild_common.cuh -- pieces shared by the two HOGWILD epoch kernels
+// (fm_hogwild.cu: sub-warp row groups, any k / row length; fm_rowlane.cu: one lane
+// per row for short rows with k <= 8): launch arguments, the TMA tile producer and
+// the mean-field step scale.  See fm_hogwild.cu for the design notes.
+#pragma once
+#include "fm_device.cuh"
+#include "fmb200_internal.h"
+
+namespace fmb {
+
+constexpr int HW_NSTAGE = 3;
+constexpr int HW_MAX_THREADS = 256;
+constexpr int HW_HDR_BYTES = 128;  // mbarriers [0,64) + per-tile bias accumulators [64,128)
+
+struct HogwildArgs {
+  const uint64_t* row_ptr;
+  const uint32_t* col;
+  const float* val;
+  const float* target;
+  uint64_t n_rows;
+  uint32_t n_tiles;
+  int tile_rows;       // TR (multiple of 32)
+  uint32_t tile_cap;   // max staged entries per tile (multiple of 4)
+  uint32_t stage_bytes;
+  float* w0;
+  float* w;
+  float* v;
+  int gp;  // float4 chunks per V row (kp / 4)
+  int use_w0, use_w, task;
+  float lr, reg0, regw, regv, min_target, max_target;
+  const float* feat_cnt;  // occurrences of each feature in this data set (DAMP)
+  float conc_scale;       // rows processed concurrently / n_rows: count -> concurrency
+  float w0_conc;          // rows in flight w.r.t. the bias (tile granularity)
+  int dbg;                // development only (FMB200_DEBUG): 1 = skip V reductions, 2 = skip w reductions
+};
+
+__device__ __forceinline__ unsigned char* stage_base(unsigned char* smem, const HogwildArgs& a,
+                                                     int stage) {
+  return smem + HW_HDR_BYTES + (size_t)stage * a.stage_bytes;
+}
+
+// TMA producer: stage one tile whose entry range [nb, ne) is already known.
+__device__ __forceinline__ void issue_tile(const HogwildArgs& a, unsigned char* smem,
+                                           uint64_t* bars, uint32_t tile, int stage,
+                                           uint64_t policy, uint64_t nb, uint64_t ne) {
+  const int TR = a.tile_rows;
+  const uint64_t r0 = (uint64_t)tile * TR;
+  const uint64_t ab = nb & ~3ull;
+  const uint64_t ae = (ne + 3ull) & ~3ull;
+  const uint32_t ebytes = (uint32_t)(ae - ab) * 4u;
+  const uint32_t rp_bytes = (uint32_t)(TR + 2) * 8u;
+  const uint32_t y_bytes = (uint32_t)TR * 4u;
+  unsigned char* sb = stage_base(smem, a, stage);
+  uint64_t* bar = bars + stage;
+  mbar_arrive_expect_tx(bar, rp_bytes + y_bytes + 2u * ebytes);
+  bulk_g2s_hint(sb, a.row_ptr + r0, rp_bytes, bar, policy);
+  bulk_g2s_hint(sb + rp_bytes, a.target + r0, y_bytes, bar, policy);
+  if (ebytes) {
+    unsigned char* cb = sb + rp_bytes + y_bytes;
+    bulk_g2s_hint(cb, a.col + ab, ebytes, bar, policy);
+    bulk_g2s_hint(cb + (size_t)a.tile_cap * 4u, a.val + ab, ebytes, bar, policy);
+  }
+}
+
+// gamma(c, u) = (1 - (1-u)^c) / (c*u): scale of each of c concurrent steps whose
+// sequential execution would contract the residual by (1-u) per step
+__device__ __forceinline__ float gamma_scale(float c, float u) {
+  if (c <= 1.f || u <= 0.f) return 1.f;
+  const float q = c * u;
+  if (q < 1e-3f) return 1.f;
+  const float a = fmaxf(1.f - u, 0.f);
+  const float ac = a > 0.f ? __expf(c * __logf(a)) : 0.f;
+  return fminf(1.f, (1.f - ac) / q);
+}
+
+
+using HogwildKernelFn = void (*)(const HogwildArgs);
+
+// fm_rowlane.cu: kernel for (float4 chunks per row gp in {1,2}, rows of at most Z entries)
+HogwildKernelFn pick_rowlane_kernel(int gp, int max_row_nnz, bool damp);
+
+}  // namespace fmb

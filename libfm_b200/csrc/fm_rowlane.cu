@@ -1,0 +1,277 @@
+// fm_rowlane.cu -- HOGWILD epoch kernel for SHORT ROWS and k <= 8: one lane per row.
+//
+// Same algorithm, staging and concurrency control as fm_sgd_hogwild_kernel
+// (fm_hogwild.cu) -- this is the instruction-lean mapping for the one-hot
+// "MovieLens" shape (BASELINE config C2: k=8, 2 nnz/row).  The sub-warp row-group
+// kernel spends ~30 warp instructions per example there (segmented shuffles,
+// per-lane address arithmetic replicated over 4 lanes per row); the measured
+// bound of the shape is the SM's L1TEX/LSU rate for scattered 32-byte sectors
+// (profiles/r01_red_microbench.txt), so everything else has to get out of the way.
+//
+// Mapping
+//  * lane t of a CTA owns row t of the staged tile (rows_per_tile == blockDim.x);
+//    all per-row math (fm_model::predict, reference fm_model.h:105-127; fm_SGD,
+//    fm_sgd.h:33-51) happens in that lane's registers: no shuffles for sums.
+//  * a factor row of k=8 floats is one 32-byte sector = two float4.  Letting every
+//    lane fetch its own two halves would cost two sector requests per row and
+//    instruction; instead lane PAIRS (2j, 2j+1) co-operate: instruction A fetches
+//    the row of lane 2j (even lane low half, odd lane high half), instruction B the
+//    row of lane 2j+1, and one 4-float __shfl_xor swaps the halves into place.
+//    The write-back mirrors it (swap, then two red.global.add.v4.f32 whose lane
+//    pairs cover one full sector each).  Sector requests per (row, entry): 1 gather
+//    + 1 reduction for V, 1 + 1 for w -- the minimum for this layout.
+//  * GP == 1 (k <= 4): a factor row is a single float4; every lane fetches its own.
+#include <algorithm>
+
+#include "fm_hogwild_common.cuh"
+
+namespace fmb {
+
+template <int GP>
+struct FactorRow {
+  float v[4 * GP];
+};
+
+template <int GP, int Z, bool DAMP>
+__global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const HogwildArgs a) {
+  constexpr int K = 4 * GP;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  float* s_acc = reinterpret_cast<float*>(smem + 64);
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int odd = lane & 1;
+  const int TR = a.tile_rows;  // == blockDim.x
+
+  uint64_t policy = 0;
+  if (tid == 0) {
+    for (int i = 0; i < HW_NSTAGE; i++) mbar_init(bars + i, 1);
+    for (int i = 0; i < 12; i++) s_acc[i] = 0.f;
+    fence_mbar_init();
+    policy = policy_evict_first();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 0; i < HW_NSTAGE; i++) {
+      const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)i * gridDim.x;
+      if (t < a.n_tiles) {
+        const uint64_t r0 = t * TR, r1 = min(r0 + (uint64_t)TR, a.n_rows);
+        issue_tile(a, smem, bars, (uint32_t)t, i, policy, __ldg(a.row_ptr + r0),
+                   __ldg(a.row_ptr + r1));
+      }
+    }
+  }
+
+  const float4* V4 = reinterpret_cast<const float4*>(a.v);
+  const bool use_w = a.use_w != 0;
+  const bool use_w0 = a.use_w0 != 0;
+  const float lr = a.lr;
+
+  int it = 0;
+  for (uint64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+    const int stage = it % HW_NSTAGE;
+    const uint32_t parity = (uint32_t)(it / HW_NSTAGE) & 1u;
+    const uint64_t nt = tile + (uint64_t)HW_NSTAGE * gridDim.x;
+    uint64_t nt_nb = 0, nt_ne = 0;
+    if (tid == 0 && nt < a.n_tiles) {
+      const uint64_t r0 = nt * TR, r1 = min(r0 + (uint64_t)TR, a.n_rows);
+      nt_nb = __ldg(a.row_ptr + r0);
+      nt_ne = __ldg(a.row_ptr + r1);
+    }
+    const float w0 = use_w0 ? ld_cg_f(a.w0) : 0.f;
+    mbar_wait(bars + stage, parity);
+
+    unsigned char* sb = stage_base(smem, a, stage);
+    const uint64_t* rp = reinterpret_cast<const uint64_t*>(sb);
+    const float* ys = reinterpret_cast<const float*>(sb + (size_t)(TR + 2) * 8);
+    const uint32_t* ids = reinterpret_cast<const uint32_t*>(sb + (size_t)(TR + 2) * 8 + (size_t)TR * 4);
+    const float* xs = reinterpret_cast<const float*>(ids + a.tile_cap);
+    const uint64_t row0 = tile * (uint64_t)TR;
+    const int rows_here = (int)min((uint64_t)TR, a.n_rows - row0);
+    const uint64_t ab = rp[0] & ~3ull;
+
+    // ---- this lane's row ----
+    const bool valid = tid < rows_here;
+    int beg = 0, cnt = 0;
+    float y = 0.f;
+    if (valid) {
+      beg = (int)(rp[tid] - ab);
+      cnt = (int)(rp[tid + 1] - ab) - beg;
+      y = ys[tid];
+    }
+    uint32_t id[Z];
+    float x[Z], wv[Z];
+    FactorRow<GP> vr[Z];
+    // ---- gather: all entries in flight at once ----
+#pragma unroll
+    for (int e = 0; e < Z; ++e) {
+      const bool on = e < cnt;
+      id[e] = on ? ids[beg + e] : 0u;
+      x[e] = on ? xs[beg + e] : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < Z; ++e) {
+      if (GP == 2) {
+        const uint32_t pid = __shfl_xor_sync(0xffffffffu, id[e], 1);
+        const uint32_t idA = odd ? pid : id[e];  // row of the even lane
+        const uint32_t idB = odd ? id[e] : pid;  // row of the odd lane
+        const float4 la = ld_cg_f4(V4 + (size_t)idA * 2 + odd);
+        const float4 lb = ld_cg_f4(V4 + (size_t)idB * 2 + odd);
+        const float4 send = odd ? la : lb;
+        float4 recv;
+        recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+        recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+        recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1);
+        recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1);
+        const float4 lo = odd ? recv : la;
+        const float4 hi = odd ? lb : recv;
+        vr[e].v[0] = lo.x; vr[e].v[1] = lo.y; vr[e].v[2] = lo.z; vr[e].v[3] = lo.w;
+        vr[e].v[4] = hi.x; vr[e].v[5] = hi.y; vr[e].v[6] = hi.z; vr[e].v[7] = hi.w;
+      } else {
+        const float4 l = ld_cg_f4(V4 + (size_t)id[e]);
+        vr[e].v[0] = l.x; vr[e].v[1] = l.y; vr[e].v[2] = l.z; vr[e].v[3] = l.w;
+      }
+      wv[e] = (use_w && e < cnt) ? ld_cg_f(a.w + id[e]) : 0.f;
+    }
+
+    // ---- fm_model::predict in registers (fm_model.h:105-127) ----
+    float sum[K];
+#pragma unroll
+    for (int f = 0; f < K; ++f) sum[f] = 0.f;
+    float sq = 0.f, lin = 0.f, xx = 0.f;
+#pragma unroll
+    for (int e = 0; e < Z; ++e) {
+#pragma unroll
+      for (int f = 0; f < K; ++f) {
+        const float d = vr[e].v[f] * x[e];
+        sum[f] += d;
+        sq += d * d;
+      }
+      lin += wv[e] * x[e];
+      xx += x[e] * x[e];
+    }
+    float s2 = 0.f;
+#pragma unroll
+    for (int f = 0; f < K; ++f) s2 += sum[f] * sum[f];
+    const float p = w0 + lin + 0.5f * (s2 - sq);
+
+    // ---- loss multiplier (fm_learn_sgd_element.h:58-65) ----
+    float mult, curv;
+    if (a.task == FMB200_TASK_REGRESSION) {
+      const float pc = fmaxf(a.min_target, fminf(a.max_target, p));
+      mult = pc - y;
+      const float den = p - y;
+      curv = (pc == p) ? 1.f : (fabsf(den) > 1e-12f ? fminf(fmaxf(mult / den, 0.f), 1.f) : 0.f);
+    } else {
+      const float sg = 1.f / (1.f + __expf(-y * p));
+      mult = -y * (1.f - sg);
+      curv = sg * (1.f - sg);
+    }
+    if (!valid) {
+      mult = 0.f;
+      curv = 0.f;
+    }
+    // joint curvature of the row's whole parameter set (see fm_hogwild.cu)
+    const float hrow = (use_w ? xx : 0.f) + fmaxf((xx - 2.f) * s2 + sq, 0.f);
+    const float hjoint = DAMP ? curv * ((use_w0 ? 1.f : 0.f) + hrow) : curv;
+
+    // ---- fm_SGD write-back (fm_sgd.h:38-50) ----
+    const float nlr_mult = -lr * mult;
+    const float nlr_regv = -lr * a.regv;
+    const float nlr_regw = -lr * a.regw;
+#pragma unroll
+    for (int e = 0; e < Z; ++e) {
+      const bool on = e < cnt;
+      float sv = 1.f, sw = 1.f;
+      if (DAMP) {
+        const float conc = on ? __ldg(a.feat_cnt + id[e]) * a.conc_scale : 0.f;
+        if (conc > 1.f) {
+          sv = gamma_scale(conc, lr * (hjoint + a.regv));
+          sw = gamma_scale(conc, lr * (hjoint + a.regw));
+        }
+      }
+      const float x2 = x[e] * x[e];
+      float d[K];
+#pragma unroll
+      for (int f = 0; f < K; ++f)
+        d[f] = sv * (nlr_mult * (sum[f] * x[e] - vr[e].v[f] * x2) + nlr_regv * vr[e].v[f]);
+      if (GP == 2) {
+        // swap halves inside the lane pair so that each reduction covers a full sector
+        const uint32_t pid = __shfl_xor_sync(0xffffffffu, id[e], 1);
+        const bool pon = __shfl_xor_sync(0xffffffffu, (int)on, 1) != 0;
+        const uint32_t idA = odd ? pid : id[e];
+        const uint32_t idB = odd ? id[e] : pid;
+        const bool onA = odd ? pon : on;
+        const bool onB = odd ? on : pon;
+        float4 send, keep;
+        if (odd) {
+          send = make_float4(d[0], d[1], d[2], d[3]);  // my low half goes to the even lane
+          keep = make_float4(d[4], d[5], d[6], d[7]);
+        } else {
+          send = make_float4(d[4], d[5], d[6], d[7]);  // my high half goes to the odd lane
+          keep = make_float4(d[0], d[1], d[2], d[3]);
+        }
+        float4 recv;
+        recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+        recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+        recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1);
+        recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1);
+        // row A (even lane's): even writes its low half, odd writes the received high half
+        const float4 va = odd ? recv : keep;
+        // row B (odd lane's): even writes the received low half, odd writes its high half
+        const float4 vb = odd ? keep : recv;
+        if (onA && !(a.dbg & 1)) red_add_f4(a.v + ((size_t)idA * 2 + odd) * 4, va.x, va.y, va.z, va.w);
+        if (onB && !(a.dbg & 1)) red_add_f4(a.v + ((size_t)idB * 2 + odd) * 4, vb.x, vb.y, vb.z, vb.w);
+      } else {
+        if (on && !(a.dbg & 1)) red_add_f4(a.v + (size_t)id[e] * 4, d[0], d[1], d[2], d[3]);
+      }
+      if (on && use_w && !(a.dbg & 2)) red_add_f(a.w + id[e], sw * (nlr_mult * x[e] + nlr_regw * wv[e]));
+    }
+
+    // ---- bias: one damped reduction into the global w0 per tile ----
+    const int slot = it % 3;
+    if (use_w0) {
+      const float msum = warp_sum(mult);
+      const float hsum = warp_sum(valid ? hjoint : 0.f);
+      if (lane == 0) {
+        atomicAdd(&s_acc[4 * slot + 0], msum);
+        atomicAdd(&s_acc[4 * slot + 1], hsum);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (nt < a.n_tiles) issue_tile(a, smem, bars, (uint32_t)nt, stage, policy, nt_nb, nt_ne);
+      if (use_w0) {
+        const float T = (float)rows_here;
+        const float M = s_acc[4 * slot + 0] + T * a.reg0 * w0;
+        const float hbar = s_acc[4 * slot + 1] / T;
+        const float gsc = gamma_scale(fmaxf(a.w0_conc, 1.f), lr * (hbar + a.reg0));
+        red_add_f(a.w0, -lr * gsc * M);
+        s_acc[4 * slot + 0] = 0.f;
+        s_acc[4 * slot + 1] = 0.f;
+      }
+    }
+  }
+}
+
+template <int GP, int Z>
+static HogwildKernelFn pick_d(bool damp) {
+  return damp ? fm_sgd_rowlane_kernel<GP, Z, true> : fm_sgd_rowlane_kernel<GP, Z, false>;
+}
+
+template <int GP>
+static HogwildKernelFn pick_z(int z, bool damp) {
+  if (z <= 1) return pick_d<GP, 1>(damp);
+  if (z <= 2) return pick_d<GP, 2>(damp);
+  if (z <= 4) return pick_d<GP, 4>(damp);
+  return nullptr;
+}
+
+HogwildKernelFn pick_rowlane_kernel(int gp, int max_row_nnz, bool damp) {
+  if (gp == 1) return pick_z<1>(max_row_nnz, damp);
+  if (gp == 2) return pick_z<2>(max_row_nnz, damp);
+  return nullptr;
+}
+
+}  // namespace fmb

@@ -86,6 +86,7 @@ struct fmb200_ctx {
   fmb::EpochConfig last_cfg;
   int tune_ctas_per_sm = 0, tune_rows_per_tile = 0, tune_threads = 0;
   int tune_damp = 0;  // 0 auto, 1 force on, -1 force off
+  int tune_variant = 0;  // 0 auto, 1 row-group kernel, 2 row-lane kernel when eligible
 };
 
 namespace fmb {

@@ -220,8 +220,9 @@ class FmLearnSgdElement:
         self._check(self.lib.fmb200_set_mode(self._ctx, mode))
         self.mode = mode
 
-    def set_tuning(self, ctas_per_sm=0, rows_per_tile=0, threads=0, damp=0) -> None:
-        self._check(self.lib.fmb200_set_tuning(self._ctx, ctas_per_sm, rows_per_tile, threads, damp))
+    def set_tuning(self, ctas_per_sm=0, rows_per_tile=0, threads=0, damp=0, variant=0) -> None:
+        self._check(self.lib.fmb200_set_tuning(self._ctx, ctas_per_sm, rows_per_tile, threads, damp,
+                                               variant))
 
     def push_hparams(self) -> None:
         self._check(self.lib.fmb200_set_hparams(self._ctx, self.task, self.learn_rate, self.fm.reg0,

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from libfm_b200 import FmLearnSgdElement, FmModel, MODE_HOGWILD, MODE_INORDER, synth
 
-def run(name, d, k, task=0, tunings=((0,0,0,0),), epochs=5, inorder=False):
+def run(name, d, k, task=0, tunings=((0,0,0,0,0),), epochs=5, inorder=False):
     n = d.num_feature
     fm = FmModel(n, k); fm.init_stdev = 0.1; fm.init_numpy(42)
     l = FmLearnSgdElement(fm, mode=MODE_HOGWILD)
@@ -29,10 +29,10 @@ def run(name, d, k, task=0, tunings=((0,0,0,0),), epochs=5, inorder=False):
 
 if __name__ == "__main__":
     d = synth.movielens_1m_shaped(seed=7)
-    tun = [(0,0,0,0), (0,0,0,1), (2,0,0,0), (0,0,128,0)]
+    tun = [(0,0,0,0,0), (0,0,0,-1,0), (0,0,128,0,0), (4,0,0,-1,0), (0,0,0,0,1), (0,0,0,-1,1)]
     run("C2", d, 8, tunings=tun, inorder=True)
     dz = synth.movielens_1m_shaped(seed=7, zipf=1.0)
-    run("C2zipf", dz, 8, tunings=[(0,0,0,0),(0,0,0,-1)])
+    run("C2zipf", dz, 8, tunings=[(0,0,0,0,0),(0,0,0,0,1)])
     d3 = synth.multi_field(1_000_000, 39, 1_000_000, 11); d3.binarize_targets()
     run("C3-1M", d3, 64, task=1)
     run("k128", d3, 128, task=1)

@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from libfm_b200 import FmLearnSgdElement, FmModel, MODE_HOGWILD, synth
 
-def run(name, d, k, k0=True, k1=True, tune=(0,0,0,-1), epochs=6):
+def run(name, d, k, k0=True, k1=True, tune=(0,0,0,-1,0), epochs=6):
     fm = FmModel(d.num_feature, k, k0, k1); fm.init_stdev = 0.1; fm.init_numpy(42)
     l = FmLearnSgdElement(fm, mode=MODE_HOGWILD)
     l.task, l.learn_rate = 0, 0.01

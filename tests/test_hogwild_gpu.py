@@ -111,6 +111,38 @@ def test_disjoint_rows_match_oracle_without_bias(built_lib):
     l.close()
 
 
+@pytest.mark.parametrize("k,maxnnz", [(8, 2), (8, 4), (4, 3), (3, 1), (7, 4)])
+def test_rowlane_and_rowgroup_kernels_agree(k, maxnnz, built_lib):
+    """The two HOGWILD epoch kernels implement the same step: on rows that share no
+    feature (any schedule is sequentially equivalent) both must equal the oracle."""
+    n_rows = 4000
+    r = np.random.default_rng(k * 10 + maxnnz)
+    lens = r.integers(0, maxnnz + 1, n_rows)
+    rp = np.zeros(n_rows + 1, dtype=np.uint64)
+    rp[1:] = np.cumsum(lens)
+    n = int(rp[-1]) + 5
+    d = Data(rp, r.permutation(n)[: int(rp[-1])].astype(np.uint32),
+             r.standard_normal(int(rp[-1])).astype(np.float32),
+             r.integers(1, 6, n_rows).astype(np.float32), n)
+    cfg = _cfg(n, k, k0=0, lr=0.05, regs=(0, 0.01, 0.02))
+    init = _rand_init(n, k, 5, stdev=0.3)
+    init32 = tuple(np.float32(x).astype(np.float64) for x in init)
+    p = _port(cfg, init32)
+    p.sgd_epoch(d, 0, 0.05, 1.0, 5.0)
+    for variant, lanes in ((1, None), (2, 1)):
+        l = make_learner(cfg, init, mode=MODE_HOGWILD)
+        l.set_tuning(variant=variant)
+        l.sgd_epoch(d)
+        if lanes is not None:
+            assert l.epoch_config()["lanes_per_row"] == lanes
+        else:
+            assert l.epoch_config()["lanes_per_row"] >= 1 and l.epoch_config()["rows_per_tile"] >= 32
+        l.pull_params()
+        np.testing.assert_allclose(l.fm.w, p.w, atol=2e-6)
+        np.testing.assert_allclose(l.fm.v, p.v, atol=2e-6)
+        l.close()
+
+
 def test_zero_learning_rate_epoch_is_identity(built_lib):
     d = synth.two_field(20000, 300, 200, seed=8)
     cfg = _cfg(500, 8, lr=0.0)
@@ -193,7 +225,7 @@ def test_c2_size_properties(built_lib):
     assert np.isfinite(l.fm.v).all() and np.isfinite(l.fm.w).all() and np.isfinite(l.fm.w0)
     assert hist[0] < base and hist[-1] < hist[0]
     cfgd = l.epoch_config()
-    assert cfgd["lanes_per_row"] == 2 and cfgd["slots"] == 2  # k=8, 2 nnz/row geometry
+    assert cfgd["lanes_per_row"] == 1 and cfgd["slots"] == 2  # one-lane-per-row kernel, 2 nnz/row
     # INORDER evaluate of the same state agrees with the fp32 evaluate
     l.set_mode(MODE_INORDER)
     assert abs(l.evaluate(d) - hist[-1]) < 1e-5
