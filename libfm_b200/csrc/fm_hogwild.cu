@@ -76,7 +76,6 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
   uint64_t policy = 0;
   if (tid == 0) {
     for (int i = 0; i < HW_NSTAGE; i++) mbar_init(bars + i, 1);
-    for (int i = 0; i < 12; i++) s_acc[i] = 0.f;
     fence_mbar_init();
     policy = policy_evict_first();
   }
@@ -112,7 +111,9 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
       nt_nb = __ldg(a.row_ptr + r0);
       nt_ne = __ldg(a.row_ptr + r1);
     }
-    const float w0 = use_w0 ? ld_cg_f(a.w0) : 0.f;  // tile-start bias
+    BiasFetch bias;
+    bias.slot = reinterpret_cast<float*>(smem + 192);
+    bias.issue(a, use_w0, tid);
     mbar_wait(bars + stage, parity);
 
     unsigned char* sb = stage_base(smem, a, stage);
@@ -125,6 +126,8 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
     const uint64_t ab = rp[0] & ~3ull;
 
     float msum = 0.f, hsum = 0.f;
+    float w0 = 0.f;
+    bool have_w0 = false;
     for (int rbase = warp * RPW; rbase < rows_here; rbase += U * rows_per_set) {
       RG g[U];
       float y[U];
@@ -142,6 +145,10 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
           y[u] = ys[r];
         }
         g[u].gather(V4, a.w, a.gp, use_w, ids, xs, beg, end, c, s);
+      }
+      if (!have_w0) {  // after this tile's first gathers are in flight
+        w0 = bias.get(use_w0, tid, it, (int)blockDim.x);
+        have_w0 = true;
       }
       // ---- phase 2: score, multiplier, write-back, one row set at a time ----
 #pragma unroll
@@ -217,27 +224,27 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
       }
     }
 
+    if (!have_w0) w0 = bias.get(use_w0, tid, it, (int)blockDim.x);  // warps without rows still sync
     // ---- bias: one damped reduction into the global w0 per tile ----
-    const int slot = it % 3;
+    float2* s_part = reinterpret_cast<float2*>(s_acc) + (it & 1) * 8;  // [2 slots][8 warps]
     if (use_w0) {
       msum = warp_sum(msum);
       hsum = warp_sum(hsum);
-      if (lane == 0) {
-        atomicAdd(&s_acc[4 * slot + 0], msum);
-        atomicAdd(&s_acc[4 * slot + 1], hsum);
-      }
+      if (lane == 0) s_part[warp] = make_float2(msum, hsum);
     }
-    __syncthreads();  // every warp is done with this stage; accumulators complete
+    __syncthreads();  // every warp is done with this stage; partials complete
     if (tid == 0) {
       if (nt < a.n_tiles) issue_tile(a, smem, bars, (uint32_t)nt, stage, policy, nt_nb, nt_ne);
       if (use_w0) {
+        float M = 0.f, H = 0.f;
+        for (int i = 0; i < nwarp; i++) {
+          M += s_part[i].x;
+          H += s_part[i].y;
+        }
         const float T = (float)rows_here;
-        const float M = s_acc[4 * slot + 0] + T * a.reg0 * w0;  // sum_t (mult_t + reg0*w0)
-        const float hbar = s_acc[4 * slot + 1] / T;
-        const float gsc = gamma_scale(fmaxf(a.w0_conc, 1.f), lr * (hbar + a.reg0));
-        red_add_f(a.w0, -lr * gsc * M);
-        s_acc[4 * slot + 0] = 0.f;  // next written after two more barriers
-        s_acc[4 * slot + 1] = 0.f;
+        M += T * a.reg0 * w0;  // sum_t (mult_t + reg0*w0)
+        const float gsc = gamma_scale(fmaxf(a.w0_conc, 1.f), lr * (H / T + a.reg0));
+        if (!(a.dbg & 4)) red_add_f(a.w0, -lr * gsc * M);
       }
     }
   }

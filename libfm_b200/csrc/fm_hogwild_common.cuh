@@ -10,7 +10,7 @@ namespace fmb {
 
 constexpr int HW_NSTAGE = 3;
 constexpr int HW_MAX_THREADS = 256;
-constexpr int HW_HDR_BYTES = 128;  // mbarriers [0,64) + per-tile bias accumulators [64,128)
+constexpr int HW_HDR_BYTES = 256;  // mbarriers [0,64) + per-warp bias partials [64,192): [2 slots][8 warps] float2
 
 struct HogwildArgs {
   const uint64_t* row_ptr;
@@ -73,6 +73,33 @@ __device__ __forceinline__ float gamma_scale(float c, float u) {
   return fminf(1.f, (1.f - ac) / q);
 }
 
+
+// The bias sector is reduced into by every CTA once per tile; loads of it queue behind
+// those reductions at its single L2 slice.  So ONE lane per CTA fetches it per tile
+// (issued at the top of the tile, consumed after the gathers are in flight) and hands
+// it to the other warps through shared memory + named barrier 1.
+struct BiasFetch {
+  float* slot;   // [2] floats in the smem header, indexed by tile parity
+  float pending; // lane 0 of warp 0: the in-flight value
+  __device__ __forceinline__ void issue(const HogwildArgs& a, bool use_w0, int tid) {
+    pending = 0.f;
+    if (use_w0 && tid == 0 && !(a.dbg & 8)) pending = ld_cg_f(a.w0);
+  }
+  // returns the tile's bias in every thread of the CTA
+  __device__ __forceinline__ float get(bool use_w0, int tid, int it, int nthreads) {
+    if (!use_w0) return 0.f;
+    float* s = slot + (it & 1);
+    if (tid < 32) {
+      const float v = __shfl_sync(0xffffffffu, pending, 0);
+      if (tid == 0) *s = v;
+      __threadfence_block();
+      named_bar_arrive(1, nthreads);
+      return v;
+    }
+    named_bar_sync(1, nthreads);
+    return *s;
+  }
+};
 
 using HogwildKernelFn = void (*)(const HogwildArgs);
 

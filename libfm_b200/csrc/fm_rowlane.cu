@@ -47,7 +47,6 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
   uint64_t policy = 0;
   if (tid == 0) {
     for (int i = 0; i < HW_NSTAGE; i++) mbar_init(bars + i, 1);
-    for (int i = 0; i < 12; i++) s_acc[i] = 0.f;
     fence_mbar_init();
     policy = policy_evict_first();
   }
@@ -79,7 +78,9 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
       nt_nb = __ldg(a.row_ptr + r0);
       nt_ne = __ldg(a.row_ptr + r1);
     }
-    const float w0 = use_w0 ? ld_cg_f(a.w0) : 0.f;
+    BiasFetch bias;
+    bias.slot = reinterpret_cast<float*>(smem + 192);
+    bias.issue(a, use_w0, tid);
     mbar_wait(bars + stage, parity);
 
     unsigned char* sb = stage_base(smem, a, stage);
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
     float s2 = 0.f;
 #pragma unroll
     for (int f = 0; f < K; ++f) s2 += sum[f] * sum[f];
+    const float w0 = bias.get(use_w0, tid, it, (int)blockDim.x);
     const float p = w0 + lin + 0.5f * (s2 - sq);
 
     // ---- loss multiplier (fm_learn_sgd_element.h:58-65) ----
@@ -230,26 +232,25 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
     }
 
     // ---- bias: one damped reduction into the global w0 per tile ----
-    const int slot = it % 3;
+    float2* s_part = reinterpret_cast<float2*>(s_acc) + (it & 1) * 8;  // [2 slots][8 warps]
     if (use_w0) {
       const float msum = warp_sum(mult);
       const float hsum = warp_sum(valid ? hjoint : 0.f);
-      if (lane == 0) {
-        atomicAdd(&s_acc[4 * slot + 0], msum);
-        atomicAdd(&s_acc[4 * slot + 1], hsum);
-      }
+      if (lane == 0) s_part[tid >> 5] = make_float2(msum, hsum);
     }
     __syncthreads();
     if (tid == 0) {
       if (nt < a.n_tiles) issue_tile(a, smem, bars, (uint32_t)nt, stage, policy, nt_nb, nt_ne);
       if (use_w0) {
+        float M = 0.f, H = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) {
+          M += s_part[i].x;
+          H += s_part[i].y;
+        }
         const float T = (float)rows_here;
-        const float M = s_acc[4 * slot + 0] + T * a.reg0 * w0;
-        const float hbar = s_acc[4 * slot + 1] / T;
-        const float gsc = gamma_scale(fmaxf(a.w0_conc, 1.f), lr * (hbar + a.reg0));
-        red_add_f(a.w0, -lr * gsc * M);
-        s_acc[4 * slot + 0] = 0.f;
-        s_acc[4 * slot + 1] = 0.f;
+        M += T * a.reg0 * w0;
+        const float gsc = gamma_scale(fmaxf(a.w0_conc, 1.f), lr * (H / T + a.reg0));
+        if (!(a.dbg & 4)) red_add_f(a.w0, -lr * gsc * M);
       }
     }
   }

@@ -38,6 +38,10 @@ __global__ void k(float* tab, uint32_t rows32 /*number of 32B rows*/, int niter,
     if (MODE == 4) { uint32_t r = hash(base + (lane >> 3)) % (rows32 / 4); red4(tab + (size_t)r * 32 + (lane & 7) * 4, 1e-9f); }
     if (MODE == 5) { uint32_t r = hash(base + (lane >> 2)) % (rows32 / 2); red4(tab + (size_t)r * 16 + (lane & 3) * 4, 1e-9f); }
     if (MODE == 6) { uint32_t r = hash(base + (lane >> 2)) % rows32; red2(tab + (size_t)r * 8 + (lane & 3) * 2, 1e-9f); }
+    if (MODE == 8) { uint32_t r = hash(base + lane) % rows32; red1(tab + r, 1e-9f); }
+    if (MODE == 9) { uint32_t r = hash(base + lane) % rows32; acc += __ldcg(tab + r); }
+    if (MODE == 10) { uint32_t r = hash(base + lane) % rows32; acc += __ldcg(tab + r); red1(tab + r, 1e-9f); }
+    if (MODE == 11) { uint32_t r = hash(base + lane) % rows32; acc += __ldcg(tab + (size_t)r * 8); red1(tab + (size_t)r * 8, 1e-9f); }
     if (MODE == 7) { uint32_t r = hash(base + (lane >> 1)) % rows32; float4 v = __ldcg(reinterpret_cast<const float4*>(tab + (size_t)r * 8 + (lane & 1) * 4)); acc += v.x + v.w; }
   }
   if (acc == 123.456f) *sink = acc;
@@ -59,17 +63,15 @@ int main() {
   float *tab, *sink; size_t bytes = 512ull << 20;
   cudaMalloc(&tab, bytes); cudaMemset(tab, 0, bytes); cudaMalloc(&sink, 4);
   const int niter = 256, block = 256;
-  for (uint32_t rows32 : {9746u, 1000000u}) {
-    for (int grid : {148 * 4, 74 * 4, 37 * 4}) {
-      run<0>("v4 paired (16 sectors)", tab, rows32, grid, block, niter, sink);
-      run<1>("scalar 16 lanes (16 sectors)", tab, rows32, grid, block, niter, sink);
-      run<2>("scalar 32 lanes (32 sectors)", tab, rows32, grid, block, niter, sink);
-      run<3>("v4 32 lanes (32 half-sectors)", tab, rows32, grid, block, niter, sink);
-      run<4>("v4 8 lanes/line (4 lines,16 sectors)", tab, rows32, grid, block, niter, sink);
-      run<5>("v4 4 lanes/64B (8x64B,16 sectors)", tab, rows32, grid, block, niter, sink);
-      run<6>("v2 4 lanes/32B row (8 sectors)", tab, rows32, grid, block, niter, sink);
-      run<7>("LOAD v4 paired (16 sectors)", tab, rows32, grid, block, niter, sink);
-    }
+  for (uint32_t rows32 : {9746u, 82248u}) {
+    int grid = 148 * 4;
+    run<2>("scalar RED 32 lanes, 32B stride", tab, rows32, grid, block, niter, sink);
+    run<8>("scalar RED 32 lanes, contiguous 4B", tab, rows32, grid, block, niter, sink);
+    run<9>("scalar LD  32 lanes, contiguous 4B", tab, rows32, grid, block, niter, sink);
+    run<10>("LD+RED same word, contiguous 4B", tab, rows32, grid, block, niter, sink);
+    run<11>("LD+RED same word, 32B stride", tab, rows32, grid, block, niter, sink);
+    run<0>("v4 paired RED (16 sectors)", tab, rows32, grid, block, niter, sink);
+    run<7>("v4 paired LD (16 sectors)", tab, rows32, grid, block, niter, sink);
   }
   return 0;
 }

@@ -14,19 +14,8 @@ def run(name, d, k, k0=True, k1=True, tune=(0,0,0,-1,0), epochs=6):
     l.close()
 
 d = synth.movielens_1m_shaped(seed=7)
-for dbg in ("0", "1", "2", "3"):
+for dbg in ("0", "4", "8", "12"):
     os.environ["FMB200_DEBUG"] = dbg
-    run("C2 full", d, 8)
+    run("C2 full (4=no w0 RED, 8=no w0 load)", d, 8)
 os.environ["FMB200_DEBUG"] = "0"
-run("C2 k1=0 (no w)", d, 8, k1=False)
-run("C2 k0=0 (no bias)", d, 8, k0=False)
-run("C2 k0=k1=0", d, 8, k0=False, k1=False)
-os.environ["FMB200_DEBUG"] = "1"
-run("C2 k0=k1=0 noVred", d, 8, k0=False, k1=False)
-os.environ["FMB200_DEBUG"] = "0"
-# spread the same rows over 16x more features: fewer same-line collisions
-import numpy as np
-d2 = synth.two_field(1_000_209, 6040 * 16, 3706 * 16, seed=7)
-run("C2 16x features", d2, 8)
-os.environ["FMB200_DEBUG"] = "3"
-run("C2 16x features noRED", d2, 8)
+run("C2 k0=0", d, 8, k0=False)
