@@ -94,7 +94,7 @@ int fmb200_predict(fmb200_ctx* ctx, int slot, int transform, double* out);
 
 /* Multi-GPU plumbing (row sharding + one all-reduce of w0|w|V per epoch; the
  * reference has no equivalent).  The HOGWILD state is one packed fp32 device
- * buffer [w0, pad x3 | w[n] padded to 4 | V[n][kp]]; the caller all-reduces it
+ * buffer [w0, pad x3 | w (strided) | V[n][kp]]; the caller all-reduces it
  * (NCCL) and calls fmb200_scale_params(1/G).  Both run on fmb200_stream(). */
 int fmb200_params_device(fmb200_ctx* ctx, void** device_ptr, uint64_t* n_floats);
 int fmb200_scale_params(fmb200_ctx* ctx, double factor);

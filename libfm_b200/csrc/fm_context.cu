@@ -166,7 +166,8 @@ int fmb200_create(fmb200_ctx** out, int device, uint32_t n_attr, int num_factor,
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
-  const uint64_t n4 = ((uint64_t)n_attr + 3) & ~3ull;
+  c->p32.ws = (n_attr <= 131072u) ? 8 : 1;
+  const uint64_t n4 = ((uint64_t)n_attr * c->p32.ws + 3) & ~3ull;
   c->p32.off_w = 4;
   c->p32.off_v = 4 + n4;
   c->p32.n_floats = 4 + n4 + (uint64_t)n_attr * c->kp;
@@ -306,7 +307,7 @@ int fmb200_set_params(fmb200_ctx* c, double w0, const double* w, const double* v
   // fp32 packed image
   std::vector<float> h32(c->p32.n_floats, 0.f);
   h32[0] = (float)w0;
-  for (uint32_t i = 0; i < n; i++) h32[c->p32.off_w + i] = (float)w[i];
+  for (uint32_t i = 0; i < n; i++) h32[c->p32.off_w + (size_t)i * c->p32.ws] = (float)w[i];
   float* hv32 = h32.data() + c->p32.off_v;
   for (int f = 0; f < k; f++)
     for (uint32_t i = 0; i < n; i++) hv32[(size_t)i * kp + f] = (float)v[(size_t)f * n + i];
@@ -336,7 +337,7 @@ int fmb200_get_params(fmb200_ctx* c, double* w0, double* w, double* v) {
     CK(cudaMemcpyAsync(h.data(), c->p32.base, h.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     *w0 = h[0];
-    for (uint32_t i = 0; i < n; i++) w[i] = h[c->p32.off_w + i];
+    for (uint32_t i = 0; i < n; i++) w[i] = h[c->p32.off_w + (size_t)i * c->p32.ws];
     const float* hv = h.data() + c->p32.off_v;
     for (int f = 0; f < k; f++)
       for (uint32_t i = 0; i < n; i++) v[(size_t)f * n + i] = hv[(size_t)i * kp + f];

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
           end = (int)(rp[r + 1] - ab);
           y[u] = ys[r];
         }
-        g[u].gather(V4, a.w, a.gp, use_w, ids, xs, beg, end, c, s);
+        g[u].gather(V4, a.w, a.gp, a.ws, use_w, ids, xs, beg, end, c, s);
       }
       if (!have_w0) {  // after this tile's first gathers are in flight
         w0 = bias.get(use_w0, tid, it, (int)blockDim.x);
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
       for (int u = 0; u < U; ++u) {
         if (U > 1 && rbase + u * rows_per_set >= rows_here) break;  // warp-uniform
         RG& gu = g[u];
-        const float part = gu.template reduce<DAMP>(V4, a.w, a.gp, use_w, ids, xs, c, s);
+        const float part = gu.template reduce<DAMP>(V4, a.w, a.gp, a.ws, use_w, ids, xs, c, s);
         const float p = w0 + part;
         float mult, curv;
         if (a.task == FMB200_TASK_REGRESSION) {
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
                        sv * (nlr_mult * gy + nlr_regv * v.y), sv * (nlr_mult * gz + nlr_regv * v.z),
                        sv * (nlr_mult * gw + nlr_regv * v.w));
           }
-          if (on && use_w && c == 0 && !(a.dbg & 2)) red_add_f(a.w + id, sw * (nlr_mult * x + nlr_regw * wv));
+          if (on && use_w && c == 0 && !(a.dbg & 2)) red_add_f(a.w + (size_t)id * a.ws, sw * (nlr_mult * x + nlr_regw * wv));
         };
 #pragma unroll
         for (int q = 0; q < R; ++q) {
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
             x = xs[j];
             id = ids[j];
             if (c < a.gp) v = ld_cg_f4(V4 + (size_t)id * a.gp + c);
-            if (use_w && c == 0) wv = ld_cg_f(a.w + id);
+            if (use_w && c == 0) wv = ld_cg_f(a.w + (size_t)id * a.ws);
           }
           if (on) update(true, id, x, v, wv);
         }
@@ -324,6 +324,7 @@ static HogwildArgs make_args(fmb200_ctx* c, const DataSlot& d, uint64_t n_tiles,
   a.w = c->p32.w();
   a.v = c->p32.v();
   a.gp = c->kp / 4;
+  a.ws = c->p32.ws;
   a.use_w0 = c->k0;
   a.use_w = c->k1;
   a.task = c->hp.task;
@@ -357,7 +358,7 @@ static cudaError_t launch_rowlane(fmb200_ctx* c, const DataSlot& d, bool* handle
   const double flight_guess = std::min<double>((double)d.n_rows, (double)c->sm_count * 3 * TR);
   const double q_max = (double)d.max_feat_cnt * flight_guess / (double)d.n_rows * c->hp.lr *
                        (1.0 + std::max(c->hp.regw, c->hp.regv));
-  const bool damp = c->tune_damp == 1 || (c->tune_damp == 0 && q_max > 0.25);
+  const bool damp = c->tune_damp == 1 || (c->tune_damp == 0 && q_max > 0.5);
   HogwildKernelFn fn = pick_rowlane_kernel(gp, (int)d.max_row_nnz, damp);
   if (fn == nullptr) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -422,7 +423,7 @@ cudaError_t launch_sgd_hogwild(fmb200_ctx* c, const DataSlot& d) {
       std::min<double>((double)d.n_rows, (double)c->sm_count * ctas_target * rows_per_cta_step);
   const double q_max = (double)d.max_feat_cnt * flight_guess / (double)d.n_rows * c->hp.lr *
                        (1.0 + std::max(c->hp.regw, c->hp.regv));
-  const bool damp = c->tune_damp == 1 || (c->tune_damp == 0 && q_max > 0.25);
+  const bool damp = c->tune_damp == 1 || (c->tune_damp == 0 && q_max > 0.5);
 
   KernelFn fn = pick_kernel(G, S, R, damp);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

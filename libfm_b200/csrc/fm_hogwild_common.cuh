@@ -26,6 +26,7 @@ struct HogwildArgs {
   float* w;
   float* v;
   int gp;  // float4 chunks per V row (kp / 4)
+  int ws;  // stride of w in floats
   int use_w0, use_w, task;
   float lr, reg0, regw, regv, min_target, max_target;
   const float* feat_cnt;  // occurrences of each feature in this data set (DAMP)

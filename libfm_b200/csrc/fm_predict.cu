@@ -22,7 +22,7 @@ struct PredictArgs {
   const float* w0;
   const float* w;
   const float* v;
-  int gp, use_w0, use_w, task, transform;
+  int gp, ws, use_w0, use_w, task, transform;
   float min_target, max_target;
   double* out_pred;
   double* partials;
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) fm_predict32_kernel(const PredictArgs a) 
       y = __ldg(a.target + r);
     }
     RG g;
-    const float part = g.score(V4, a.w, a.gp, a.use_w != 0, a.col + beg, a.val + beg, 0,
+    const float part = g.score(V4, a.w, a.gp, a.ws, a.use_w != 0, a.col + beg, a.val + beg, 0,
                                (int)(end - beg), c, s);
     float p = w0 + part;
     if (valid && lig == 0) {
@@ -138,6 +138,7 @@ cudaError_t launch_predict32(fmb200_ctx* c, const DataSlot& d, int transform, do
   a.w = c->p32.w();
   a.v = c->p32.v();
   a.gp = c->kp / 4;
+  a.ws = c->p32.ws;
   a.use_w0 = c->k0;
   a.use_w = c->k1;
   a.task = c->hp.task;
@@ -162,7 +163,7 @@ __global__ void p64_to_p32_kernel(Params64 s, Params32 d, uint32_t n, int k, int
   }
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
        i += (uint64_t)gridDim.x * blockDim.x)
-    d.w()[i] = (float)s.w()[i];
+    d.w()[i * d.ws] = (float)s.w()[i];
   if (blockIdx.x == 0 && threadIdx.x == 0) d.w0()[0] = (float)s.w0()[0];
 }
 
@@ -176,7 +177,7 @@ __global__ void p32_to_p64_kernel(Params32 s, Params64 d, uint32_t n, int k, int
   }
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
        i += (uint64_t)gridDim.x * blockDim.x)
-    d.w()[i] = (double)s.w()[i];
+    d.w()[i] = (double)s.w()[i * s.ws];
   if (blockIdx.x == 0 && threadIdx.x == 0) d.w0()[0] = (double)s.w0()[0];
 }
 

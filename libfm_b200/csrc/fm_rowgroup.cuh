@@ -37,7 +37,7 @@ struct RowGroup {
 
   template <typename IdPtr, typename ValPtr>
   __device__ __forceinline__ void gather(const float4* __restrict__ V4,
-                                         const float* __restrict__ w, int gp, bool use_w,
+                                         const float* __restrict__ w, int gp, int ws, bool use_w,
                                          IdPtr ids, ValPtr xs, int beg_, int end_, int c, int s) {
     beg = beg_;
     end = end_;
@@ -55,7 +55,7 @@ struct RowGroup {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       float wv = 0.f;
       if (on && chunk_on) v = ld_cg_f4(V4 + (size_t)id * gp + c);
-      if (on && use_w && c == 0) wv = ld_cg_f(w + id);
+      if (on && use_w && c == 0) wv = ld_cg_f(w + (size_t)id * ws);
       idc[it] = id;
       xc[it] = x;
       vc[it] = v;
@@ -69,7 +69,7 @@ struct RowGroup {
   // A = sum_i x_i^2  (exact for x in {0,1}, a damping heuristic otherwise).
   template <bool WANT_H, typename IdPtr, typename ValPtr>
   __device__ __forceinline__ float reduce(const float4* __restrict__ V4,
-                                          const float* __restrict__ w, int gp, bool use_w,
+                                          const float* __restrict__ w, int gp, int ws, bool use_w,
                                           IdPtr ids, ValPtr xs, int c, int s) {
     acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float sq = 0.f, lin = 0.f, xx = 0.f;
@@ -89,7 +89,7 @@ struct RowGroup {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         float wv = 0.f;
         if (chunk_on) v = ld_cg_f4(V4 + (size_t)id * gp + c);
-        if (use_w && c == 0) wv = ld_cg_f(w + id);
+        if (use_w && c == 0) wv = ld_cg_f(w + (size_t)id * ws);
         accumulate(v, x, wv, sq, lin);
         if (WANT_H && c == 0) xx += x * x;
       }
@@ -127,10 +127,10 @@ struct RowGroup {
   // gather + reduce in one go (scoring kernels)
   template <typename IdPtr, typename ValPtr>
   __device__ __forceinline__ float score(const float4* __restrict__ V4,
-                                         const float* __restrict__ w, int gp, bool use_w,
+                                         const float* __restrict__ w, int gp, int ws, bool use_w,
                                          IdPtr ids, ValPtr xs, int beg_, int end_, int c, int s) {
-    gather(V4, w, gp, use_w, ids, xs, beg_, end_, c, s);
-    return reduce<false>(V4, w, gp, use_w, ids, xs, c, s);
+    gather(V4, w, gp, ws, use_w, ids, xs, beg_, end_, c, s);
+    return reduce<false>(V4, w, gp, ws, use_w, ids, xs, c, s);
   }
 
   __device__ __forceinline__ void accumulate(const float4& v, float x, float wv, float& sq,

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
         const float4 l = ld_cg_f4(V4 + (size_t)id[e]);
         vr[e].v[0] = l.x; vr[e].v[1] = l.y; vr[e].v[2] = l.z; vr[e].v[3] = l.w;
       }
-      wv[e] = (use_w && e < cnt) ? ld_cg_f(a.w + id[e]) : 0.f;
+      wv[e] = (use_w && e < cnt) ? ld_cg_f(a.w + (size_t)id[e] * a.ws) : 0.f;
     }
 
     // ---- fm_model::predict in registers (fm_model.h:105-127) ----
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
       } else {
         if (on && !(a.dbg & 1)) red_add_f4(a.v + (size_t)id[e] * 4, d[0], d[1], d[2], d[3]);
       }
-      if (on && use_w && !(a.dbg & 2)) red_add_f(a.w + id[e], sw * (nlr_mult * x[e] + nlr_regw * wv[e]));
+      if (on && use_w && !(a.dbg & 2)) red_add_f(a.w + (size_t)id[e] * a.ws, sw * (nlr_mult * x[e] + nlr_regw * wv[e]));
     }
 
     // ---- bias: one damped reduction into the global w0 per tile ----

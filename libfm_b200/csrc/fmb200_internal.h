@@ -27,12 +27,16 @@ struct DataSlot {
   uint32_t tile_span[5] = {0, 0, 0, 0, 0};
 };
 
-// Packed fp32 state: [w0, 0, 0, 0 | w[n] padded to a multiple of 4 | V[n][kp]]
+// Packed fp32 state: [w0, 0, 0, 0 | w[n*ws] padded to a multiple of 4 | V[n][kp]].
+// ws = stride of the linear weights in floats: 8 (one w per 32-byte sector) for small
+// tables, whose few lines otherwise serialise at L2 under load+reduction traffic
+// (profiles/r01_red_microbench.txt: 260 vs 128 cycles per load+RED pair at n=9746), else 1.
 struct Params32 {
   float* base = nullptr;
   uint64_t n_floats = 0;
   uint64_t off_w = 4;
   uint64_t off_v = 0;
+  int ws = 1;
   __host__ __device__ float* w0() const { return base; }
   __host__ __device__ float* w() const { return base + off_w; }
   __host__ __device__ float* v() const { return base + off_v; }
