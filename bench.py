@@ -247,17 +247,9 @@ def run_gpu_arm(args):
     value = world * rows / (ms_per_step * 1e-3)
 
     # ---- end to end through the C ABI, host buffers ------------------------
-    def pinned(a):
-        t = torch.from_numpy(a).pin_memory()
-        return t.numpy(), t
     import ctypes as C
-    keep = []
-    host = []
-    for a in (data.row_ptr, data.col, data.val, data.target):
-        arr, t = pinned(a)
-        keep.append(t)
-        host.append(arr)
-    rp, col, val, tgt = host
+    from libfm_b200.model import pinned_copy
+    rp, col, val, tgt = [pinned_copy(a) for a in (data.row_ptr, data.col, data.val, data.target)]
     w0 = C.c_double()
     w_out = np.empty(n, dtype=np.float64)
     v_out = np.empty((K_FACTORS, n), dtype=np.float64)

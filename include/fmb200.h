@@ -68,6 +68,13 @@ int fmb200_upload_data_aos(fmb200_ctx* ctx, int slot, uint64_t n_rows, const voi
                            const float* target);
 int fmb200_free_data(fmb200_ctx* ctx, int slot);
 
+/* Page-locked host memory for the arrays handed to fmb200_upload_data: uploads from it
+ * run at full PCIe rate and asynchronously (pageable memory is staged by the driver).
+ * The reference allocates its CSR with plain new[] (Data.h:238); a loader that wants
+ * the fast path allocates here instead.  Any host memory is accepted by the upload. */
+int fmb200_host_alloc(void** out, uint64_t bytes);
+int fmb200_host_free(void* p);
+
 /* Replaces: reading / writing fm_model::w0, w, v (fm_model.h:46-48).  v is the
  * reference's FACTOR-MAJOR double [num_factor][n_attr] (util/matrix.h:152-175). */
 int fmb200_set_params(fmb200_ctx* ctx, double w0, const double* w, const double* v_factor_major);

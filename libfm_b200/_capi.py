@@ -29,6 +29,8 @@ SYMBOLS = {
     "fmb200_upload_data": (C.c_int, [_ctx, C.c_int, C.c_uint64, C.c_uint64, _u64p, _u32p, _f32p, _f32p]),
     "fmb200_upload_data_aos": (C.c_int, [_ctx, C.c_int, C.c_uint64, C.c_void_p, _f32p]),
     "fmb200_free_data": (C.c_int, [_ctx, C.c_int]),
+    "fmb200_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
+    "fmb200_host_free": (C.c_int, [C.c_void_p]),
     "fmb200_set_params": (C.c_int, [_ctx, C.c_double, _f64p, _f64p]),
     "fmb200_get_params": (C.c_int, [_ctx, _f64p, _f64p, _f64p]),
     "fmb200_sgd_epoch": (C.c_int, [_ctx, C.c_int, _f64p]),

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -86,10 +87,10 @@ int upload_common(fmb200_ctx* c, int slot, uint64_t n_rows, uint64_t nnz, const 
   // per-feature occurrence counts used by the HOGWILD damping.
   CK(cudaMemsetAsync(c->d_flag, 0, 16 * sizeof(unsigned int), c->stream));
   CK(launch_csr_inspect(c, s.row_ptr, n_rows, nnz, c->d_flag));
-  if (nnz > 0) CK(launch_max_col(c, s.col, nnz, c->d_flag + 8));
-  unsigned int h[16];
-  CK(cudaMemcpyAsync(h, c->d_flag, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  CK(launch_feature_counts(c, s.col, nnz, s.feat_cnt, c->d_flag + 8, c->d_flag + 9));
+  unsigned int* h = c->h_flag;
+  CK(cudaMemcpyAsync(h, c->d_flag, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));  // the one host sync of an upload
   if (h[0] & 1u) return fail("row_ptr[0] must be 0");
   if (h[0] & 2u) return fail("row_ptr is not monotone");
   if (h[0] & 4u) return fail("row_ptr[n_rows] != nnz");
@@ -98,11 +99,7 @@ int upload_common(fmb200_ctx* c, int slot, uint64_t n_rows, uint64_t nnz, const 
     return fail("feature id %u out of range (num_attribute=%u)", h[8], c->n);
   s.max_row_nnz = h[1];
   for (int i = 0; i < 5; i++) s.tile_span[i] = h[2 + i];
-  // counts only after the ids are known to be in range (the histogram indexes by id)
-  CK(launch_feature_counts(c, s.col, nnz, s.feat_cnt, c->d_flag + 9));
-  CK(cudaMemcpyAsync(h, c->d_flag + 9, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  s.max_feat_cnt = h[0];
+  s.max_feat_cnt = h[9];
   s.present = true;
   return 0;
 }
@@ -180,6 +177,14 @@ int fmb200_create(fmb200_ctx** out, int device, uint32_t n_attr, int num_factor,
   CK(cudaMalloc(&c->d_w0_accum, sizeof(float)));
   CK(cudaMalloc(&c->d_done, sizeof(unsigned int)));
   CK(cudaMalloc(&c->d_flag, 16 * sizeof(unsigned int)));
+  CK(cudaHostAlloc((void**)&c->h_flag, 16 * sizeof(unsigned int), cudaHostAllocDefault));
+  {
+    const size_t need = std::max(c->p32.n_floats * sizeof(float), c->p64.n_doubles * sizeof(double));
+    if (need <= (64u << 20)) {
+      CK(cudaHostAlloc(&c->h_stage, need, cudaHostAllocDefault));
+      c->h_stage_bytes = need;
+    }
+  }
   CK(cudaMemsetAsync(c->d_w0_accum, 0, sizeof(float), c->stream));
   CK(cudaMemsetAsync(c->d_done, 0, sizeof(unsigned int), c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -199,6 +204,8 @@ void fmb200_destroy(fmb200_ctx* c) {
   if (c->d_w0_accum) cudaFree(c->d_w0_accum);
   if (c->d_done) cudaFree(c->d_done);
   if (c->d_flag) cudaFree(c->d_flag);
+  if (c->h_flag) cudaFreeHost(c->h_flag);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -282,6 +289,18 @@ int fmb200_upload_data_aos(fmb200_ctx* c, int slot, uint64_t n_rows, const void*
   return upload_common(c, slot, n_rows, nnz, rp.data(), col.data(), val.data(), target);
 }
 
+int fmb200_host_alloc(void** out, uint64_t bytes) {
+  if (!out) return fail("null out pointer");
+  *out = nullptr;
+  CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return 0;
+}
+
+int fmb200_host_free(void* p) {
+  if (p) CK(cudaFreeHost(p));
+  return 0;
+}
+
 int fmb200_free_data(fmb200_ctx* c, int slot) {
   NEED_CTX(c);
   if (slot < 0 || slot >= FMB200_MAX_SLOTS) return fail("slot %d out of range", slot);
@@ -333,14 +352,19 @@ int fmb200_get_params(fmb200_ctx* c, double* w0, double* w, double* v) {
     for (int f = 0; f < k; f++)
       for (uint32_t i = 0; i < n; i++) v[(size_t)f * n + i] = hv[(size_t)i * k + f];
   } else {
-    std::vector<float> h(c->p32.n_floats);
-    CK(cudaMemcpyAsync(h.data(), c->p32.base, h.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    std::vector<float> pageable;
+    float* h = static_cast<float*>(c->h_stage);
+    if (h == nullptr) {
+      pageable.resize(c->p32.n_floats);
+      h = pageable.data();
+    }
+    CK(cudaMemcpyAsync(h, c->p32.base, c->p32.n_floats * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     *w0 = h[0];
     for (uint32_t i = 0; i < n; i++) w[i] = h[c->p32.off_w + (size_t)i * c->p32.ws];
-    const float* hv = h.data() + c->p32.off_v;
-    for (int f = 0; f < k; f++)
-      for (uint32_t i = 0; i < n; i++) v[(size_t)f * n + i] = hv[(size_t)i * kp + f];
+    const float* hv = h + c->p32.off_v;
+    for (uint32_t i = 0; i < n; i++)
+      for (int f = 0; f < k; f++) v[(size_t)f * n + i] = hv[(size_t)i * kp + f];
   }
   return 0;
 }

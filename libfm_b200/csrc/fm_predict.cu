@@ -197,10 +197,38 @@ __global__ void max_col_kernel(const uint32_t* __restrict__ col, uint64_t nnz,
   if ((threadIdx.x & 31) == 0) atomicMax(out_max, m);
 }
 
-__global__ void hist_kernel(const uint32_t* __restrict__ col, uint64_t nnz, unsigned int* cnt) {
+// occurrence histogram of the column ids + the largest id seen (ids >= n are
+// counted nowhere: the caller rejects the data set when max id >= n).
+// SMEM_BINS > 0: the table fits in shared memory (n <= SMEM_BINS): per-CTA private
+// histogram, flushed once -- a few thousand counters under 2M increments would
+// otherwise serialise at L2.
+template <int SMEM_BINS>
+__global__ void hist_kernel(const uint32_t* __restrict__ col, uint64_t nnz, uint32_t n,
+                            unsigned int* cnt, unsigned int* out_max) {
+  __shared__ unsigned int s_cnt[SMEM_BINS > 0 ? SMEM_BINS : 1];
+  if (SMEM_BINS > 0) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_cnt[i] = 0u;
+    __syncthreads();
+  }
+  unsigned int m = 0;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nnz;
-       i += (uint64_t)gridDim.x * blockDim.x)
-    atomicAdd(cnt + col[i], 1u);
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t id = col[i];
+    m = max(m, id);
+    if (id < n) {
+      if (SMEM_BINS > 0) atomicAdd(s_cnt + id, 1u);
+      else atomicAdd(cnt + id, 1u);
+    }
+  }
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out_max, m);
+  if (SMEM_BINS > 0) {
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned int v = s_cnt[i];
+      if (v) atomicAdd(cnt + i, v);
+    }
+  }
 }
 
 // in place: uint32 counts -> float counts, and the maximum
@@ -297,12 +325,18 @@ cudaError_t launch_csr_inspect(fmb200_ctx* c, const uint64_t* rp, uint64_t n_row
 }
 
 cudaError_t launch_feature_counts(fmb200_ctx* c, const uint32_t* col, uint64_t nnz, float* cnt,
-                                  unsigned int* out_max) {
+                                  unsigned int* out_max_id, unsigned int* out_max) {
   unsigned int* u = reinterpret_cast<unsigned int*>(cnt);
   cudaError_t e = cudaMemsetAsync(u, 0, sizeof(unsigned int) * (size_t)c->n, c->stream);
   if (e != cudaSuccess) return e;
   if (nnz > 0) {
-    hist_kernel<<<grid_for(c, nnz), 256, 0, c->stream>>>(col, nnz, u);
+    constexpr int BINS = 12288;  // 48 KB of static shared memory
+    if (c->n <= (uint32_t)BINS) {
+      const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((nnz + 16383) / 16384, (uint64_t)c->sm_count));
+      hist_kernel<BINS><<<grid, 1024, 0, c->stream>>>(col, nnz, c->n, u, out_max_id);
+    } else {
+      hist_kernel<0><<<grid_for(c, nnz), 256, 0, c->stream>>>(col, nnz, c->n, u, out_max_id);
+    }
     c->launches++;
   }
   if (c->n > 0) {

@@ -86,6 +86,9 @@ struct fmb200_ctx {
   float* d_w0_accum = nullptr;       // hogwild: row-weighted sum of CTA-local biases
   unsigned int* d_done = nullptr;    // hogwild: CTAs finished
   unsigned int* d_flag = nullptr;    // 16 device words: upload-time inspection results
+  unsigned int* h_flag = nullptr;    // pinned host mirror of d_flag
+  void* h_stage = nullptr;           // pinned staging for set/get_params (small models)
+  size_t h_stage_bytes = 0;
   uint64_t launches = 0;
   fmb::EpochConfig last_cfg;
   int tune_ctas_per_sm = 0, tune_rows_per_tile = 0, tune_threads = 0;
@@ -116,7 +119,7 @@ cudaError_t launch_csr_inspect(fmb200_ctx* c, const uint64_t* rp, uint64_t n_row
                                unsigned int* out8);
 // histogram of column ids -> float counts in cnt[n]; *out_max = largest count
 cudaError_t launch_feature_counts(fmb200_ctx* c, const uint32_t* col, uint64_t nnz, float* cnt,
-                                  unsigned int* out_max);
+                                  unsigned int* out_max_id, unsigned int* out_max);
 
 // pick the sub-warp geometry for a data set: G lanes per V row (power of two
 // covering kp/4 float4 chunks), S entry slots per row group

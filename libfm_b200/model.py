@@ -98,6 +98,18 @@ class Data:
                     np.array(val, dtype=np.float32), np.array(target, dtype=np.float32))
 
 
+def pinned_copy(arr: np.ndarray) -> np.ndarray:
+    """Copy `arr` into page-locked memory from fmb200_host_alloc (kept alive by the array)."""
+    lib = _capi.load()
+    p = C.c_void_p()
+    if lib.fmb200_host_alloc(C.byref(p), arr.nbytes) != 0:
+        raise FmError(lib.fmb200_last_error().decode())
+    buf = (C.c_char * max(arr.nbytes, 1)).from_address(p.value)
+    out = np.frombuffer(buf, dtype=arr.dtype, count=arr.size).reshape(arr.shape)
+    out[...] = arr
+    return out  # never freed explicitly: process-lifetime staging buffers
+
+
 class _LibcRand:
     """glibc srand()/rand(): the reference's only entropy source (random.h:172-174)."""
 

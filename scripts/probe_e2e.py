@@ -15,7 +15,8 @@ def stage(pin):
     out = []
     for a in (d.row_ptr, d.col, d.val, d.target):
         if pin:
-            t = torch.from_numpy(a.copy()).pin_memory(); out.append((t.numpy(), t))
+            from libfm_b200.model import pinned_copy
+            out.append((pinned_copy(a), None))
         else:
             out.append((a.copy(), None))
     return out
