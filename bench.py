@@ -196,19 +196,44 @@ def run_gpu_arm(args):
 
     stream = torch.cuda.ExternalStream(lrn.stream(), device=local_rank)
     ptr, n_floats = lrn.params_device()
-    params = torch.as_tensor(_DevBuf(ptr, n_floats), device=torch.device("cuda", local_rank))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     lib, ctx = lrn.lib, lrn._ctx
+    import ctypes as C
+
+    # the per-epoch exchange: one-shot all-reduce over NVLink peer memory (fm_peer.cu),
+    # NCCL through torch.distributed as the fallback / comparison
+    collective = "none"
+    params = None
+    if world > 1:
+        collective = args.collective
+        if collective in ("auto", "p2p"):
+            h = C.create_string_buffer(64)
+            ok = lib.fmb200_peer_export(ctx, h) == 0
+            handles = [None] * world
+            dist.all_gather_object(handles, h.raw if ok else b"")
+            ok = ok and all(len(x) == 64 for x in handles)
+            if ok:
+                ok = lib.fmb200_peer_attach_ipc(ctx, world, rank, b"".join(handles)) == 0
+            flag = torch.tensor([1 if ok else 0], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 1:
+                collective = "p2p"
+            elif collective == "p2p":
+                raise RuntimeError("peer attach failed: " + lib.fmb200_last_error().decode())
+            else:
+                collective = "nccl"
+        if collective == "nccl":
+            params = torch.as_tensor(_DevBuf(ptr, n_floats), device=torch.device("cuda", local_rank))
 
     def step():
         rc = lib.fmb200_sgd_epoch_async(ctx, 0)
-        if rc != 0:
-            raise RuntimeError(lib.fmb200_last_error().decode())
-        if world > 1:
+        if rc == 0 and collective == "p2p":
+            rc = lib.fmb200_allreduce_mean(ctx)
+        elif rc == 0 and collective == "nccl":
             dist.all_reduce(params)  # sum over ranks on the library's stream
             rc = lib.fmb200_scale_params(ctx, 1.0 / world)
-            if rc != 0:
-                raise RuntimeError(lib.fmb200_last_error().decode())
+        if rc != 0:
+            raise RuntimeError(lib.fmb200_last_error().decode())
 
     def barrier():
         if world > 1:
@@ -247,7 +272,6 @@ def run_gpu_arm(args):
     value = world * rows / (ms_per_step * 1e-3)
 
     # ---- end to end through the C ABI, host buffers ------------------------
-    import ctypes as C
     from libfm_b200.model import pinned_copy
     rp, col, val, tgt = [pinned_copy(a) for a in (data.row_ptr, data.col, data.val, data.target)]
     w0 = C.c_double()
@@ -259,11 +283,9 @@ def run_gpu_arm(args):
     def e2e_step():
         rc = lib.fmb200_upload_data(ctx, 0, rows, int(rp[-1]), P(rp, C.c_uint64), P(col, C.c_uint32),
                                     P(val, C.c_float), P(tgt, C.c_float))
-        rc |= lib.fmb200_sgd_epoch_async(ctx, 0)
-        if world > 1 and rc == 0:
+        if rc == 0:
             with torch.cuda.stream(stream):
-                dist.all_reduce(params)
-            rc |= lib.fmb200_scale_params(ctx, 1.0 / world)
+                step()
         rc |= lib.fmb200_get_params(ctx, C.byref(w0), P(w_out, C.c_double), P(v_out, C.c_double))
         if rc != 0:
             raise RuntimeError(lib.fmb200_last_error().decode())
@@ -327,7 +349,8 @@ def run_gpu_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(WORKLOAD, parallelism="row-sharded dp%d, per-epoch NCCL all-reduce" % world,
+        "config": dict(WORKLOAD, parallelism="row-sharded dp%d, per-epoch all-reduce of w0|w|V (%s)" % (
+            world, {"p2p": "one-shot kernel over NVLink peer memory", "nccl": "NCCL", "none": "single GPU"}[collective]),
                        kernel_geometry=cfg),
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -350,6 +373,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -40,6 +40,8 @@ typedef struct fmb200_ctx fmb200_ctx;
                                  write-back, damped per-tile bias step */
 
 #define FMB200_MAX_SLOTS 8
+#define FMB200_MAX_PEERS 16
+#define FMB200_IPC_HANDLE_BYTES 64
 
 /* Replaces: fm_model construction, libfm.cpp:245-256 (num_attribute, k0, k1, num_factor).
  * `device` is the CUDA ordinal. */
@@ -106,6 +108,17 @@ int fmb200_predict(fmb200_ctx* ctx, int slot, int transform, double* out);
 int fmb200_params_device(fmb200_ctx* ctx, void** device_ptr, uint64_t* n_floats);
 int fmb200_scale_params(fmb200_ctx* ctx, double factor);
 int fmb200_stream(fmb200_ctx* ctx, void** cuda_stream);
+
+/* The same exchange without NCCL, over NVLink peer memory: every rank maps the
+ * peers' state (CUDA IPC between processes: export -> exchange the 64-byte handles by
+ * any means -> attach; or attach_local for contexts of one process) and
+ * fmb200_allreduce_mean() launches ONE kernel per rank that barriers through peer
+ * flags and averages all replicas into a second local buffer (double-buffered, so
+ * fmb200_params_device() changes after every call).  Attach once, before training. */
+int fmb200_peer_export(fmb200_ctx* ctx, void* handle /* FMB200_IPC_HANDLE_BYTES */);
+int fmb200_peer_attach_ipc(fmb200_ctx* ctx, int world, int rank, const void* handles /* world x 64 B */);
+int fmb200_peer_attach_local(fmb200_ctx* ctx, int world, int rank, fmb200_ctx* const* contexts);
+int fmb200_allreduce_mean(fmb200_ctx* ctx);
 
 /* Introspection for tests / bench */
 int fmb200_kernel_launches(fmb200_ctx* ctx, uint64_t* count); /* kernels launched so far */

@@ -41,6 +41,10 @@ SYMBOLS = {
     "fmb200_params_device": (C.c_int, [_ctx, C.POINTER(C.c_void_p), _u64p]),
     "fmb200_scale_params": (C.c_int, [_ctx, C.c_double]),
     "fmb200_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),
+    "fmb200_peer_export": (C.c_int, [_ctx, C.c_void_p]),
+    "fmb200_peer_attach_ipc": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_void_p]),
+    "fmb200_peer_attach_local": (C.c_int, [_ctx, C.c_int, C.c_int, C.POINTER(_ctx)]),
+    "fmb200_allreduce_mean": (C.c_int, [_ctx]),
     "fmb200_kernel_launches": (C.c_int, [_ctx, _u64p]),
     "fmb200_last_epoch_config": (C.c_int, [_ctx] + [_intp] * 7),
     "fmb200_set_tuning": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -31,6 +31,7 @@ CU_SOURCES = {
     "fm_context.cu": [],
     "fm_hogwild.cu": [],
     "fm_rowlane.cu": [],
+    "fm_peer.cu": [],
     "fm_predict.cu": [],
     "fm_inorder.cu": ["--fmad=false"],
 }

@@ -170,7 +170,11 @@ int fmb200_create(fmb200_ctx** out, int device, uint32_t n_attr, int num_factor,
   c->p32.n_floats = 4 + n4 + (uint64_t)n_attr * c->kp;
   c->p64.off_v = 1 + (uint64_t)n_attr;
   c->p64.n_doubles = 1 + (uint64_t)n_attr + (uint64_t)n_attr * num_factor;
-  CK(cudaMalloc(&c->p32.base, c->p32.n_floats * sizeof(float)));
+  c->comm_buf_bytes = (c->p32.n_floats * sizeof(float) + 255) & ~(size_t)255;
+  CK(cudaMalloc(&c->comm_base, c->comm_hdr + 2 * c->comm_buf_bytes));
+  CK(cudaMemsetAsync(c->comm_base, 0, c->comm_hdr + 2 * c->comm_buf_bytes, c->stream));
+  c->p32.base = reinterpret_cast<float*>(c->comm_base + c->comm_hdr);
+  c->peer_base[0] = c->comm_base;
   CK(cudaMalloc(&c->p64.base, c->p64.n_doubles * sizeof(double)));
   CK(cudaMemsetAsync(c->p32.base, 0, c->p32.n_floats * sizeof(float), c->stream));
   CK(cudaMemsetAsync(c->p64.base, 0, c->p64.n_doubles * sizeof(double), c->stream));
@@ -197,7 +201,9 @@ void fmb200_destroy(fmb200_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (int i = 0; i < FMB200_MAX_SLOTS; i++) free_slot(c->slots[i]);
-  if (c->p32.base) cudaFree(c->p32.base);
+  for (int q = 0; q < FMB200_MAX_PEERS; q++)
+    if (c->peer_ipc[q] && c->peer_base[q]) cudaIpcCloseMemHandle(c->peer_base[q]);
+  if (c->comm_base) cudaFree(c->comm_base);
   if (c->p64.base) cudaFree(c->p64.base);
   if (c->d_partials) cudaFree(c->d_partials);
   if (c->d_pred) cudaFree(c->d_pred);
@@ -474,6 +480,80 @@ int fmb200_scale_params(fmb200_ctx* c, double factor) {
   if (c->mode != FMB200_MODE_HOGWILD) return fail("scale_params applies to the HOGWILD state");
   if (bind(c)) return 1;
   CK(launch_scale_p32(c, (float)factor));
+  return 0;
+}
+
+int fmb200_peer_export(fmb200_ctx* c, void* handle) {
+  NEED_CTX(c);
+  if (!handle) return fail("null handle pointer");
+  if (bind(c)) return 1;
+  static_assert(sizeof(cudaIpcMemHandle_t) == FMB200_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, c->comm_base));
+  memcpy(handle, &h, sizeof(h));
+  return 0;
+}
+
+static int peer_precheck(fmb200_ctx* c, int world, int rank) {
+  if (world < 1 || world > FMB200_MAX_PEERS) return fail("world %d outside [1,%d]", world, FMB200_MAX_PEERS);
+  if (rank < 0 || rank >= world) return fail("rank %d outside world %d", rank, world);
+  if (c->peer_seq != 0 || c->peer_world != 1) return fail("peers are already attached");
+  if (c->mode != FMB200_MODE_HOGWILD) return fail("peer averaging applies to the HOGWILD state");
+  return 0;
+}
+
+int fmb200_peer_attach_ipc(fmb200_ctx* c, int world, int rank, const void* handles) {
+  NEED_CTX(c);
+  if (!handles) return fail("null handles");
+  if (peer_precheck(c, world, rank)) return 1;
+  if (bind(c)) return 1;
+  const unsigned char* hb = static_cast<const unsigned char*>(handles);
+  for (int q = 0; q < world; q++) {
+    if (q == rank) {
+      c->peer_base[q] = c->comm_base;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, hb + (size_t)q * FMB200_IPC_HANDLE_BYTES, sizeof(h));
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_base[q] = static_cast<unsigned char*>(p);
+    c->peer_ipc[q] = true;
+  }
+  c->peer_world = world;
+  c->peer_rank = rank;
+  return 0;
+}
+
+int fmb200_peer_attach_local(fmb200_ctx* c, int world, int rank, fmb200_ctx* const* all) {
+  NEED_CTX(c);
+  if (!all) return fail("null context list");
+  if (peer_precheck(c, world, rank)) return 1;
+  if (bind(c)) return 1;
+  for (int q = 0; q < world; q++) {
+    if (!all[q] || all[q]->p32.n_floats != c->p32.n_floats) return fail("peer %d has a different model shape", q);
+    if (q != rank && all[q]->device != c->device) {
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, c->device, all[q]->device));
+      if (!can) return fail("device %d cannot access device %d", c->device, all[q]->device);
+      cudaError_t e = cudaDeviceEnablePeerAccess(all[q]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return fail("cudaDeviceEnablePeerAccess failed: %s", cudaGetErrorString(e));
+      (void)cudaGetLastError();
+    }
+    c->peer_base[q] = all[q]->comm_base;
+  }
+  c->peer_world = world;
+  c->peer_rank = rank;
+  return 0;
+}
+
+int fmb200_allreduce_mean(fmb200_ctx* c) {
+  NEED_CTX(c);
+  if (c->mode != FMB200_MODE_HOGWILD) return fail("peer averaging applies to the HOGWILD state");
+  if (c->peer_world <= 1) return 0;
+  if (bind(c)) return 1;
+  CK(launch_peer_mean(c));
   return 0;
 }
 

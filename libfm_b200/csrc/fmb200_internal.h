@@ -92,6 +92,13 @@ struct fmb200_ctx {
   uint64_t launches = 0;
   fmb::EpochConfig last_cfg;
   int tune_ctas_per_sm = 0, tune_rows_per_tile = 0, tune_threads = 0;
+  // peer-memory parameter averaging (fm_peer.cu).  comm block = [flags | buf0 | buf1]
+  unsigned char* comm_base = nullptr;
+  size_t comm_hdr = 1024, comm_buf_bytes = 0;
+  unsigned char* peer_base[FMB200_MAX_PEERS] = {nullptr};
+  bool peer_ipc[FMB200_MAX_PEERS] = {false};
+  int peer_world = 1, peer_rank = 0, peer_cur = 0;
+  unsigned int peer_seq = 0;
   int tune_damp = 0;  // 0 auto, 1 force on, -1 force off
   int tune_variant = 0;  // 0 auto, 1 row-group kernel, 2 row-lane kernel when eligible
 };
@@ -113,6 +120,8 @@ cudaError_t launch_predict32(fmb200_ctx* c, const DataSlot& d, int transform, do
 cudaError_t launch_p64_to_p32(fmb200_ctx* c);
 cudaError_t launch_p32_to_p64(fmb200_ctx* c);
 cudaError_t launch_scale_p32(fmb200_ctx* c, float factor);
+// fm_peer.cu: one-shot all-reduce (mean) of the packed fp32 state over peer memory
+cudaError_t launch_peer_mean(fmb200_ctx* c);
 cudaError_t launch_max_col(fmb200_ctx* c, const uint32_t* col, uint64_t nnz, unsigned int* out_max);
 // device-side structural check of row offsets (see fm_predict.cu)
 cudaError_t launch_csr_inspect(fmb200_ctx* c, const uint64_t* rp, uint64_t n_rows, uint64_t nnz,

@@ -230,6 +230,15 @@ class GpuSgdLearner {
       ck(fmb200_create(&ctx_[g], first_device + g, fm->num_attribute, fm->num_factor, fm->k0, fm->k1));
       ck(fmb200_set_mode(ctx_[g], mode));
     }
+    // per-epoch exchange: NVLink peer-memory averaging when the devices can map each
+    // other, NCCL otherwise (or when FMB200_CLI_NCCL is set)
+    if (num_gpus > 1 && getenv("FMB200_CLI_NCCL") == nullptr) {
+      use_peer_ = true;
+      for (int g = 0; g < num_gpus && use_peer_; g++)
+        if (fmb200_peer_attach_local(ctx_[g], num_gpus, g, ctx_.data()) != 0) use_peer_ = false;
+      if (!use_peer_) std::cerr << "note: peer access unavailable (" << fmb200_last_error() << "), using NCCL" << std::endl;
+    }
+    if (use_peer_) return;
 #ifdef FMB200_WITH_NCCL
     if (num_gpus > 1) {
       std::vector<int> devs(num_gpus);
@@ -272,8 +281,10 @@ class GpuSgdLearner {
   double epoch() {
     const auto t0 = std::chrono::steady_clock::now();
     for (auto c : ctx_) ck(fmb200_sgd_epoch_async(c, 0));
+    if (use_peer_)
+      for (auto c : ctx_) ck(fmb200_allreduce_mean(c));
 #ifdef FMB200_WITH_NCCL
-    if (num_gpus > 1) {
+    if (num_gpus > 1 && !use_peer_) {
       ncclGroupStart();
       for (int g = 0; g < num_gpus; g++) {
         void *buf = nullptr, *st = nullptr;
@@ -362,6 +373,7 @@ class GpuSgdLearner {
   std::vector<ncclComm_t> comms_;
 #endif
   uint64_t n_train_ = 0, n_test_ = 0;
+  bool use_peer_ = false;
 };
 
 }  // namespace host
