@@ -230,3 +230,35 @@ def test_c2_size_properties(built_lib):
     l.set_mode(MODE_INORDER)
     assert abs(l.evaluate(d) - hist[-1]) < 1e-5
     l.close()
+
+
+def test_peer_allreduce_mean_two_contexts(built_lib):
+    """fm_peer.cu: two replicas (two contexts of one process, same device) average
+    their packed state through mapped peer buffers; both end bit-identical."""
+    import ctypes as C
+    n, k = 300, 8
+    cfg = _cfg(n, k)
+    a = make_learner(cfg, _rand_init(n, k, 1), mode=MODE_HOGWILD)
+    b = make_learner(cfg, _rand_init(n, k, 2), mode=MODE_HOGWILD)
+    arr = (C.c_void_p * 2)(a._ctx, b._ctx)
+    for rank, l in enumerate((a, b)):
+        assert l.lib.fmb200_peer_attach_local(l._ctx, 2, rank, arr) == 0, l.lib.fmb200_last_error()
+    a.pull_params(); b.pull_params()
+    want_w0 = np.float32(0.5) * (np.float32(a.fm.w0) + np.float32(b.fm.w0))
+    want_v = (np.float32(0.5) * (a.fm.v.astype(np.float32) + b.fm.v.astype(np.float32))).astype(np.float64)
+    want_w = (np.float32(0.5) * (a.fm.w.astype(np.float32) + b.fm.w.astype(np.float32))).astype(np.float64)
+    for rounds in range(3):  # exercises the double buffering
+        for l in (a, b):
+            assert l.lib.fmb200_allreduce_mean(l._ctx) == 0, l.lib.fmb200_last_error()
+        for l in (a, b):
+            assert l.lib.fmb200_sync(l._ctx) == 0
+        a.pull_params(); b.pull_params()
+        assert a.fm.w0 == b.fm.w0 and np.array_equal(a.fm.v, b.fm.v) and np.array_equal(a.fm.w, b.fm.w)
+        assert abs(a.fm.w0 - float(want_w0)) < 1e-7
+        np.testing.assert_allclose(a.fm.v, want_v, atol=1e-7)
+        np.testing.assert_allclose(a.fm.w, want_w, atol=1e-7)
+    # training continues on the swapped buffer
+    d = synth.two_field(5000, 200, 100, seed=3)
+    a.sgd_epoch(d)
+    assert np.isfinite(a.evaluate(d))
+    a.close(); b.close()
