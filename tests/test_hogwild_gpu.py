@@ -262,3 +262,29 @@ def test_peer_allreduce_mean_two_contexts(built_lib):
     a.sgd_epoch(d)
     assert np.isfinite(a.evaluate(d))
     a.close(); b.close()
+
+
+def test_c3_shape_properties(built_lib):
+    """BASELINE config C3 shape (Criteo-like: 39 one-hot fields over 1M features, k=64,
+    classification), 300k rows: score parity on a sample, loss decreases, state finite."""
+    d = synth.multi_field(300_000, 39, 1_000_000, seed=11)
+    d.binarize_targets()
+    n, k = d.num_feature, 64
+    cfg = _cfg(n, k, task=1, lr=0.01, regs=(0, 0, 0.0), mn=-1.0, mx=1.0)
+    r = np.random.default_rng(4)
+    init = (0.0, np.zeros(n), (r.standard_normal((k, n)) * 0.01))
+    l = make_learner(cfg, init, mode=MODE_HOGWILD)
+    sample = d.rows(1000, 3000)
+    got = l.predict(sample, transform=False)
+    want = _port(cfg, init).predict(sample, 1, 0, 0, transform=False)
+    assert np.max(np.abs(got - want)) < 5e-5
+    acc0 = l.evaluate(d)
+    for _ in range(3):
+        l.sgd_epoch(d)
+    acc1 = l.evaluate(d)
+    cfgd = l.epoch_config()
+    assert cfgd["lanes_per_row"] == 16  # k=64 -> 16 float4 lanes per factor row
+    assert acc1 > acc0 + 0.02  # random labels: it can only memorise, and it does
+    l.pull_params()
+    assert np.isfinite(l.fm.v).all() and np.isfinite(l.fm.w).all()
+    l.close()
