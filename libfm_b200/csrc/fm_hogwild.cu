@@ -52,10 +52,10 @@
 
 namespace fmb {
 
-template <int G, int S, int R, int U, bool DAMP>
+template <int G, int S, int R, int RW, int U, bool DAMP>
 __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
     fm_sgd_hogwild_kernel(const HogwildArgs a) {
-  using RG = RowGroup<G, S, R>;
+  using RG = RowGroup<G, S, R, RW>;
   constexpr int E = RG::E;
   constexpr int RPW = 32 / E;  // rows per warp per row set
   extern __shared__ __align__(128) unsigned char smem[];
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
           end = (int)(rp[r + 1] - ab);
           y[u] = ys[r];
         }
-        g[u].gather(V4, a.w, a.gp, a.ws, use_w, ids, xs, beg, end, c, s);
+        g[u].gather(V4, a.w, a.gp, a.ws, use_w, ids, xs, beg, end, c, s, lig);
       }
       if (!have_w0) {  // after this tile's first gathers are in flight
         w0 = bias.get(use_w0, tid, it, (int)blockDim.x);
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
       for (int u = 0; u < U; ++u) {
         if (U > 1 && rbase + u * rows_per_set >= rows_here) break;  // warp-uniform
         RG& gu = g[u];
-        const float part = gu.template reduce<DAMP>(V4, a.w, a.gp, a.ws, use_w, ids, xs, c, s);
+        const float part = gu.template reduce<DAMP>(V4, a.w, a.gp, a.ws, use_w, ids, xs, c, s, lig);
         const float p = w0 + part;
         float mult, curv;
         if (a.task == FMB200_TASK_REGRESSION) {
@@ -181,45 +181,54 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
 
         // ---- fm_SGD write-back (fm_sgd.h:38-50) as L2 reductions ----
         const float nlr_mult = -lr * mult;
-        auto update = [&](bool on, uint32_t id, float x, const float4& v, float wv) {
+        // factor rows, chunk-parallel: -lr*(mult*(sum_f*x - v*x^2) + regv*v)
+        auto update_v = [&](int j, const float4& v) {
+          const uint32_t id = ids[j];
+          const float x = xs[j];
           const float x2 = x * x;
-          const float gx = gu.acc.x * x - v.x * x2, gy = gu.acc.y * x - v.y * x2;
-          const float gz = gu.acc.z * x - v.z * x2, gw = gu.acc.w * x - v.w * x2;
-          float sv = 1.f, sw = 1.f;
+          float sv = 1.f;
           if (DAMP) {
             const float conc = __ldg(a.feat_cnt + id) * a.conc_scale;  // expected concurrency
-            if (conc > 1.f) {
-              sv = gamma_scale(conc, lr * (hjoint + a.regv));
-              sw = gamma_scale(conc, lr * (hjoint + a.regw));
-            }
+            if (conc > 1.f) sv = gamma_scale(conc, lr * (hjoint + a.regv));
           }
-          if (on && c < a.gp && !(a.dbg & 1)) {
-            // -lr*(mult*(sum_f*x - v*x^2) + regv*v)
-            red_add_f4(a.v + ((size_t)id * a.gp + c) * 4, sv * (nlr_mult * gx + nlr_regv * v.x),
-                       sv * (nlr_mult * gy + nlr_regv * v.y), sv * (nlr_mult * gz + nlr_regv * v.z),
-                       sv * (nlr_mult * gw + nlr_regv * v.w));
-          }
-          if (on && use_w && c == 0 && !(a.dbg & 2)) red_add_f(a.w + (size_t)id * a.ws, sw * (nlr_mult * x + nlr_regw * wv));
+          red_add_f4(a.v + ((size_t)id * a.gp + c) * 4,
+                     sv * (nlr_mult * (gu.acc.x * x - v.x * x2) + nlr_regv * v.x),
+                     sv * (nlr_mult * (gu.acc.y * x - v.y * x2) + nlr_regv * v.y),
+                     sv * (nlr_mult * (gu.acc.z * x - v.z * x2) + nlr_regv * v.z),
+                     sv * (nlr_mult * (gu.acc.w * x - v.w * x2) + nlr_regv * v.w));
         };
+        if (c < a.gp && !(a.dbg & 1)) {
 #pragma unroll
-        for (int q = 0; q < R; ++q) {
-          const int j = gu.beg + s + q * S;
-          const bool on = j < gu.end;
-          if (on) update(true, gu.idc[q], gu.xc[q], gu.vc[q], gu.wc[q]);
-        }
-        for (int q = R; q < gu.maxit; ++q) {
-          const int j = gu.beg + s + q * S;
-          const bool on = j < gu.end;
-          uint32_t id = 0;
-          float x = 0.f, wv = 0.f;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (on) {
-            x = xs[j];
-            id = ids[j];
-            if (c < a.gp) v = ld_cg_f4(V4 + (size_t)id * a.gp + c);
-            if (use_w && c == 0) wv = ld_cg_f(a.w + (size_t)id * a.ws);
+          for (int q = 0; q < R; ++q) {
+            const int j = gu.beg + s + q * S;
+            if (j < gu.end) update_v(j, gu.vc[q]);
           }
-          if (on) update(true, id, x, v, wv);
+          for (int q = R; q < gu.maxit; ++q) {
+            const int j = gu.beg + s + q * S;
+            if (j < gu.end) update_v(j, ld_cg_f4(V4 + (size_t)ids[j] * a.gp + c));
+          }
+        }
+        // linear weights, entry-parallel: -lr*(mult*x + regw*w)
+        auto update_w = [&](int j, float wv) {
+          const uint32_t id = ids[j];
+          const float x = xs[j];
+          float sw = 1.f;
+          if (DAMP) {
+            const float conc = __ldg(a.feat_cnt + id) * a.conc_scale;
+            if (conc > 1.f) sw = gamma_scale(conc, lr * (hjoint + a.regw));
+          }
+          red_add_f(a.w + (size_t)id * a.ws, sw * (nlr_mult * x + nlr_regw * wv));
+        };
+        if (use_w && !(a.dbg & 2)) {
+#pragma unroll
+          for (int t = 0; t < RW; ++t) {
+            const int j = gu.beg + lig + t * E;
+            if (j < gu.end) update_w(j, gu.wc[t]);
+          }
+          for (int t = RW; t < gu.maxwit; ++t) {
+            const int j = gu.beg + lig + t * E;
+            if (j < gu.end) update_w(j, ld_cg_f(a.w + (size_t)ids[j] * a.ws));
+          }
         }
       }
     }
@@ -253,19 +262,22 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
 // ---------------------------------------------------------------------------
 using KernelFn = HogwildKernelFn;
 
-template <int G, int S, int R, int U>
+template <int G, int S, int R, int RW, int U>
 KernelFn pick_damp(bool damp) {
-  return damp ? fm_sgd_hogwild_kernel<G, S, R, U, true> : fm_sgd_hogwild_kernel<G, S, R, U, false>;
+  return damp ? fm_sgd_hogwild_kernel<G, S, R, RW, U, true>
+              : fm_sgd_hogwild_kernel<G, S, R, RW, U, false>;
 }
 
-// R entries cached per lane, U row sets in flight: (1,4) short one-hot rows,
-// (2,2), and (8,1) for long rows
+// (R factor chunks, RW weights) cached per lane, U row sets in flight:
+//   class 0: rows of <= 2*S entries           -> R=2,  RW=1, U=2
+//   class 1: medium rows (<= 8*S entries)     -> R=8,  RW=2, U=1
+//   class 2: long rows (Criteo-like, 39/row)  -> R=20, RW=2, U=1  (no re-gather up to 20*S)
 template <int G, int S>
-KernelFn pick_r(int R, bool damp) {
-  switch (R) {
-    case 1: return pick_damp<G, S, 1, 4>(damp);
-    case 2: return pick_damp<G, S, 2, 2>(damp);
-    default: return pick_damp<G, S, 8, 1>(damp);
+KernelFn pick_r(int cls, bool damp) {
+  switch (cls) {
+    case 0: return pick_damp<G, S, 2, 1, 2>(damp);
+    case 1: return pick_damp<G, S, 8, 2, 1>(damp);
+    default: return pick_damp<G, S, 20, 2, 1>(damp);
   }
 }
 
@@ -392,8 +404,9 @@ cudaError_t launch_sgd_hogwild(fmb200_ctx* c, const DataSlot& d) {
   pick_geometry(c->kp, d.n_rows, d.nnz, &G, &S);
   const double avg = (double)d.nnz / (double)d.n_rows;
   const int iters = (int)((avg + S - 1) / S);
-  const int R = iters <= 1 ? 1 : (iters <= 2 ? 2 : 8);
-  const int U = R == 1 ? 4 : (R == 2 ? 2 : 1);
+  const int cls = iters <= 2 ? 0 : (iters <= 8 ? 1 : 2);
+  const int R = cls == 0 ? 2 : (cls == 1 ? 8 : 20);
+  const int U = cls == 0 ? 2 : 1;
   const int threads = c->tune_threads > 0 ? std::min(c->tune_threads, HW_MAX_THREADS) : 256;
   const int ctas_target = (R * U <= 4) ? 3 : 2;
 
@@ -425,7 +438,7 @@ cudaError_t launch_sgd_hogwild(fmb200_ctx* c, const DataSlot& d) {
                        (1.0 + std::max(c->hp.regw, c->hp.regv));
   const bool damp = c->tune_damp == 1 || (c->tune_damp == 0 && q_max > 0.5);
 
-  KernelFn fn = pick_kernel(G, S, R, damp);
+  KernelFn fn = pick_kernel(G, S, cls, damp);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int occ = 0;

@@ -30,7 +30,7 @@ struct PredictArgs {
 
 template <int G, int S>
 __global__ void __launch_bounds__(256) fm_predict32_kernel(const PredictArgs a) {
-  using RG = RowGroup<G, S, 1>;
+  using RG = RowGroup<G, S, 2, 1>;
   constexpr int E = RG::E;
   constexpr int RPW = 32 / E;
   const int lane = threadIdx.x & 31;
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) fm_predict32_kernel(const PredictArgs a) 
     }
     RG g;
     const float part = g.score(V4, a.w, a.gp, a.ws, a.use_w != 0, a.col + beg, a.val + beg, 0,
-                               (int)(end - beg), c, s);
+                               (int)(end - beg), c, s, lig);
     float p = w0 + part;
     if (valid && lig == 0) {
       if (a.task == FMB200_TASK_REGRESSION) {
