@@ -275,6 +275,7 @@ KernelFn pick_damp(bool damp) {
 template <int G, int S>
 KernelFn pick_r(int cls, bool damp) {
   switch (cls) {
+    case -1: return pick_damp<G, S, 1, 1, 4>(damp);  // rows of <= S entries: 4 row sets in flight
     case 0: return pick_damp<G, S, 2, 1, 2>(damp);
     case 1: return pick_damp<G, S, 8, 2, 1>(damp);
     default: return pick_damp<G, S, 20, 2, 1>(damp);
@@ -404,9 +405,9 @@ cudaError_t launch_sgd_hogwild(fmb200_ctx* c, const DataSlot& d) {
   pick_geometry(c->kp, d.n_rows, d.nnz, &G, &S);
   const double avg = (double)d.nnz / (double)d.n_rows;
   const int iters = (int)((avg + S - 1) / S);
-  const int cls = iters <= 2 ? 0 : (iters <= 8 ? 1 : 2);
-  const int R = cls == 0 ? 2 : (cls == 1 ? 8 : 20);
-  const int U = cls == 0 ? 2 : 1;
+  const int cls = iters <= 1 ? -1 : (iters <= 2 ? 0 : (iters <= 8 ? 1 : 2));
+  const int R = cls < 0 ? 1 : (cls == 0 ? 2 : (cls == 1 ? 8 : 20));
+  const int U = cls < 0 ? 4 : (cls == 0 ? 2 : 1);
   const int threads = c->tune_threads > 0 ? std::min(c->tune_threads, HW_MAX_THREADS) : 256;
   const int ctas_target = (R * U <= 4) ? 3 : 2;
 
