@@ -63,6 +63,15 @@ int fmb200_set_mode(fmb200_ctx* ctx, int mode);
 int fmb200_upload_data(fmb200_ctx* ctx, int slot, uint64_t n_rows, uint64_t nnz,
                        const uint64_t* row_ptr, const uint32_t* col, const float* val,
                        const float* target);
+/* Asynchronous variant: enqueues the copy (and the device-side validation) on the
+ * context's copy stream and returns.  The slot must not be in use by a running epoch.
+ * The next call that touches the slot (epoch / evaluate / predict) waits for the copy
+ * and reports a validation failure; this lets the upload of the NEXT batch overlap the
+ * epoch on the current one (two slots, ping-pong).  Host buffers must stay valid and
+ * should be page-locked (fmb200_host_alloc) for the copy to be truly asynchronous. */
+int fmb200_upload_data_async(fmb200_ctx* ctx, int slot, uint64_t n_rows, uint64_t nnz,
+                             const uint64_t* row_ptr, const uint32_t* col, const float* val,
+                             const float* target);
 /* Same, straight from the reference's AoS layout (util/fmatrix.h:34-42):
  * `rows` points at n_rows sparse_row{sparse_entry* data; uint size;} records (16 B
  * each on LP64), each entry {uint id; float value} (8 B). */

@@ -27,6 +27,7 @@ SYMBOLS = {
     "fmb200_set_hparams": (C.c_int, [_ctx, C.c_int] + [C.c_double] * 6),
     "fmb200_set_mode": (C.c_int, [_ctx, C.c_int]),
     "fmb200_upload_data": (C.c_int, [_ctx, C.c_int, C.c_uint64, C.c_uint64, _u64p, _u32p, _f32p, _f32p]),
+    "fmb200_upload_data_async": (C.c_int, [_ctx, C.c_int, C.c_uint64, C.c_uint64, _u64p, _u32p, _f32p, _f32p]),
     "fmb200_upload_data_aos": (C.c_int, [_ctx, C.c_int, C.c_uint64, C.c_void_p, _f32p]),
     "fmb200_free_data": (C.c_int, [_ctx, C.c_int]),
     "fmb200_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),

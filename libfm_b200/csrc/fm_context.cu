@@ -47,6 +47,9 @@ void free_slot(DataSlot& s) {
   if (s.val) cudaFree(s.val);
   if (s.target) cudaFree(s.target);
   if (s.feat_cnt) cudaFree(s.feat_cnt);
+  if (s.d_flag) cudaFree(s.d_flag);
+  if (s.h_flag) cudaFreeHost(s.h_flag);
+  if (s.ready) cudaEventDestroy(s.ready);
   s = DataSlot();
 }
 
@@ -55,9 +58,15 @@ void free_slot(DataSlot& s) {
 constexpr uint64_t kRowSlack = 512 + 8;
 constexpr uint64_t kEntrySlack = 16;
 
-int upload_common(fmb200_ctx* c, int slot, uint64_t n_rows, uint64_t nnz, const uint64_t* row_ptr,
-                  const uint32_t* col, const float* val, const float* target) {
+// Enqueue the copies + the device-side inspection of one data set on `st` and leave
+// the results in the slot's pinned flag mirror; upload_finish() collects them.
+int upload_enqueue(fmb200_ctx* c, int slot, uint64_t n_rows, uint64_t nnz, const uint64_t* row_ptr,
+                   const uint32_t* col, const float* val, const float* target, cudaStream_t st) {
   DataSlot& s = c->slots[slot];
+  if (s.pending) {  // an earlier asynchronous upload into this slot: drain it first
+    CK(cudaEventSynchronize(s.ready));
+    s.pending = false;
+  }
   // re-uploads into a slot reuse its buffers when they are large enough
   if (!(s.row_ptr && s.cap_rows >= n_rows && s.cap_nnz >= nnz)) {
     free_slot(s);
@@ -66,36 +75,54 @@ int upload_common(fmb200_ctx* c, int slot, uint64_t n_rows, uint64_t nnz, const 
     CK(cudaMalloc(&s.col, (nnz + kEntrySlack) * sizeof(uint32_t)));
     CK(cudaMalloc(&s.val, (nnz + kEntrySlack) * sizeof(float)));
     CK(cudaMalloc(&s.feat_cnt, sizeof(float) * (size_t)(c->n ? c->n : 1)));
+    CK(cudaMalloc(&s.d_flag, 16 * sizeof(unsigned int)));
+    CK(cudaHostAlloc((void**)&s.h_flag, 16 * sizeof(unsigned int), cudaHostAllocDefault));
+    CK(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
     // the slack is only ever read by whole-tile bulk copies and never used
-    CK(cudaMemsetAsync(s.row_ptr, 0, (n_rows + 1 + kRowSlack) * sizeof(uint64_t), c->stream));
-    CK(cudaMemsetAsync(s.target, 0, (n_rows + kRowSlack) * sizeof(float), c->stream));
-    CK(cudaMemsetAsync(s.col, 0, (nnz + kEntrySlack) * sizeof(uint32_t), c->stream));
-    CK(cudaMemsetAsync(s.val, 0, (nnz + kEntrySlack) * sizeof(float), c->stream));
+    CK(cudaMemsetAsync(s.row_ptr, 0, (n_rows + 1 + kRowSlack) * sizeof(uint64_t), st));
+    CK(cudaMemsetAsync(s.target, 0, (n_rows + kRowSlack) * sizeof(float), st));
+    CK(cudaMemsetAsync(s.col, 0, (nnz + kEntrySlack) * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(s.val, 0, (nnz + kEntrySlack) * sizeof(float), st));
     s.cap_rows = n_rows;
     s.cap_nnz = nnz;
   }
   s.present = false;
   s.n_rows = n_rows;
   s.nnz = nnz;
-  CK(cudaMemcpyAsync(s.row_ptr, row_ptr, (n_rows + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(s.target, target, n_rows * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(s.col, col, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(s.val, val, nnz * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  // Inspection runs on the device, in the shadow of nothing but itself: offsets
-  // monotone and consistent, longest row, tile spans, largest column id (the
-  // reference asserts id < num_attribute per access, fm_model.h:112), and the
-  // per-feature occurrence counts used by the HOGWILD damping.
-  CK(cudaMemsetAsync(c->d_flag, 0, 16 * sizeof(unsigned int), c->stream));
-  CK(launch_csr_inspect(c, s.row_ptr, n_rows, nnz, c->d_flag));
-  CK(launch_feature_counts(c, s.col, nnz, s.feat_cnt, c->d_flag + 8, c->d_flag + 9));
-  unsigned int* h = c->h_flag;
-  CK(cudaMemcpyAsync(h, c->d_flag, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));  // the one host sync of an upload
+  CK(cudaMemcpyAsync(s.row_ptr, row_ptr, (n_rows + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s.target, target, n_rows * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s.col, col, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s.val, val, nnz * sizeof(float), cudaMemcpyHostToDevice, st));
+  // Inspection runs on the device: offsets monotone and consistent, longest row, tile
+  // spans, largest column id (the reference asserts id < num_attribute per access,
+  // fm_model.h:112), and the per-feature occurrence counts used by the HOGWILD damping.
+  cudaStream_t saved = c->stream;
+  c->stream = st;  // the launch helpers enqueue on c->stream
+  cudaError_t e1 = cudaMemsetAsync(s.d_flag, 0, 16 * sizeof(unsigned int), st);
+  cudaError_t e2 = launch_csr_inspect(c, s.row_ptr, n_rows, nnz, s.d_flag);
+  cudaError_t e3 = launch_feature_counts(c, s.col, nnz, s.feat_cnt, s.d_flag + 8, s.d_flag + 9);
+  c->stream = saved;
+  CK(e1);
+  CK(e2);
+  CK(e3);
+  CK(cudaMemcpyAsync(s.h_flag, s.d_flag, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(s.ready, st));
+  s.pending = true;
+  return 0;
+}
+
+// The one host sync of an upload: wait for the slot's event and read the verdict.
+int upload_finish(fmb200_ctx* c, int slot) {
+  DataSlot& s = c->slots[slot];
+  if (!s.pending) return 0;
+  CK(cudaEventSynchronize(s.ready));
+  s.pending = false;
+  const unsigned int* h = s.h_flag;
   if (h[0] & 1u) return fail("row_ptr[0] must be 0");
   if (h[0] & 2u) return fail("row_ptr is not monotone");
   if (h[0] & 4u) return fail("row_ptr[n_rows] != nnz");
   if (h[0] & 8u) return fail("a row is longer than 2^32-1 entries");
-  if (nnz > 0 && h[8] >= c->n)
+  if (s.nnz > 0 && h[8] >= c->n)
     return fail("feature id %u out of range (num_attribute=%u)", h[8], c->n);
   s.max_row_nnz = h[1];
   for (int i = 0; i < 5; i++) s.tile_span[i] = h[2 + i];
@@ -104,8 +131,15 @@ int upload_common(fmb200_ctx* c, int slot, uint64_t n_rows, uint64_t nnz, const 
   return 0;
 }
 
+int upload_common(fmb200_ctx* c, int slot, uint64_t n_rows, uint64_t nnz, const uint64_t* row_ptr,
+                  const uint32_t* col, const float* val, const float* target) {
+  if (upload_enqueue(c, slot, n_rows, nnz, row_ptr, col, val, target, c->stream)) return 1;
+  return upload_finish(c, slot);
+}
+
 int need_slot(fmb200_ctx* c, int slot) {
   if (slot < 0 || slot >= FMB200_MAX_SLOTS) return fail("slot %d out of range", slot);
+  if (c->slots[slot].pending && upload_finish(c, slot)) return 1;
   if (!c->slots[slot].present) return fail("slot %d holds no data", slot);
   return 0;
 }
@@ -214,6 +248,7 @@ void fmb200_destroy(fmb200_ctx* c) {
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -259,6 +294,18 @@ int fmb200_upload_data(fmb200_ctx* c, int slot, uint64_t n_rows, uint64_t nnz,
   if (n_rows > 0xffffffffull) return fail("row count exceeds the reference's uint range");
   if (bind(c)) return 1;
   return upload_common(c, slot, n_rows, nnz, row_ptr, col, val, target);
+}
+
+int fmb200_upload_data_async(fmb200_ctx* c, int slot, uint64_t n_rows, uint64_t nnz,
+                             const uint64_t* row_ptr, const uint32_t* col, const float* val,
+                             const float* target) {
+  NEED_CTX(c);
+  if (slot < 0 || slot >= FMB200_MAX_SLOTS) return fail("slot %d out of range", slot);
+  if (!row_ptr || (n_rows && !target) || (nnz && (!col || !val))) return fail("null data pointer");
+  if (n_rows > 0xffffffffull) return fail("row count exceeds the reference's uint range");
+  if (bind(c)) return 1;
+  if (c->copy_stream == nullptr) CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  return upload_enqueue(c, slot, n_rows, nnz, row_ptr, col, val, target, c->copy_stream);
 }
 
 int fmb200_upload_data_aos(fmb200_ctx* c, int slot, uint64_t n_rows, const void* rows,
@@ -312,6 +359,7 @@ int fmb200_free_data(fmb200_ctx* c, int slot) {
   if (slot < 0 || slot >= FMB200_MAX_SLOTS) return fail("slot %d out of range", slot);
   if (bind(c)) return 1;
   CK(cudaStreamSynchronize(c->stream));
+  if (c->slots[slot].pending) CK(cudaEventSynchronize(c->slots[slot].ready));
   free_slot(c->slots[slot]);
   return 0;
 }

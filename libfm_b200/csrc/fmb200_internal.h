@@ -21,6 +21,10 @@ struct DataSlot {
   uint32_t max_row_nnz = 0;
   uint64_t cap_rows = 0, cap_nnz = 0;  // allocated capacity (re-uploads reuse the buffers)
   float* feat_cnt = nullptr;    // [n_attr] occurrences of each feature in this data set
+  unsigned int* d_flag = nullptr;  // 16 words: inspection results of the last upload
+  unsigned int* h_flag = nullptr;  // pinned mirror
+  cudaEvent_t ready = nullptr;     // recorded behind the upload's last operation
+  bool pending = false;            // an upload is enqueued and not yet collected
   uint32_t max_feat_cnt = 0;
   // worst-case 4-element-aligned nnz span of any tile of 2^(5+i) rows
   // (i = 0..4 -> 32, 64, 128, 256, 512 rows); sizes the smem staging buffers
@@ -69,6 +73,7 @@ struct fmb200_ctx {
   int sm_count = 0;
   int max_smem_optin = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // asynchronous uploads (fmb200_upload_data_async)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   uint32_t n = 0;
   int k = 0, kp = 0;

@@ -197,3 +197,34 @@ def test_aos_upload_equals_soa_upload(built_lib):
     p = _port(cfg, init)
     assert np.array_equal(out0, p.predict(d, 0, 0, 0, transform=False))
     l.close()
+
+
+def test_async_upload_ping_pong(built_lib):
+    """fmb200_upload_data_async: two slots alternate; an epoch on a slot waits for that
+    slot's copy; a bad data set surfaces its error at the first use of the slot."""
+    import ctypes as C
+    from libfm_b200.model import pinned_copy
+    d = synth.two_field(3000, 60, 40, seed=3)
+    cfg = _cfg(100, 4, mn=d.min_target, mx=d.max_target)
+    init = _rand_init(100, 4, 2)
+    l = make_learner(cfg, init, mode=MODE_INORDER)
+    p = _port(cfg, init)
+    P = lambda a, t: a.ctypes.data_as(C.POINTER(t))  # noqa: E731
+    bufs = [pinned_copy(a) for a in (d.row_ptr, d.col, d.val, d.target)]
+    def up(slot, col=None):
+        return l.lib.fmb200_upload_data_async(l._ctx, slot, d.num_cases, d.num_values, P(bufs[0], C.c_uint64),
+                                              P(bufs[1] if col is None else col, C.c_uint32),
+                                              P(bufs[2], C.c_float), P(bufs[3], C.c_float))
+    assert up(2) == 0
+    for step in range(3):
+        assert up(3 if step % 2 == 0 else 2) == 0
+        assert l.lib.fmb200_sgd_epoch(l._ctx, 2 if step % 2 == 0 else 3, None) == 0
+        p.sgd_epoch(d, 0, 0.01, cfg["min_target"], cfg["max_target"])
+    l.pull_params()
+    assert l.fm.w0 == p.w0.value and np.array_equal(l.fm.v, p.v)
+    bad = pinned_copy(d.col.copy())
+    bad[5] = 1000  # out of range for num_attribute = 100
+    assert up(4, bad) == 0  # the copy is only enqueued ...
+    assert l.lib.fmb200_sgd_epoch(l._ctx, 4, None) != 0  # ... the verdict arrives at first use
+    assert b"out of range" in l.lib.fmb200_last_error()
+    l.close()
