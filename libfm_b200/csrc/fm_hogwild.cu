@@ -53,7 +53,7 @@
 namespace fmb {
 
 template <int G, int S, int R, int RW, int U, bool DAMP>
-__global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : 2))
+__global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : (R > 20 ? 1 : 2)))
     fm_sgd_hogwild_kernel(const HogwildArgs a) {
   using RG = RowGroup<G, S, R, RW>;
   constexpr int E = RG::E;
@@ -278,7 +278,12 @@ KernelFn pick_r(int cls, bool damp) {
     case -1: return pick_damp<G, S, 1, 1, 4>(damp);  // rows of <= S entries: 4 row sets in flight
     case 0: return pick_damp<G, S, 2, 1, 2>(damp);
     case 1: return pick_damp<G, S, 8, 2, 1>(damp);
-    default: return pick_damp<G, S, 20, 2, 1>(damp);
+    case 2: return pick_damp<G, S, 20, 2, 1>(damp);
+    default:
+      // k = 128 (G = 32, S = 1): a lane walks every entry of the row; 40 cached chunks
+      // (160 registers, one CTA per SM) keep a 39-entry row entirely in registers
+      if constexpr (G == 32) return pick_damp<G, S, 40, 2, 1>(damp);
+      else return pick_damp<G, S, 20, 2, 1>(damp);
   }
 }
 
@@ -372,7 +377,10 @@ static cudaError_t launch_rowlane(fmb200_ctx* c, const DataSlot& d, bool* handle
   const double q_max = (double)d.max_feat_cnt * flight_guess / (double)d.n_rows * c->hp.lr *
                        (1.0 + std::max(c->hp.regw, c->hp.regv));
   const bool damp = c->tune_damp == 1 || (c->tune_damp == 0 && q_max > 0.5);
-  HogwildKernelFn fn = pick_rowlane_kernel(gp, (int)d.max_row_nnz, damp);
+  // in-warp merging of same-feature steps pays once a warp of 32 rows is likely to hold
+  // the hottest feature more than once
+  const bool combine = (double)d.max_feat_cnt * 32.0 / (double)d.n_rows > 0.5;
+  HogwildKernelFn fn = pick_rowlane_kernel(gp, (int)d.max_row_nnz, damp, combine);
   if (fn == nullptr) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
@@ -405,11 +413,11 @@ cudaError_t launch_sgd_hogwild(fmb200_ctx* c, const DataSlot& d) {
   pick_geometry(c->kp, d.n_rows, d.nnz, &G, &S);
   const double avg = (double)d.nnz / (double)d.n_rows;
   const int iters = (int)((avg + S - 1) / S);
-  const int cls = iters <= 1 ? -1 : (iters <= 2 ? 0 : (iters <= 8 ? 1 : 2));
-  const int R = cls < 0 ? 1 : (cls == 0 ? 2 : (cls == 1 ? 8 : 20));
+  const int cls = iters <= 1 ? -1 : (iters <= 2 ? 0 : (iters <= 8 ? 1 : ((iters <= 20 || G < 32) ? 2 : 3)));
+  const int R = cls < 0 ? 1 : (cls == 0 ? 2 : (cls == 1 ? 8 : (cls == 2 ? 20 : 40)));
   const int U = cls < 0 ? 4 : (cls == 0 ? 2 : 1);
   const int threads = c->tune_threads > 0 ? std::min(c->tune_threads, HW_MAX_THREADS) : 256;
-  const int ctas_target = (R * U <= 4) ? 3 : 2;
+  const int ctas_target = (R * U <= 4) ? 3 : (R > 20 ? 1 : 2);
 
   // tile geometry: largest tile (<= 256 rows by default) whose worst-case
   // staged entry count keeps NSTAGE stages within the CTA's share of the SM's smem

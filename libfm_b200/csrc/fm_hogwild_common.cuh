@@ -105,6 +105,6 @@ struct BiasFetch {
 using HogwildKernelFn = void (*)(const HogwildArgs);
 
 // fm_rowlane.cu: kernel for (float4 chunks per row gp in {1,2}, rows of at most Z entries)
-HogwildKernelFn pick_rowlane_kernel(int gp, int max_row_nnz, bool damp);
+HogwildKernelFn pick_rowlane_kernel(int gp, int max_row_nnz, bool damp, bool combine);
 
 }  // namespace fmb

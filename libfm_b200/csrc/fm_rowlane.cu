@@ -32,7 +32,7 @@ struct FactorRow {
   float v[4 * GP];
 };
 
-template <int GP, int Z, bool DAMP>
+template <int GP, int Z, bool DAMP, bool COMBINE>
 __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const HogwildArgs a) {
   constexpr int K = 4 * GP;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -198,14 +198,45 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
 #pragma unroll
       for (int f = 0; f < K; ++f)
         d[f] = sv * (nlr_mult * (sum[f] * x[e] - vr[e].v[f] * x2) + nlr_regv * vr[e].v[f]);
+      float dw = sw * (nlr_mult * x[e] + nlr_regw * wv[e]);
+      bool on_c = on;  // this lane still owns a reduction for entry e
+      if (COMBINE) {
+        // Skewed data: several rows of a warp hit the same feature.  Sum their steps
+        // inside the warp (log-step segmented reduction over the lanes that share the
+        // id, after "Voting and Shuffling to Optimize Atomic Operations") and let the
+        // lowest lane issue ONE reduction: hot rows serialise at L2, so every merged
+        // reduction is time saved for the whole chip.
+        const uint32_t key = on ? id[e] : (0x80000000u | (uint32_t)lane);  // inactive: unique
+        unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (__any_sync(0xffffffffu, __popc(peers) > 1)) {
+          const int first = __ffs(peers) - 1;
+          int rel = __popc(peers << (31 - lane) << 1);  // peers below this lane
+          peers &= (0xfffffffeu << lane);               // peers above this lane
+          while (__any_sync(0xffffffffu, peers != 0u)) {
+            const int next = __ffs(peers);
+            const int src = next ? next - 1 : lane;
+#pragma unroll
+            for (int f = 0; f < K; ++f) {
+              const float t = __shfl_sync(0xffffffffu, d[f], src);
+              if (next) d[f] += t;
+            }
+            const float tw = __shfl_sync(0xffffffffu, dw, src);
+            if (next) dw += tw;
+            const unsigned done = __ballot_sync(0xffffffffu, rel & 1);
+            peers &= ~done;
+            rel >>= 1;
+          }
+          on_c = on && (lane == first);
+        }
+      }
       if (GP == 2) {
         // swap halves inside the lane pair so that each reduction covers a full sector
         const uint32_t pid = __shfl_xor_sync(0xffffffffu, id[e], 1);
-        const bool pon = __shfl_xor_sync(0xffffffffu, (int)on, 1) != 0;
+        const bool pon = __shfl_xor_sync(0xffffffffu, (int)on_c, 1) != 0;
         const uint32_t idA = odd ? pid : id[e];
         const uint32_t idB = odd ? id[e] : pid;
-        const bool onA = odd ? pon : on;
-        const bool onB = odd ? on : pon;
+        const bool onA = odd ? pon : on_c;
+        const bool onB = odd ? on_c : pon;
         float4 send, keep;
         if (odd) {
           send = make_float4(d[0], d[1], d[2], d[3]);  // my low half goes to the even lane
@@ -226,9 +257,9 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
         if (onA && !(a.dbg & 1)) red_add_f4(a.v + ((size_t)idA * 2 + odd) * 4, va.x, va.y, va.z, va.w);
         if (onB && !(a.dbg & 1)) red_add_f4(a.v + ((size_t)idB * 2 + odd) * 4, vb.x, vb.y, vb.z, vb.w);
       } else {
-        if (on && !(a.dbg & 1)) red_add_f4(a.v + (size_t)id[e] * 4, d[0], d[1], d[2], d[3]);
+        if (on_c && !(a.dbg & 1)) red_add_f4(a.v + (size_t)id[e] * 4, d[0], d[1], d[2], d[3]);
       }
-      if (on && use_w && !(a.dbg & 2)) red_add_f(a.w + (size_t)id[e] * a.ws, sw * (nlr_mult * x[e] + nlr_regw * wv[e]));
+      if (on_c && use_w && !(a.dbg & 2)) red_add_f(a.w + (size_t)id[e] * a.ws, dw);
     }
 
     // ---- bias: one damped reduction into the global w0 per tile ----
@@ -257,21 +288,23 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
 }
 
 template <int GP, int Z>
-static HogwildKernelFn pick_d(bool damp) {
-  return damp ? fm_sgd_rowlane_kernel<GP, Z, true> : fm_sgd_rowlane_kernel<GP, Z, false>;
+static HogwildKernelFn pick_d(bool damp, bool combine) {
+  if (combine)
+    return damp ? fm_sgd_rowlane_kernel<GP, Z, true, true> : fm_sgd_rowlane_kernel<GP, Z, false, true>;
+  return damp ? fm_sgd_rowlane_kernel<GP, Z, true, false> : fm_sgd_rowlane_kernel<GP, Z, false, false>;
 }
 
 template <int GP>
-static HogwildKernelFn pick_z(int z, bool damp) {
-  if (z <= 1) return pick_d<GP, 1>(damp);
-  if (z <= 2) return pick_d<GP, 2>(damp);
-  if (z <= 4) return pick_d<GP, 4>(damp);
+static HogwildKernelFn pick_z(int z, bool damp, bool combine) {
+  if (z <= 1) return pick_d<GP, 1>(damp, combine);
+  if (z <= 2) return pick_d<GP, 2>(damp, combine);
+  if (z <= 4) return pick_d<GP, 4>(damp, combine);
   return nullptr;
 }
 
-HogwildKernelFn pick_rowlane_kernel(int gp, int max_row_nnz, bool damp) {
-  if (gp == 1) return pick_z<1>(max_row_nnz, damp);
-  if (gp == 2) return pick_z<2>(max_row_nnz, damp);
+HogwildKernelFn pick_rowlane_kernel(int gp, int max_row_nnz, bool damp, bool combine) {
+  if (gp == 1) return pick_z<1>(max_row_nnz, damp, combine);
+  if (gp == 2) return pick_z<2>(max_row_nnz, damp, combine);
   return nullptr;
 }
 

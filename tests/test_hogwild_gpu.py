@@ -288,3 +288,29 @@ def test_c3_shape_properties(built_lib):
     l.pull_params()
     assert np.isfinite(l.fm.v).all() and np.isfinite(l.fm.w).all()
     l.close()
+
+
+def test_in_warp_combining_sums_every_step(built_lib):
+    """Skewed ids switch the row-lane kernel to in-warp merging of same-feature steps.
+    With a tiny learning rate an epoch is linear in the per-row steps (every row sees
+    ~the initial state), so the merged write-back must equal the unmerged row-group
+    kernel's to rounding: nothing may be dropped or double-counted."""
+    d = synth.two_field(30_000, 50, 40, seed=9, zipf=1.2)
+    n, k = 90, 8
+    cfg = _cfg(n, k, lr=1e-6, regs=(0, 0.5, 0.25), mn=1.0, mx=5.0)
+    init = _rand_init(n, k, 11, stdev=0.3)
+    outs = []
+    for variant in (1, 2):
+        l = make_learner(cfg, init, mode=MODE_HOGWILD)
+        l.set_tuning(damp=-1, variant=variant)
+        l.sgd_epoch(d)
+        l.pull_params()
+        outs.append((l.fm.w.copy(), l.fm.v.copy(), l.epoch_config()))
+        l.close()
+    assert outs[0][2]["lanes_per_row"] != 1 and outs[1][2]["lanes_per_row"] == 1
+    init32 = [np.float32(x).astype(np.float64) for x in init]
+    dw_a, dw_b = outs[0][0] - init32[1], outs[1][0] - init32[1]
+    dv_a, dv_b = outs[0][1] - init32[2], outs[1][1] - init32[2]
+    assert np.abs(dv_a).max() > 1e-4  # hot features accumulate thousands of steps
+    np.testing.assert_allclose(dw_b, dw_a, rtol=2e-3, atol=2e-7)
+    np.testing.assert_allclose(dv_b, dv_a, rtol=2e-3, atol=2e-7)
