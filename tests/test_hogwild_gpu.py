@@ -307,13 +307,16 @@ def test_in_warp_combining_sums_every_step(built_lib):
     vu, vi = v[:, ids[:, 0]], v[:, ids[:, 1]]          # [k, rows]
     p = w0 + w[ids[:, 0]] + w[ids[:, 1]] + (vu * vi).sum(0)
     mult = np.clip(p, 1.0, 5.0) - d.target
-    dw = np.zeros(n)
-    dv = np.zeros((k, n))
+    dw, aw = np.zeros(n), np.zeros(n)            # sum of steps, sum of |steps|
+    dv, av = np.zeros((k, n)), np.zeros((k, n))
     for side, other in ((0, vi), (1, vu)):
-        np.add.at(dw, ids[:, side], -lr * (mult + 0.5 * w[ids[:, side]]))
+        sw_ = -lr * (mult + 0.5 * w[ids[:, side]])
+        np.add.at(dw, ids[:, side], sw_)
+        np.add.at(aw, ids[:, side], np.abs(sw_))
         step = -lr * (mult[None, :] * other + 0.25 * v[:, ids[:, side]])   # grad = s_f - v_f = other side
         for f in range(k):
             np.add.at(dv[f], ids[:, side], step[f])
+            np.add.at(av[f], ids[:, side], np.abs(step[f]))
     for variant in (1, 2):
         l = make_learner(cfg, init, mode=MODE_HOGWILD)
         l.set_tuning(damp=-1, variant=variant)
@@ -323,6 +326,9 @@ def test_in_warp_combining_sums_every_step(built_lib):
         got_w, got_v = l.fm.w - w, l.fm.v - v
         l.close()
         # rows see a state that has drifted by up to ~1% (order-dependent) and fp32 adds
-        # round: 3% / 2e-6; a dropped or doubled merged step is a 10-50% error on hot features
-        np.testing.assert_allclose(got_w, dw, rtol=3e-2, atol=2e-6, err_msg="variant %d w" % variant)
-        np.testing.assert_allclose(got_v, dv, rtol=3e-2, atol=2e-6, err_msg="variant %d v" % variant)
+        # round: allow 2% of the summed |steps| per element; a dropped or doubled merged
+        # step would be a 10-50% error on the hot features
+        assert np.all(np.abs(got_w - dw) <= 0.02 * aw + 2e-6), "variant %d w" % variant
+        assert np.all(np.abs(got_v - dv) <= 0.02 * av + 2e-6), "variant %d v" % variant
+        hot = np.argmax(aw)
+        assert abs(got_w[hot] - dw[hot]) < 0.05 * abs(dw[hot])  # the hottest feature, relative
