@@ -214,6 +214,8 @@ int fmb200_create(fmb200_ctx** out, int device, uint32_t n_attr, int num_factor,
   CK(cudaMemsetAsync(c->p64.base, 0, c->p64.n_doubles * sizeof(double), c->stream));
   CK(cudaMalloc(&c->d_w0_accum, sizeof(float)));
   CK(cudaMalloc(&c->d_done, sizeof(unsigned int)));
+  CK(cudaMalloc(&c->d_sched, 2 * sizeof(unsigned int)));
+  CK(cudaMemsetAsync(c->d_sched, 0, 2 * sizeof(unsigned int), c->stream));
   CK(cudaMalloc(&c->d_flag, 16 * sizeof(unsigned int)));
   CK(cudaHostAlloc((void**)&c->h_flag, 16 * sizeof(unsigned int), cudaHostAllocDefault));
   {
@@ -243,6 +245,7 @@ void fmb200_destroy(fmb200_ctx* c) {
   if (c->d_pred) cudaFree(c->d_pred);
   if (c->d_w0_accum) cudaFree(c->d_w0_accum);
   if (c->d_done) cudaFree(c->d_done);
+  if (c->d_sched) cudaFree(c->d_sched);
   if (c->d_flag) cudaFree(c->d_flag);
   if (c->h_flag) cudaFreeHost(c->h_flag);
   if (c->h_stage) cudaFreeHost(c->h_stage);

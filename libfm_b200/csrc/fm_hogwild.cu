@@ -80,16 +80,19 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : (R > 20 ? 1 
     policy = policy_evict_first();
   }
   __syncthreads();
+  uint32_t* s_tile = reinterpret_cast<uint32_t*>(smem + 208);  // [HW_NSTAGE] tile staged per stage
+  TileSched sched{a.sched, a.n_tiles, false};
   if (tid == 0) {
     for (int i = 0; i < HW_NSTAGE; i++) {
-      const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)i * gridDim.x;
-      if (t < a.n_tiles) {
-        const uint64_t r0 = t * TR, r1 = min(r0 + (uint64_t)TR, a.n_rows);
-        issue_tile(a, smem, bars, (uint32_t)t, i, policy, __ldg(a.row_ptr + r0),
-                   __ldg(a.row_ptr + r1));
+      const uint32_t t = sched.claim();
+      s_tile[i] = t;
+      if (t != HW_NO_TILE) {
+        const uint64_t r0 = (uint64_t)t * TR, r1 = min(r0 + (uint64_t)TR, a.n_rows);
+        issue_tile(a, smem, bars, t, i, policy, __ldg(a.row_ptr + r0), __ldg(a.row_ptr + r1));
       }
     }
   }
+  __syncthreads();
 
   const float4* V4 = reinterpret_cast<const float4*>(a.v);
   const bool use_w = a.use_w != 0;
@@ -99,17 +102,22 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : (R > 20 ? 1 
   const float nlr_regw = -lr * a.regw;
 
   int it = 0;
-  for (uint64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+  for (;; ++it) {
     const int stage = it % HW_NSTAGE;
     const uint32_t parity = (uint32_t)(it / HW_NSTAGE) & 1u;
+    const uint64_t tile = s_tile[stage];
+    if (tile == HW_NO_TILE) break;  // this CTA's claims ran dry
     // producer: fetch the entry range of the tile that will refill this stage now,
     // so the two dependent global loads overlap this tile's compute
-    const uint64_t nt = tile + (uint64_t)HW_NSTAGE * gridDim.x;
+    uint32_t nt = HW_NO_TILE;
     uint64_t nt_nb = 0, nt_ne = 0;
-    if (tid == 0 && nt < a.n_tiles) {
-      const uint64_t r0 = nt * TR, r1 = min(r0 + (uint64_t)TR, a.n_rows);
-      nt_nb = __ldg(a.row_ptr + r0);
-      nt_ne = __ldg(a.row_ptr + r1);
+    if (tid == 0) {
+      nt = sched.claim();
+      if (nt != HW_NO_TILE) {
+        const uint64_t r0 = (uint64_t)nt * TR, r1 = min(r0 + (uint64_t)TR, a.n_rows);
+        nt_nb = __ldg(a.row_ptr + r0);
+        nt_ne = __ldg(a.row_ptr + r1);
+      }
     }
     BiasFetch bias;
     bias.slot = reinterpret_cast<float*>(smem + 192);
@@ -243,7 +251,8 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : (R > 20 ? 1 
     }
     __syncthreads();  // every warp is done with this stage; partials complete
     if (tid == 0) {
-      if (nt < a.n_tiles) issue_tile(a, smem, bars, (uint32_t)nt, stage, policy, nt_nb, nt_ne);
+      s_tile[stage] = nt;
+      if (nt != HW_NO_TILE) issue_tile(a, smem, bars, nt, stage, policy, nt_nb, nt_ne);
       if (use_w0) {
         float M = 0.f, H = 0.f;
         for (int i = 0; i < nwarp; i++) {
@@ -257,6 +266,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : (R > 20 ? 1 
       }
     }
   }
+  if (tid == 0) sched.finish(gridDim.x);
 }
 
 // ---------------------------------------------------------------------------
@@ -355,6 +365,7 @@ static HogwildArgs make_args(fmb200_ctx* c, const DataSlot& d, uint64_t n_tiles,
   a.feat_cnt = d.feat_cnt;
   a.conc_scale = 1.f;
   a.w0_conc = 1.f;
+  a.sched = c->d_sched;
   const char* dbg = getenv("FMB200_DEBUG");
   a.dbg = dbg ? atoi(dbg) : 0;
   return a;

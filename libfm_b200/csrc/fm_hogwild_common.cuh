@@ -32,6 +32,7 @@ struct HogwildArgs {
   const float* feat_cnt;  // occurrences of each feature in this data set (DAMP)
   float conc_scale;       // rows processed concurrently / n_rows: count -> concurrency
   float w0_conc;          // rows in flight w.r.t. the bias (tile granularity)
+  unsigned int* sched;    // [0] next unclaimed tile, [1] CTAs that ran dry (both 0 between launches)
   int dbg;                // development only (FMB200_DEBUG): 1 = skip V reductions, 2 = skip w reductions
 };
 
@@ -99,6 +100,34 @@ struct BiasFetch {
     }
     named_bar_sync(1, nthreads);
     return *s;
+  }
+};
+
+// Dynamic tile scheduler: CTAs claim row tiles from a global counter in file order, so
+// the tail of the epoch is balanced (a static round-robin leaves 1/9 of the CTAs a whole
+// tile short on C2) and the rows in flight stay one contiguous window.  Used by thread 0
+// only.  The last CTA to run dry resets the two words for the next launch.
+constexpr uint32_t HW_NO_TILE = 0xffffffffu;
+struct TileSched {
+  unsigned int* w;
+  uint32_t n_tiles;
+  bool dry;
+  __device__ __forceinline__ uint32_t claim() {
+    if (dry) return HW_NO_TILE;
+    const uint32_t t = atomicAdd(w, 1u);
+    if (t >= n_tiles) {
+      dry = true;
+      return HW_NO_TILE;
+    }
+    return t;
+  }
+  __device__ __forceinline__ void finish(unsigned int n_ctas) {
+    while (!dry) claim();  // exactly one failed claim per CTA
+    __threadfence();
+    if (atomicAdd(w + 1, 1u) == n_ctas - 1) {
+      w[0] = 0u;
+      w[1] = 0u;
+    }
   }
 };
 

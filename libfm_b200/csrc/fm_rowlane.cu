@@ -51,16 +51,19 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
     policy = policy_evict_first();
   }
   __syncthreads();
+  uint32_t* s_tile = reinterpret_cast<uint32_t*>(smem + 208);  // [HW_NSTAGE] tile staged per stage
+  TileSched sched{a.sched, a.n_tiles, false};
   if (tid == 0) {
     for (int i = 0; i < HW_NSTAGE; i++) {
-      const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)i * gridDim.x;
-      if (t < a.n_tiles) {
-        const uint64_t r0 = t * TR, r1 = min(r0 + (uint64_t)TR, a.n_rows);
-        issue_tile(a, smem, bars, (uint32_t)t, i, policy, __ldg(a.row_ptr + r0),
-                   __ldg(a.row_ptr + r1));
+      const uint32_t t = sched.claim();
+      s_tile[i] = t;
+      if (t != HW_NO_TILE) {
+        const uint64_t r0 = (uint64_t)t * TR, r1 = min(r0 + (uint64_t)TR, a.n_rows);
+        issue_tile(a, smem, bars, t, i, policy, __ldg(a.row_ptr + r0), __ldg(a.row_ptr + r1));
       }
     }
   }
+  __syncthreads();
 
   const float4* V4 = reinterpret_cast<const float4*>(a.v);
   const bool use_w = a.use_w != 0;
@@ -68,15 +71,20 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
   const float lr = a.lr;
 
   int it = 0;
-  for (uint64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+  for (;; ++it) {
     const int stage = it % HW_NSTAGE;
     const uint32_t parity = (uint32_t)(it / HW_NSTAGE) & 1u;
-    const uint64_t nt = tile + (uint64_t)HW_NSTAGE * gridDim.x;
+    const uint64_t tile = s_tile[stage];
+    if (tile == HW_NO_TILE) break;  // this CTA's claims ran dry
+    uint32_t nt = HW_NO_TILE;
     uint64_t nt_nb = 0, nt_ne = 0;
-    if (tid == 0 && nt < a.n_tiles) {
-      const uint64_t r0 = nt * TR, r1 = min(r0 + (uint64_t)TR, a.n_rows);
-      nt_nb = __ldg(a.row_ptr + r0);
-      nt_ne = __ldg(a.row_ptr + r1);
+    if (tid == 0) {
+      nt = sched.claim();
+      if (nt != HW_NO_TILE) {
+        const uint64_t r0 = (uint64_t)nt * TR, r1 = min(r0 + (uint64_t)TR, a.n_rows);
+        nt_nb = __ldg(a.row_ptr + r0);
+        nt_ne = __ldg(a.row_ptr + r1);
+      }
     }
     BiasFetch bias;
     bias.slot = reinterpret_cast<float*>(smem + 192);
@@ -271,7 +279,8 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
     }
     __syncthreads();
     if (tid == 0) {
-      if (nt < a.n_tiles) issue_tile(a, smem, bars, (uint32_t)nt, stage, policy, nt_nb, nt_ne);
+      s_tile[stage] = nt;
+      if (nt != HW_NO_TILE) issue_tile(a, smem, bars, nt, stage, policy, nt_nb, nt_ne);
       if (use_w0) {
         float M = 0.f, H = 0.f;
         for (int i = 0; i < (int)(blockDim.x >> 5); i++) {
@@ -285,6 +294,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
       }
     }
   }
+  if (tid == 0) sched.finish(gridDim.x);
 }
 
 template <int GP, int Z>

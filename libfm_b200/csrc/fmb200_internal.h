@@ -89,7 +89,8 @@ struct fmb200_ctx {
   double* d_pred = nullptr;  // predict output staging
   uint64_t pred_cap = 0;
   float* d_w0_accum = nullptr;       // hogwild: row-weighted sum of CTA-local biases
-  unsigned int* d_done = nullptr;    // hogwild: CTAs finished
+  unsigned int* d_done = nullptr;    // (unused)
+  unsigned int* d_sched = nullptr;   // hogwild tile scheduler: [next tile, CTAs run dry]
   unsigned int* d_flag = nullptr;    // 16 device words: upload-time inspection results
   unsigned int* h_flag = nullptr;    // pinned host mirror of d_flag
   void* h_stage = nullptr;           // pinned staging for set/get_params (small models)
