@@ -75,10 +75,6 @@ __device__ __forceinline__ double predict_row_exact(const RowCtx& m, double w0,
   return result;
 }
 
-__device__ __forceinline__ void prefetch_l1(const void* p) {
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-}
-
 __global__ void __launch_bounds__(32, 1)
     fm_sgd_inorder_kernel(Params64 p, int n_factor, int use_w0, int use_w, HParams hp,
                           uint64_t n_rows, const uint64_t* __restrict__ row_ptr,
@@ -108,45 +104,9 @@ __global__ void __launch_bounds__(32, 1)
       my_y = target[rr];
     }
     int cnt = (int)min((uint64_t)32, n_rows - r0);
-    // The epoch is one dependency chain of L2 round trips.  Everything that does not
-    // depend on the chain is pulled into this SM's L1 ahead of time: the block's CSR
-    // entries now, each next row's w / V lines while the current row computes (a line
-    // the current row then stores to is updated in L1 by the same SM: still coherent).
-    {
-      const uint64_t eb = __shfl_sync(0xffffffffu, my_beg, 0);
-      const uint64_t ee = __shfl_sync(0xffffffffu, my_end, cnt - 1);
-      for (uint64_t j = eb + (uint64_t)lane * 32; j < ee; j += 32 * 32) {
-        prefetch_l1(col + j);
-        prefetch_l1(val + j);
-      }
-    }
     for (int q = 0; q < cnt; q++) {
       uint64_t beg = __shfl_sync(0xffffffffu, my_beg, q);
       uint64_t end = __shfl_sync(0xffffffffu, my_end, q);
-      if (q + 1 < cnt) {
-        // next row's lines -> L1, unless THIS row is about to store into the same 128-byte
-        // line (a fill racing with the write-through store could land stale data)
-        const uint64_t nb = __shfl_sync(0xffffffffu, my_beg, q + 1);
-        const uint64_t ne = __shfl_sync(0xffffffffu, my_end, q + 1);
-        const uint32_t nsz = (uint32_t)(ne - nb), csz = (uint32_t)(end - beg);
-        if (nsz <= 8 && csz <= 8) {
-          const uint64_t row_bytes = (uint64_t)m.k * 8;
-          for (uint32_t i = 0; i < nsz; i++) {
-            const uint32_t id = __ldg(col + nb + i);
-            const uint64_t v_lo = (id * row_bytes) >> 7, v_hi = (id * row_bytes + row_bytes - 1) >> 7;
-            bool clash = false;
-            for (uint32_t j = 0; j < csz; j++) {
-              const uint32_t cid = __ldg(col + beg + j);
-              const uint64_t c_lo = (cid * row_bytes) >> 7, c_hi = (cid * row_bytes + row_bytes - 1) >> 7;
-              clash |= !(v_hi < c_lo || c_hi < v_lo) || ((id >> 4) == (cid >> 4));
-            }
-            if (!clash) {
-              for (int f = lane * 16; f < m.k; f += 32 * 16) prefetch_l1(v + (size_t)id * m.k + f);
-              if (lane == 31 && m.k1) prefetch_l1(w + id);
-            }
-          }
-        }
-      }
       double y = (double)__shfl_sync(0xffffffffu, my_y, q);
       uint32_t size = (uint32_t)(end - beg);
       const uint32_t* c = col + beg;
