@@ -332,3 +332,39 @@ def test_in_warp_combining_sums_every_step(built_lib):
         assert np.all(np.abs(got_v - dv) <= 0.02 * av + 2e-6), "variant %d v" % variant
         hot = np.argmax(aw)
         assert abs(got_w[hot] - dw[hot]) < 0.05 * abs(dw[hot])  # the hottest feature, relative
+
+
+def test_c3_full_size_properties(built_lib):
+    """BASELINE config C3 at its full size: 10M rows x 39 one-hot fields over 1M features,
+    k=64, classification (390M entries, 3.2 GB of CSR).  Size-independent checks: a
+    zero-learning-rate epoch is the identity, training accuracy rises, state stays finite."""
+    n_rows, fields, n = 10_000_000, 39, 1_000_000
+    r = np.random.default_rng(11)
+    per = n // fields
+    col = r.integers(0, per, size=(n_rows, fields), dtype=np.uint32)
+    col += (np.arange(fields, dtype=np.uint32) * np.uint32(per))[None, :]
+    d = Data(np.arange(0, (n_rows + 1) * fields, fields, dtype=np.uint64), col.reshape(-1),
+             np.ones(n_rows * fields, dtype=np.float32),
+             np.where(r.random(n_rows) < 0.5, -1.0, 1.0).astype(np.float32), n)
+    del col
+    k = 64
+    cfg = _cfg(n, k, task=1, lr=0.0, mn=-1.0, mx=1.0)
+    init = (0.0, np.zeros(n), (r.standard_normal((k, n)) * 0.01))
+    l = make_learner(cfg, init, mode=MODE_HOGWILD)
+    l.pull_params()
+    v_before = l.fm.v.copy()
+    t0 = l.sgd_epoch(d)
+    l.pull_params()
+    assert np.array_equal(l.fm.v, v_before) and not l.fm.w.any()  # lr = 0: identity
+    acc0 = l.evaluate(d)
+    l.learn_rate = 0.01
+    l.push_hparams()
+    secs = [l.sgd_epoch(d) for _ in range(2)]
+    acc1 = l.evaluate(d)
+    print("C3 full size: %.1f ms/epoch (%.2f G ex/s), accuracy %.4f -> %.4f" % (
+        1e3 * min(secs), n_rows / min(secs) / 1e9, acc0, acc1))
+    assert acc1 > acc0 + 0.005
+    l.pull_params()
+    assert np.isfinite(l.fm.v).all() and np.isfinite(l.fm.w).all() and np.isfinite(l.fm.w0)
+    assert min(secs) < 0.2  # 10M rows: tens of milliseconds, not seconds
+    l.close()
