@@ -241,6 +241,18 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    tick = torch.zeros(1, device="cuda")
+
+    def align():
+        # the L2 flush takes a different time on every rank; without re-aligning, the
+        # first rank to start its epoch would be charged the other ranks' flush time
+        # while it waits in the exchange
+        if collective == "p2p":
+            if lib.fmb200_peer_barrier(ctx) != 0:
+                raise RuntimeError(lib.fmb200_last_error().decode())
+        elif collective == "nccl":
+            dist.all_reduce(tick)
+
     sampler = ClockSampler(local_rank)
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
@@ -254,6 +266,7 @@ def run_gpu_arm(args):
         wall0 = time.perf_counter()
         for a, b in ev:
             flush.zero_()          # evict the CSR and the parameters from L2 (untimed)
+            align()                # N > 1: all ranks enter the step together (untimed)
             a.record(stream)
             step()
             b.record(stream)

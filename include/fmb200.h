@@ -128,6 +128,8 @@ int fmb200_peer_export(fmb200_ctx* ctx, void* handle /* FMB200_IPC_HANDLE_BYTES 
 int fmb200_peer_attach_ipc(fmb200_ctx* ctx, int world, int rank, const void* handles /* world x 64 B */);
 int fmb200_peer_attach_local(fmb200_ctx* ctx, int world, int rank, fmb200_ctx* const* contexts);
 int fmb200_allreduce_mean(fmb200_ctx* ctx);
+/* stream-ordered barrier across the attached peers (no data); used to align ranks */
+int fmb200_peer_barrier(fmb200_ctx* ctx);
 
 /* Introspection for tests / bench */
 int fmb200_kernel_launches(fmb200_ctx* ctx, uint64_t* count); /* kernels launched so far */

@@ -46,6 +46,7 @@ SYMBOLS = {
     "fmb200_peer_attach_ipc": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_void_p]),
     "fmb200_peer_attach_local": (C.c_int, [_ctx, C.c_int, C.c_int, C.POINTER(_ctx)]),
     "fmb200_allreduce_mean": (C.c_int, [_ctx]),
+    "fmb200_peer_barrier": (C.c_int, [_ctx]),
     "fmb200_kernel_launches": (C.c_int, [_ctx, _u64p]),
     "fmb200_last_epoch_config": (C.c_int, [_ctx] + [_intp] * 7),
     "fmb200_set_tuning": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -608,6 +608,14 @@ int fmb200_allreduce_mean(fmb200_ctx* c) {
   return 0;
 }
 
+int fmb200_peer_barrier(fmb200_ctx* c) {
+  NEED_CTX(c);
+  if (c->peer_world <= 1) return 0;
+  if (bind(c)) return 1;
+  CK(launch_peer_barrier(c));
+  return 0;
+}
+
 int fmb200_stream(fmb200_ctx* c, void** cuda_stream) {
   NEED_CTX(c);
   if (cuda_stream) *cuda_stream = (void*)c->stream;

@@ -70,6 +70,28 @@ __global__ void __launch_bounds__(256) fm_peer_mean_kernel(const PeerArgs a) {
   }
 }
 
+// Cross-GPU barrier on the stream (no data): same signal / wait through the peers' flag
+// blocks, on its own flag row and sequence so it never interferes with the averaging.
+__global__ void fm_peer_barrier_kernel(const PeerArgs a) {
+  if (threadIdx.x < a.world) {
+    st_release_sys(a.flags[threadIdx.x] + FMB200_MAX_PEERS + a.rank, a.seq);
+    const unsigned int* mine = a.flags[a.rank] + FMB200_MAX_PEERS + threadIdx.x;
+    while ((int)(ld_acquire_sys(mine) - a.seq) < 0) {
+    }
+  }
+}
+
+cudaError_t launch_peer_barrier(fmb200_ctx* c) {
+  PeerArgs a;
+  for (int q = 0; q < c->peer_world; q++) a.flags[q] = reinterpret_cast<unsigned int*>(c->peer_base[q]);
+  a.world = c->peer_world;
+  a.rank = c->peer_rank;
+  a.seq = ++c->peer_bar_seq;
+  fm_peer_barrier_kernel<<<1, 32, 0, c->stream>>>(a);
+  c->launches++;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_peer_mean(fmb200_ctx* c) {
   PeerArgs a;
   const int cur = c->peer_cur;

@@ -104,7 +104,7 @@ struct fmb200_ctx {
   unsigned char* peer_base[FMB200_MAX_PEERS] = {nullptr};
   bool peer_ipc[FMB200_MAX_PEERS] = {false};
   int peer_world = 1, peer_rank = 0, peer_cur = 0;
-  unsigned int peer_seq = 0;
+  unsigned int peer_seq = 0, peer_bar_seq = 0;
   int tune_damp = 0;  // 0 auto, 1 force on, -1 force off
   int tune_variant = 0;  // 0 auto, 1 row-group kernel, 2 row-lane kernel when eligible
 };
@@ -128,6 +128,7 @@ cudaError_t launch_p32_to_p64(fmb200_ctx* c);
 cudaError_t launch_scale_p32(fmb200_ctx* c, float factor);
 // fm_peer.cu: one-shot all-reduce (mean) of the packed fp32 state over peer memory
 cudaError_t launch_peer_mean(fmb200_ctx* c);
+cudaError_t launch_peer_barrier(fmb200_ctx* c);
 cudaError_t launch_max_col(fmb200_ctx* c, const uint32_t* col, uint64_t nnz, unsigned int* out_max);
 // device-side structural check of row offsets (see fm_predict.cu)
 cudaError_t launch_csr_inspect(fmb200_ctx* c, const uint64_t* rp, uint64_t n_rows, uint64_t nnz,
