@@ -77,12 +77,17 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : (R > 20 ? 1 
   if (tid == 0) {
     for (int i = 0; i < HW_NSTAGE; i++) mbar_init(bars + i, 1);
     fence_mbar_init();
-    policy = policy_evict_first();
   }
+  if (tid == (int)blockDim.x - 32) policy = policy_evict_first();
   __syncthreads();
   uint32_t* s_tile = reinterpret_cast<uint32_t*>(smem + 208);  // [HW_NSTAGE] tile staged per stage
   TileSched sched{a.sched, a.n_tiles, false};
-  if (tid == 0) {
+  // producer duties (tile claims, TMA issue, bias reduction) sit on lane 0 of the LAST
+  // warp; warp 0 fetches and publishes the bias -- nobody waits on the producer before
+  // the end-of-tile barrier
+  const int ptid = (int)blockDim.x - 32;
+  uint32_t claim_raw = HW_NO_TILE;  // producer: a claim in flight (resolved one tile later)
+  if (tid == ptid) {
     for (int i = 0; i < HW_NSTAGE; i++) {
       const uint32_t t = sched.claim();
       s_tile[i] = t;
@@ -91,6 +96,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : (R > 20 ? 1 
         issue_tile(a, smem, bars, t, i, policy, __ldg(a.row_ptr + r0), __ldg(a.row_ptr + r1));
       }
     }
+    claim_raw = sched.fire();
   }
   __syncthreads();
 
@@ -111,8 +117,9 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : (R > 20 ? 1 
     // so the two dependent global loads overlap this tile's compute
     uint32_t nt = HW_NO_TILE;
     uint64_t nt_nb = 0, nt_ne = 0;
-    if (tid == 0) {
-      nt = sched.claim();
+    if (tid == ptid) {
+      nt = sched.resolve(claim_raw);  // fired a tile ago: long since returned
+      claim_raw = sched.fire();       // not looked at before the next tile
       if (nt != HW_NO_TILE) {
         const uint64_t r0 = (uint64_t)nt * TR, r1 = min(r0 + (uint64_t)TR, a.n_rows);
         nt_nb = __ldg(a.row_ptr + r0);
@@ -250,7 +257,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : (R > 20 ? 1 
       if (lane == 0) s_part[warp] = make_float2(msum, hsum);
     }
     __syncthreads();  // every warp is done with this stage; partials complete
-    if (tid == 0) {
+    if (tid == ptid) {
       s_tile[stage] = nt;
       if (nt != HW_NO_TILE) issue_tile(a, smem, bars, nt, stage, policy, nt_nb, nt_ne);
       if (use_w0) {
@@ -266,7 +273,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : (R > 20 ? 1 
       }
     }
   }
-  if (tid == 0) sched.finish(gridDim.x);
+  if (tid == ptid) sched.finish(gridDim.x, claim_raw);
 }
 
 // ---------------------------------------------------------------------------

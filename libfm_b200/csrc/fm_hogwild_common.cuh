@@ -85,7 +85,7 @@ struct BiasFetch {
   float pending; // lane 0 of warp 0: the in-flight value
   __device__ __forceinline__ void issue(const HogwildArgs& a, bool use_w0, int tid) {
     pending = 0.f;
-    if (use_w0 && tid == 0 && !(a.dbg & 8)) pending = ld_cg_f(a.w0);
+    if (use_w0 && tid == 0 && !(a.dbg & 8)) pending = ld_cg_f(a.w0);  // warp 0 fetches the bias
   }
   // returns the tile's bias in every thread of the CTA
   __device__ __forceinline__ float get(bool use_w0, int tid, int it, int nthreads) {
@@ -121,10 +121,23 @@ struct TileSched {
     }
     return t;
   }
-  __device__ __forceinline__ void finish(unsigned int n_ctas) {
-    while (!dry) claim();  // exactly one failed claim per CTA
+  // split claim: fire() only issues the atomic (its latency must not stall the producer
+  // thread, which also processes rows); resolve() interprets the value a tile later
+  __device__ __forceinline__ uint32_t fire() { return dry ? HW_NO_TILE : atomicAdd(w, 1u); }
+  __device__ __forceinline__ uint32_t resolve(uint32_t raw) {
+    if (raw >= n_tiles) {
+      dry = true;
+      return HW_NO_TILE;
+    }
+    return raw;
+  }
+  // `last_raw`: the claim still in flight.  Its value must have RETURNED (the counter
+  // increment performed) before this CTA reports itself dry, or the reset below could be
+  // overtaken by it and the next launch would start at tile 1.
+  __device__ __forceinline__ void finish(unsigned int n_ctas, uint32_t last_raw) {
+    unsigned int inc = (last_raw == 0x7fffffffu) ? 2u : 1u;  // data dependence on the return value
     __threadfence();
-    if (atomicAdd(w + 1, 1u) == n_ctas - 1) {
+    if (atomicAdd(w + 1, inc) == n_ctas - 1) {
       w[0] = 0u;
       w[1] = 0u;
     }

@@ -48,12 +48,17 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
   if (tid == 0) {
     for (int i = 0; i < HW_NSTAGE; i++) mbar_init(bars + i, 1);
     fence_mbar_init();
-    policy = policy_evict_first();
   }
+  if (tid == (int)blockDim.x - 32) policy = policy_evict_first();
   __syncthreads();
   uint32_t* s_tile = reinterpret_cast<uint32_t*>(smem + 208);  // [HW_NSTAGE] tile staged per stage
   TileSched sched{a.sched, a.n_tiles, false};
-  if (tid == 0) {
+  // producer duties (tile claims, TMA issue, bias reduction) sit on lane 0 of the LAST
+  // warp; warp 0 fetches and publishes the bias -- nobody waits on the producer before
+  // the end-of-tile barrier
+  const int ptid = (int)blockDim.x - 32;
+  uint32_t claim_raw = HW_NO_TILE;  // producer: a claim in flight (resolved one tile later)
+  if (tid == ptid) {
     for (int i = 0; i < HW_NSTAGE; i++) {
       const uint32_t t = sched.claim();
       s_tile[i] = t;
@@ -62,6 +67,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
         issue_tile(a, smem, bars, t, i, policy, __ldg(a.row_ptr + r0), __ldg(a.row_ptr + r1));
       }
     }
+    claim_raw = sched.fire();
   }
   __syncthreads();
 
@@ -78,8 +84,9 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
     if (tile == HW_NO_TILE) break;  // this CTA's claims ran dry
     uint32_t nt = HW_NO_TILE;
     uint64_t nt_nb = 0, nt_ne = 0;
-    if (tid == 0) {
-      nt = sched.claim();
+    if (tid == ptid) {
+      nt = sched.resolve(claim_raw);  // fired a tile ago: long since returned
+      claim_raw = sched.fire();       // not looked at before the next tile
       if (nt != HW_NO_TILE) {
         const uint64_t r0 = (uint64_t)nt * TR, r1 = min(r0 + (uint64_t)TR, a.n_rows);
         nt_nb = __ldg(a.row_ptr + r0);
@@ -278,7 +285,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
       if (lane == 0) s_part[tid >> 5] = make_float2(msum, hsum);
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid == ptid) {
       s_tile[stage] = nt;
       if (nt != HW_NO_TILE) issue_tile(a, smem, bars, nt, stage, policy, nt_nb, nt_ne);
       if (use_w0) {
@@ -294,7 +301,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
       }
     }
   }
-  if (tid == 0) sched.finish(gridDim.x);
+  if (tid == ptid) sched.finish(gridDim.x, claim_raw);
 }
 
 template <int GP, int Z>
