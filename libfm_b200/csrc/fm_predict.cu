@@ -28,9 +28,9 @@ struct PredictArgs {
   double* partials;
 };
 
-template <int G, int S>
+template <int G, int S, int R, int RW>
 __global__ void __launch_bounds__(256) fm_predict32_kernel(const PredictArgs a) {
-  using RG = RowGroup<G, S, 2, 1>;
+  using RG = RowGroup<G, S, R, RW>;
   constexpr int E = RG::E;
   constexpr int RPW = 32 / E;
   const int lane = threadIdx.x & 31;
@@ -100,18 +100,29 @@ __global__ void __launch_bounds__(256) fm_predict32_kernel(const PredictArgs a) 
 
 using PredictFn = void (*)(const PredictArgs);
 
+// the same (R, RW) register-cache classes as the training kernel: all of a row's gathers
+// are in flight before the first is consumed
+template <int G, int S>
+static PredictFn pick_predict_r(int cls) {
+  switch (cls) {
+    case 0: return fm_predict32_kernel<G, S, 2, 1>;
+    case 1: return fm_predict32_kernel<G, S, 8, 2>;
+    default: return fm_predict32_kernel<G, S, 20, 2>;
+  }
+}
+
 template <int G>
-static PredictFn pick_predict_s(int S) {
+static PredictFn pick_predict_s(int S, int cls) {
   if constexpr (G <= 4) {
-    if (S >= 8) return fm_predict32_kernel<G, 8>;
+    if (S >= 8) return pick_predict_r<G, 8>(cls);
   }
   if constexpr (G <= 8) {
-    if (S >= 4) return fm_predict32_kernel<G, 4>;
+    if (S >= 4) return pick_predict_r<G, 4>(cls);
   }
   if constexpr (G <= 16) {
-    if (S >= 2) return fm_predict32_kernel<G, 2>;
+    if (S >= 2) return pick_predict_r<G, 2>(cls);
   }
-  return fm_predict32_kernel<G, 1>;
+  return pick_predict_r<G, 1>(cls);
 }
 
 cudaError_t launch_predict32(fmb200_ctx* c, const DataSlot& d, int transform, double* out_pred,
@@ -119,14 +130,17 @@ cudaError_t launch_predict32(fmb200_ctx* c, const DataSlot& d, int transform, do
   if (c->kp / 4 > 32) return cudaErrorInvalidValue;
   int G, S;
   pick_geometry(c->kp, d.n_rows, d.nnz, &G, &S);
+  const double avg = d.n_rows ? (double)d.nnz / (double)d.n_rows : 1.0;
+  const int iters = (int)((avg + S - 1) / S);
+  const int cls = iters <= 2 ? 0 : (iters <= 8 ? 1 : 2);
   PredictFn fn;
   switch (G) {
-    case 1: fn = pick_predict_s<1>(S); break;
-    case 2: fn = pick_predict_s<2>(S); break;
-    case 4: fn = pick_predict_s<4>(S); break;
-    case 8: fn = pick_predict_s<8>(S); break;
-    case 16: fn = pick_predict_s<16>(S); break;
-    default: fn = pick_predict_s<32>(S); break;
+    case 1: fn = pick_predict_s<1>(S, cls); break;
+    case 2: fn = pick_predict_s<2>(S, cls); break;
+    case 4: fn = pick_predict_s<4>(S, cls); break;
+    case 8: fn = pick_predict_s<8>(S, cls); break;
+    case 16: fn = pick_predict_s<16>(S, cls); break;
+    default: fn = pick_predict_s<32>(S, cls); break;
   }
   PredictArgs a;
   a.row_ptr = d.row_ptr;
