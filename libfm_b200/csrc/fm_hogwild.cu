@@ -398,12 +398,19 @@ static cudaError_t launch_rowlane(fmb200_ctx* c, const DataSlot& d, bool* handle
   // in-warp merging of same-feature steps pays once a warp of 32 rows is likely to hold
   // the hottest feature more than once
   const bool combine = (double)d.max_feat_cnt * 32.0 / (double)d.n_rows > 0.5;
-  HogwildKernelFn fn = pick_rowlane_kernel(gp, (int)d.max_row_nnz, damp, combine);
+  // variant 3 = warp-specialised (producer warp + mbarrier hand-offs, no block barrier)
+  const char* ev = getenv("FMB200_VARIANT");  // development override
+  const bool ws = (ev ? atoi(ev) : c->tune_variant) == 3;
+  HogwildKernelFn fn = ws ? pick_rowlane_ws_kernel(gp, (int)d.max_row_nnz, damp, combine)
+                          : pick_rowlane_kernel(gp, (int)d.max_row_nnz, damp, combine);
   if (fn == nullptr) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int hdr = ws ? 512 : HW_HDR_BYTES;
+  const int smem_ws = hdr + HW_NSTAGE * (int)sbytes;
+  const int launch_threads = ws ? threads + 32 : threads;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ws);
   if (e != cudaSuccess) return e;
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, launch_threads, smem_ws);
   if (e != cudaSuccess) return e;
   if (occ < 1) return cudaErrorInvalidConfiguration;
   const int per_sm = c->tune_ctas_per_sm > 0 ? std::min(c->tune_ctas_per_sm, occ) : occ;
@@ -411,10 +418,11 @@ static cudaError_t launch_rowlane(fmb200_ctx* c, const DataSlot& d, bool* handle
   const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)c->sm_count * per_sm);
   HogwildArgs a = make_args(c, d, n_tiles, TR, cap, sbytes);
   a.conc_scale = (float)(std::min<double>((double)d.n_rows, (double)grid * TR) / (double)d.n_rows);
-  a.w0_conc = (float)std::min<double>((double)d.n_rows, (double)grid * TR);
-  fn<<<grid, threads, smem, c->stream>>>(a);
+  // the warp-specialised kernel reads the bias when a stage is filled: HW_NSTAGE tiles ahead
+  a.w0_conc = (float)std::min<double>((double)d.n_rows, (double)grid * TR * (ws ? HW_NSTAGE : 1));
+  fn<<<grid, launch_threads, smem_ws, c->stream>>>(a);
   c->launches++;
-  c->last_cfg = EpochConfig{1, (int)std::max<uint32_t>(1, d.max_row_nnz), TR, grid, threads, smem, damp ? 1 : 0};
+  c->last_cfg = EpochConfig{1, (int)std::max<uint32_t>(1, d.max_row_nnz), TR, grid, launch_threads, smem_ws, damp ? 1 : 0};
   *handled = true;
   return cudaGetLastError();
 }

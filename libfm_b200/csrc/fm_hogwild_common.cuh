@@ -148,5 +148,7 @@ using HogwildKernelFn = void (*)(const HogwildArgs);
 
 // fm_rowlane.cu: kernel for (float4 chunks per row gp in {1,2}, rows of at most Z entries)
 HogwildKernelFn pick_rowlane_kernel(int gp, int max_row_nnz, bool damp, bool combine);
+// warp-specialised variant: blockDim = rows_per_tile + 32, smem header 512 B
+HogwildKernelFn pick_rowlane_ws_kernel(int gp, int max_row_nnz, bool damp, bool combine);
 
 }  // namespace fmb

@@ -29,10 +29,10 @@ def run(name, d, k, task=0, tunings=((0,0,0,0,0),), epochs=5, inorder=False):
 
 if __name__ == "__main__":
     d = synth.movielens_1m_shaped(seed=7)
-    tun = [(0,0,0,0,0), (0,0,0,-1,0), (0,0,128,0,0), (4,0,0,-1,0), (0,0,0,0,1), (0,0,0,-1,1)]
+    tun = [(0,0,0,0,0), (0,0,0,0,3), (0,0,128,0,3), (4,0,0,0,3), (0,0,0,0,1)]
     run("C2", d, 8, tunings=tun, inorder=True)
     dz = synth.movielens_1m_shaped(seed=7, zipf=1.0)
-    run("C2zipf", dz, 8, tunings=[(0,0,0,0,0),(0,0,0,0,1)])
+    run("C2zipf", dz, 8, tunings=[(0,0,0,0,0),(0,0,0,0,3)])
     d3 = synth.multi_field(1_000_000, 39, 1_000_000, 11); d3.binarize_targets()
     run("C3-1M", d3, 64, task=1)
     run("k128", d3, 128, task=1)
