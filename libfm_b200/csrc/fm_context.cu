@@ -212,8 +212,6 @@ int fmb200_create(fmb200_ctx** out, int device, uint32_t n_attr, int num_factor,
   CK(cudaMalloc(&c->p64.base, c->p64.n_doubles * sizeof(double)));
   CK(cudaMemsetAsync(c->p32.base, 0, c->p32.n_floats * sizeof(float), c->stream));
   CK(cudaMemsetAsync(c->p64.base, 0, c->p64.n_doubles * sizeof(double), c->stream));
-  CK(cudaMalloc(&c->d_w0_accum, sizeof(float)));
-  CK(cudaMalloc(&c->d_done, sizeof(unsigned int)));
   CK(cudaMalloc(&c->d_sched, 2 * sizeof(unsigned int)));
   CK(cudaMemsetAsync(c->d_sched, 0, 2 * sizeof(unsigned int), c->stream));
   CK(cudaMalloc(&c->d_flag, 16 * sizeof(unsigned int)));
@@ -225,8 +223,6 @@ int fmb200_create(fmb200_ctx** out, int device, uint32_t n_attr, int num_factor,
       c->h_stage_bytes = need;
     }
   }
-  CK(cudaMemsetAsync(c->d_w0_accum, 0, sizeof(float), c->stream));
-  CK(cudaMemsetAsync(c->d_done, 0, sizeof(unsigned int), c->stream));
   CK(cudaStreamSynchronize(c->stream));
   *out = c;
   return 0;
@@ -243,8 +239,6 @@ void fmb200_destroy(fmb200_ctx* c) {
   if (c->p64.base) cudaFree(c->p64.base);
   if (c->d_partials) cudaFree(c->d_partials);
   if (c->d_pred) cudaFree(c->d_pred);
-  if (c->d_w0_accum) cudaFree(c->d_w0_accum);
-  if (c->d_done) cudaFree(c->d_done);
   if (c->d_sched) cudaFree(c->d_sched);
   if (c->d_flag) cudaFree(c->d_flag);
   if (c->h_flag) cudaFreeHost(c->h_flag);

@@ -5,20 +5,26 @@
 // + loss multiplier + fm_SGD, fm_sgd.h:33-51) with ONE persistent kernel launch
 // per epoch.
 //
-// Structure
-//  * grid = (#SMs x CTAs/SM) persistent CTAs; CTA b takes row tiles b, b+grid, ...
-//    (tiles = rows_per_tile consecutive rows, so the set of rows in flight is a
-//    window sliding through the file in order).
-//  * CSR staging: thread 0 is the TMA producer.  Per tile it issues four 1-D bulk
-//    copies (cp.async.bulk global->shared, mbarrier complete_tx): row offsets,
-//    targets, column ids, values; NSTAGE tiles are in flight per CTA, marked
-//    L2 evict_first (the CSR is streamed once per epoch).
+// Structure (shared with the one-lane-per-row kernel of fm_rowlane.cu, which serves
+// k <= 8 with short rows; this kernel serves every other shape)
+//  * persistent grid = (#SMs x CTAs/SM); CTAs claim row tiles (rows_per_tile consecutive
+//    rows) from a global counter in file order (TileSched), so the rows in flight are one
+//    window sliding through the file and the tail of the epoch is balanced.
+//  * CSR staging: lane 0 of the last warp is the TMA producer.  Per tile it issues four
+//    1-D bulk copies (cp.async.bulk global->shared, mbarrier complete_tx): row offsets,
+//    targets, column ids, values; NSTAGE tiles are in flight per CTA, marked L2
+//    evict_first (the CSR is streamed once per epoch).  Claims and the row offsets of the
+//    next tile are fetched a tile ahead so the producer never stalls on them.
 //  * compute: every warp handles U x 32/E rows at a time with the RowGroup mapping
 //    (fm_rowgroup.cuh): the gathers of all U row sets are issued before any is
 //    consumed (memory-level parallelism), V rows as float4 with ld.global.cg
 //    (parameters are mutated by other SMs through L2, so L1 must not serve them),
 //    per-factor sums by segmented warp shuffles, write-back as fire-and-forget
 //    red.global.add.v4.f32 / red.global.add.f32 (Hogwild: no locks, no CAS).
+//  * bias: warp 0 fetches w0 once per tile (its sector is reduced into by every CTA, so
+//    loads of it queue at one L2 slice) and publishes it through shared memory + named
+//    barrier 1; per-warp partial sums meet in shared memory; one damped reduction per
+//    tile goes to the global w0.
 //  * concurrency control.  The reference is strictly sequential; Hogwild sums the
 //    steps of all examples that are in flight together.  For a parameter block
 //    shared by c concurrent examples that sum has gain c*lr*h (h = curvature of
@@ -32,11 +38,10 @@
 //    which reproduces the reference step for cold features / a single row.
 //      - w0: every CTA accumulates sum(mult + reg0*w0) and the mean SECANT curvature
 //        h_t = mult_t / (p_raw_t - y_t) of a tile (1 where the score is unclamped,
-//        < 1 where fm_learn_sgd_element.h:60-61 clamps it; logistic: s(1-s)) and
-//        applies ONE damped reduction to the global w0 per tile, with
+//        < 1 where fm_learn_sgd_element.h:60-61 clamps it; logistic: s(1-s)), with
 //        c = rows in flight = min(N, grid * rows_per_tile).
-//      - w_i, V_i (template flag DAMP, on when some feature is hot enough to
-//        matter): c_i = max(1, count_i * W / N) from a per-feature occurrence table
+//      - w_i, V_i (template flag DAMP, compiled in when the hottest feature
+//        has c*lr > 0.5): c_i = max(1, count_i * W / N) from a per-feature occurrence table
 //        built at upload (W = rows being processed concurrently).
 //      - every block a row touches contracts the SAME residual, so all of them use
 //        the row's JOINT curvature h = h_loss * (1 + sum_i x_i^2 + sum_i |d p/d V_i|^2)
@@ -45,7 +50,6 @@
 // Algorithmic HBM traffic per example (roofline numerator, BASELINE.json):
 // 2*k*nnz*4 bytes (V rows read + written back).
 #include <algorithm>
-#include <cstdlib>
 
 #include "fm_hogwild_common.cuh"
 #include "fm_rowgroup.cuh"
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : (R > 20 ? 1 
                      sv * (nlr_mult * (gu.acc.z * x - v.z * x2) + nlr_regv * v.z),
                      sv * (nlr_mult * (gu.acc.w * x - v.w * x2) + nlr_regv * v.w));
         };
-        if (c < a.gp && !(a.dbg & 1)) {
+        if (c < a.gp) {
 #pragma unroll
           for (int q = 0; q < R; ++q) {
             const int j = gu.beg + s + q * S;
@@ -234,7 +238,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : (R > 20 ? 1 
           }
           red_add_f(a.w + (size_t)id * a.ws, sw * (nlr_mult * x + nlr_regw * wv));
         };
-        if (use_w && !(a.dbg & 2)) {
+        if (use_w) {
 #pragma unroll
           for (int t = 0; t < RW; ++t) {
             const int j = gu.beg + lig + t * E;
@@ -269,7 +273,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : (R > 20 ? 1 
         const float T = (float)rows_here;
         M += T * a.reg0 * w0;  // sum_t (mult_t + reg0*w0)
         const float gsc = gamma_scale(fmaxf(a.w0_conc, 1.f), lr * (H / T + a.reg0));
-        if (!(a.dbg & 4)) red_add_f(a.w0, -lr * gsc * M);
+        red_add_f(a.w0, -lr * gsc * M);
       }
     }
   }
@@ -373,8 +377,6 @@ static HogwildArgs make_args(fmb200_ctx* c, const DataSlot& d, uint64_t n_tiles,
   a.conc_scale = 1.f;
   a.w0_conc = 1.f;
   a.sched = c->d_sched;
-  const char* dbg = getenv("FMB200_DEBUG");
-  a.dbg = dbg ? atoi(dbg) : 0;
   return a;
 }
 
@@ -399,8 +401,7 @@ static cudaError_t launch_rowlane(fmb200_ctx* c, const DataSlot& d, bool* handle
   // the hottest feature more than once
   const bool combine = (double)d.max_feat_cnt * 32.0 / (double)d.n_rows > 0.5;
   // variant 3 = warp-specialised (producer warp + mbarrier hand-offs, no block barrier)
-  const char* ev = getenv("FMB200_VARIANT");  // development override
-  const bool ws = (ev ? atoi(ev) : c->tune_variant) == 3;
+  const bool ws = c->tune_variant == 3;
   HogwildKernelFn fn = ws ? pick_rowlane_ws_kernel(gp, (int)d.max_row_nnz, damp, combine)
                           : pick_rowlane_kernel(gp, (int)d.max_row_nnz, damp, combine);
   if (fn == nullptr) return cudaSuccess;

@@ -33,7 +33,6 @@ struct HogwildArgs {
   float conc_scale;       // rows processed concurrently / n_rows: count -> concurrency
   float w0_conc;          // rows in flight w.r.t. the bias (tile granularity)
   unsigned int* sched;    // [0] next unclaimed tile, [1] CTAs that ran dry (both 0 between launches)
-  int dbg;                // development only (FMB200_DEBUG): 1 = skip V reductions, 2 = skip w reductions
 };
 
 __device__ __forceinline__ unsigned char* stage_base(unsigned char* smem, const HogwildArgs& a,
@@ -85,7 +84,7 @@ struct BiasFetch {
   float pending; // lane 0 of warp 0: the in-flight value
   __device__ __forceinline__ void issue(const HogwildArgs& a, bool use_w0, int tid) {
     pending = 0.f;
-    if (use_w0 && tid == 0 && !(a.dbg & 8)) pending = ld_cg_f(a.w0);  // warp 0 fetches the bias
+    if (use_w0 && tid == 0) pending = ld_cg_f(a.w0);  // warp 0 fetches the bias
   }
   // returns the tile's bias in every thread of the CTA
   __device__ __forceinline__ float get(bool use_w0, int tid, int it, int nthreads) {

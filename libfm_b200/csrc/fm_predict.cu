@@ -201,16 +201,6 @@ __global__ void scale_kernel(float* p, uint64_t n, float f) {
     p[i] *= f;
 }
 
-__global__ void max_col_kernel(const uint32_t* __restrict__ col, uint64_t nnz,
-                               unsigned int* out_max) {
-  unsigned int m = 0;
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nnz;
-       i += (uint64_t)gridDim.x * blockDim.x)
-    m = max(m, col[i]);
-  m = __reduce_max_sync(0xffffffffu, m);
-  if ((threadIdx.x & 31) == 0) atomicMax(out_max, m);
-}
-
 // occurrence histogram of the column ids + the largest id seen (ids >= n are
 // counted nowhere: the caller rejects the data set when max id >= n).
 // SMEM_BINS > 0: the table fits in shared memory (n <= SMEM_BINS): per-CTA private
@@ -320,13 +310,6 @@ cudaError_t launch_p32_to_p64(fmb200_ctx* c) {
 cudaError_t launch_scale_p32(fmb200_ctx* c, float factor) {
   scale_kernel<<<grid_for(c, c->p32.n_floats), 256, 0, c->stream>>>(c->p32.base, c->p32.n_floats,
                                                                    factor);
-  c->launches++;
-  return cudaGetLastError();
-}
-
-cudaError_t launch_max_col(fmb200_ctx* c, const uint32_t* col, uint64_t nnz,
-                           unsigned int* out_max) {
-  max_col_kernel<<<grid_for(c, nnz), 256, 0, c->stream>>>(col, nnz, out_max);
   c->launches++;
   return cudaGetLastError();
 }

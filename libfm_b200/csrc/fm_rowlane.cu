@@ -210,12 +210,12 @@ __device__ __forceinline__ void rowlane_tile(const HogwildArgs& a, const uint64_
       const float4 va = odd ? recv : keep;
       // row B (odd lane's): even writes the received low half, odd writes its high half
       const float4 vb = odd ? keep : recv;
-      if (onA && !(a.dbg & 1)) red_add_f4(a.v + ((size_t)idA * 2 + odd) * 4, va.x, va.y, va.z, va.w);
-      if (onB && !(a.dbg & 1)) red_add_f4(a.v + ((size_t)idB * 2 + odd) * 4, vb.x, vb.y, vb.z, vb.w);
+      if (onA) red_add_f4(a.v + ((size_t)idA * 2 + odd) * 4, va.x, va.y, va.z, va.w);
+      if (onB) red_add_f4(a.v + ((size_t)idB * 2 + odd) * 4, vb.x, vb.y, vb.z, vb.w);
     } else {
-      if (on_c && !(a.dbg & 1)) red_add_f4(a.v + (size_t)id[e] * 4, d[0], d[1], d[2], d[3]);
+      if (on_c) red_add_f4(a.v + (size_t)id[e] * 4, d[0], d[1], d[2], d[3]);
     }
-    if (on_c && use_w && !(a.dbg & 2)) red_add_f(a.w + (size_t)id[e] * a.ws, dw);
+    if (on_c && use_w) red_add_f(a.w + (size_t)id[e] * a.ws, dw);
   }
 
   mult_out = mult;
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
         const float T = (float)rows_here;
         M += T * a.reg0 * w0;
         const float gsc = gamma_scale(fmaxf(a.w0_conc, 1.f), lr * (H / T + a.reg0));
-        if (!(a.dbg & 4)) red_add_f(a.w0, -lr * gsc * M);
+        red_add_f(a.w0, -lr * gsc * M);
       }
     }
   }
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS + 32, 3) fm_sgd_rowlane_ws_kern
         mbar_arrive(full + stage);  // wakes the consumers; they see NO_TILE and leave
         return;
       }
-      s_w0[stage] = (use_w0 && !(a.dbg & 8)) ? ld_cg_f(a.w0) : 0.f;
+      s_w0[stage] = use_w0 ? ld_cg_f(a.w0) : 0.f;
       const uint64_t r0 = (uint64_t)t * TR, r1 = min(r0 + (uint64_t)TR, a.n_rows);
       const uint64_t nb = __ldg(a.row_ptr + r0), ne = __ldg(a.row_ptr + r1);
       const uint64_t ab = nb & ~3ull, ae = (ne + 3ull) & ~3ull;
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS + 32, 3) fm_sgd_rowlane_ws_kern
         const float T = (float)min((uint64_t)TR, a.n_rows - row0);
         M += T * a.reg0 * s_w0[stage];
         const float gsc = gamma_scale(fmaxf(a.w0_conc, 1.f), a.lr * (H / T + a.reg0));
-        if (!(a.dbg & 4)) red_add_f(a.w0, -a.lr * gsc * M);
+        red_add_f(a.w0, -a.lr * gsc * M);
       }
       fill(stage, sched.claim());
     }

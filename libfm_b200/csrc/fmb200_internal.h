@@ -88,8 +88,6 @@ struct fmb200_ctx {
   int n_partials = 0;
   double* d_pred = nullptr;  // predict output staging
   uint64_t pred_cap = 0;
-  float* d_w0_accum = nullptr;       // hogwild: row-weighted sum of CTA-local biases
-  unsigned int* d_done = nullptr;    // (unused)
   unsigned int* d_sched = nullptr;   // hogwild tile scheduler: [next tile, CTAs run dry]
   unsigned int* d_flag = nullptr;    // 16 device words: upload-time inspection results
   unsigned int* h_flag = nullptr;    // pinned host mirror of d_flag
@@ -129,7 +127,6 @@ cudaError_t launch_scale_p32(fmb200_ctx* c, float factor);
 // fm_peer.cu: one-shot all-reduce (mean) of the packed fp32 state over peer memory
 cudaError_t launch_peer_mean(fmb200_ctx* c);
 cudaError_t launch_peer_barrier(fmb200_ctx* c);
-cudaError_t launch_max_col(fmb200_ctx* c, const uint32_t* col, uint64_t nnz, unsigned int* out_max);
 // device-side structural check of row offsets (see fm_predict.cu)
 cudaError_t launch_csr_inspect(fmb200_ctx* c, const uint64_t* rp, uint64_t n_rows, uint64_t nnz,
                                unsigned int* out8);

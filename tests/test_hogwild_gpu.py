@@ -129,7 +129,7 @@ def test_rowlane_and_rowgroup_kernels_agree(k, maxnnz, built_lib):
     init32 = tuple(np.float32(x).astype(np.float64) for x in init)
     p = _port(cfg, init32)
     p.sgd_epoch(d, 0, 0.05, 1.0, 5.0)
-    for variant, lanes in ((1, None), (2, 1)):
+    for variant, lanes in ((1, None), (2, 1), (3, 1)):  # row-group, row-lane, warp-specialised row-lane
         l = make_learner(cfg, init, mode=MODE_HOGWILD)
         l.set_tuning(variant=variant)
         l.sgd_epoch(d)
