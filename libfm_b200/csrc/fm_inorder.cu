@@ -35,6 +35,17 @@ __device__ __forceinline__ double predict_row_exact(const RowCtx& m, double w0,
                                                     const uint32_t* __restrict__ col,
                                                     const float* __restrict__ val, uint32_t size,
                                                     double (&sum)[KF_MAX], int lane) {
+  // Issue this lane's factor gathers BEFORE lane 0 walks the linear weights: both are
+  // L2 round trips, and the warp would otherwise serialise them (lane 0's branch runs
+  // first).  Short rows of models with k <= 32 keep the values in registers.
+  constexpr int VC = 8;
+  const bool cached = size <= (uint32_t)VC && m.k <= 32;
+  double vcache[VC];
+  if (cached && lane < m.k) {
+#pragma unroll
+    for (int i = 0; i < VC; i++)
+      if ((uint32_t)i < size) vcache[i] = m.v[(size_t)col[i] * m.k + lane];
+  }
   double result = 0;
   if (lane == 0) {
     if (m.k0) result += w0;
@@ -51,10 +62,21 @@ __device__ __forceinline__ double predict_row_exact(const RowCtx& m, double w0,
     int f = lane + 32 * j;
     double s = 0, ss = 0;
     if (f < m.k) {
-      for (uint32_t i = 0; i < size; i++) {
-        double d = m.v[(size_t)col[i] * m.k + f] * (double)val[i];
-        s += d;
-        ss += d * d;
+      if (cached) {  // j == 0 only (k <= 32)
+#pragma unroll
+        for (int i = 0; i < VC; i++) {
+          if ((uint32_t)i < size) {
+            double d = vcache[i] * (double)val[i];
+            s += d;
+            ss += d * d;
+          }
+        }
+      } else {
+        for (uint32_t i = 0; i < size; i++) {
+          double d = m.v[(size_t)col[i] * m.k + f] * (double)val[i];
+          s += d;
+          ss += d * d;
+        }
       }
     }
     sum[j] = s;

@@ -152,3 +152,33 @@ def test_world_size_2_gloo_allreduce_and_shards(tmp_path):
                               stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under libfm_b200/ (Python, C++, CUDA) may
+    import, include, link or dlopen it."""
+    import re
+    bad = []
+    for root, _, files in os.walk(os.path.join(ROOT, "libfm_b200")):
+        if "__pycache__" in root:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(root, f), errors="ignore").read()
+                if re.search(r"(import\s+oracle|from\s+oracle|libfm_oracle|libfm_ref|oracle/)", txt):
+                    bad.append(os.path.join(root, f))
+    assert not bad, bad
+
+
+def test_bench_reference_arm_line(tmp_path):
+    """`bench.py --impl reference` runs the reference's CPU row loop and prints the contract's JSON."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "examples/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("MovieLens-1M-shaped examples/sec")
+    assert line["cpu_baseline"]["cores"] == 1 and line["cpu_baseline"]["kind"] in ("reference", "port")
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert 1e6 < line["value"] < 1e9  # a single CPU core: tens of millions of examples/s
