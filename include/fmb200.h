@@ -140,7 +140,8 @@ int fmb200_last_epoch_config(fmb200_ctx* ctx, int* lanes_per_row, int* slots, in
  * damping (on when the hottest feature's expected concurrency matters), 1 = force
  * on, -1 = force off (plain summed Hogwild on w/V).  variant: 0 = automatic choice
  * of the epoch kernel, 1 = sub-warp row-group kernel, 2 = one-lane-per-row kernel
- * (k <= 8, rows of <= 4 entries; ignored when not applicable). */
+ * (k <= 8, rows of <= 4 entries; ignored when not applicable), 3 = its warp-specialised
+ * form (producer warp + mbarrier hand-offs; bias read three tiles ahead). */
 int fmb200_set_tuning(fmb200_ctx* ctx, int ctas_per_sm, int rows_per_tile, int threads, int damp,
                       int variant);
 
