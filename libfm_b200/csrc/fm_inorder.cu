@@ -31,10 +31,14 @@ struct RowCtx {
 
 // Exact fm_model::predict for one row, executed by a full warp.  Returns the
 // score in every lane; sum[j] holds sum_f for f = lane + 32*j.
+// KF = factors per lane (1, 2, 4 or 8): the single warp of the in-order epoch has no
+// other warp to hide behind, so dead predicated code for unused factor slots (and the
+// instruction-cache misses it causes) is paid in full -- the kernels are instantiated per KF.
+template <int KF>
 __device__ __forceinline__ double predict_row_exact(const RowCtx& m, double w0,
                                                     const uint32_t* __restrict__ col,
                                                     const float* __restrict__ val, uint32_t size,
-                                                    double (&sum)[KF_MAX], int lane) {
+                                                    double (&sum)[KF], int lane) {
   // Issue this lane's factor gathers BEFORE lane 0 walks the linear weights: both are
   // L2 round trips, and the warp would otherwise serialise them (lane 0's branch runs
   // first).  Short rows of models with k <= 32 keep the values in registers.
@@ -56,9 +60,9 @@ __device__ __forceinline__ double predict_row_exact(const RowCtx& m, double w0,
     }
   }
   result = __shfl_sync(0xffffffffu, result, 0);
-  double term[KF_MAX];
+  double term[KF];
 #pragma unroll
-  for (int j = 0; j < KF_MAX; j++) {
+  for (int j = 0; j < KF; j++) {
     int f = lane + 32 * j;
     double s = 0, ss = 0;
     if (f < m.k) {
@@ -84,7 +88,7 @@ __device__ __forceinline__ double predict_row_exact(const RowCtx& m, double w0,
   }
   // ordered accumulation over f = 0..k-1 (all lanes redundantly, same ops)
 #pragma unroll
-  for (int j = 0; j < KF_MAX; j++) {
+  for (int j = 0; j < KF; j++) {
     int fbase = 32 * j;
     if (fbase < m.k) {
       int cnt = min(32, m.k - fbase);
@@ -97,6 +101,7 @@ __device__ __forceinline__ double predict_row_exact(const RowCtx& m, double w0,
   return result;
 }
 
+template <int KF>
 __global__ void __launch_bounds__(32, 1)
     fm_sgd_inorder_kernel(Params64 p, int n_factor, int use_w0, int use_w, HParams hp,
                           uint64_t n_rows, const uint64_t* __restrict__ row_ptr,
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(32, 1)
   double* v = p.v();
   double w0 = *p.w0();
   const double lr = hp.lr, reg0 = hp.reg0, regw = hp.regw, regv = hp.regv;
-  double sum[KF_MAX];
+  double sum[KF];
 
   for (uint64_t r0 = 0; r0 < n_rows; r0 += 32) {
     // the CSR is immutable: fetch 32 rows' bounds and targets at once
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(32, 1)
       const uint32_t* c = col + beg;
       const float* x = val + beg;
 
-      double pr = predict_row_exact(m, w0, c, x, size, sum, lane);
+      double pr = predict_row_exact<KF>(m, w0, c, x, size, sum, lane);
       // fm_learn_sgd_element.h:58-65
       double mult = 0;
       if (hp.task == FMB200_TASK_REGRESSION) {
@@ -157,7 +162,7 @@ __global__ void __launch_bounds__(32, 1)
       }
       // fm_sgd.h:44-50 (lane f%32 is the only reader/writer of V[:, f])
 #pragma unroll
-      for (int j = 0; j < KF_MAX; j++) {
+      for (int j = 0; j < KF; j++) {
         int f = lane + 32 * j;
         if (f < m.k) {
           for (uint32_t i = 0; i < size; i++) {
@@ -177,6 +182,7 @@ __global__ void __launch_bounds__(32, 1)
 
 // Exact fp64 scores: one warp per row; optional metric partials per block in
 // fixed (deterministic) order: each block reduces its warps in warp order.
+template <int KF>
 __global__ void __launch_bounds__(256)
     fm_predict64_kernel(Params64 p, int n_factor, int use_w0, int use_w, HParams hp, int transform,
                         uint64_t n_rows, const uint64_t* __restrict__ row_ptr,
@@ -193,7 +199,7 @@ __global__ void __launch_bounds__(256)
   m.w = p.w();
   m.v = p.v();
   const double w0 = *p.w0();
-  double sum[KF_MAX];
+  double sum[KF];
   double sq = 0, ab = 0, ok = 0;
   // contiguous row ranges per warp keep the reduction order a pure function of
   // (n_rows, grid, block)
@@ -203,7 +209,7 @@ __global__ void __launch_bounds__(256)
   uint64_t rbeg = gw * per, rend = min(n_rows, rbeg + per);
   for (uint64_t r = rbeg; r < rend; r++) {
     uint64_t beg = row_ptr[r], end = row_ptr[r + 1];
-    double pr = predict_row_exact(m, w0, col + beg, val + beg, (uint32_t)(end - beg), sum, lane);
+    double pr = predict_row_exact<KF>(m, w0, col + beg, val + beg, (uint32_t)(end - beg), sum, lane);
     double y = (double)target[r];
     if (hp.task == FMB200_TASK_REGRESSION) {
       // fm_learn.h:138-142
@@ -244,8 +250,15 @@ __global__ void __launch_bounds__(256)
 
 cudaError_t launch_sgd_inorder(fmb200_ctx* c, const DataSlot& d) {
   if (c->k > 32 * KF_MAX) return cudaErrorInvalidValue;
-  fm_sgd_inorder_kernel<<<1, 32, 0, c->stream>>>(c->p64, c->k, c->k0, c->k1, c->hp, d.n_rows,
-                                                 d.row_ptr, d.col, d.val, d.target);
+  const int kf = (c->k + 31) / 32;
+#define FMB_INORDER(KF)                                                                         \
+  fm_sgd_inorder_kernel<KF><<<1, 32, 0, c->stream>>>(c->p64, c->k, c->k0, c->k1, c->hp, d.n_rows, \
+                                                     d.row_ptr, d.col, d.val, d.target)
+  if (kf <= 1) FMB_INORDER(1);
+  else if (kf <= 2) FMB_INORDER(2);
+  else if (kf <= 4) FMB_INORDER(4);
+  else FMB_INORDER(8);
+#undef FMB_INORDER
   c->launches++;
   c->last_cfg = EpochConfig{32, 1, 1, 1, 32, 0};
   return cudaGetLastError();
@@ -254,9 +267,16 @@ cudaError_t launch_sgd_inorder(fmb200_ctx* c, const DataSlot& d) {
 cudaError_t launch_predict64(fmb200_ctx* c, const DataSlot& d, int transform, double* out_pred,
                              double* partials, int n_blocks) {
   if (c->k > 32 * KF_MAX) return cudaErrorInvalidValue;
-  fm_predict64_kernel<<<n_blocks, 256, 0, c->stream>>>(c->p64, c->k, c->k0, c->k1, c->hp, transform,
-                                                       d.n_rows, d.row_ptr, d.col, d.val, d.target,
-                                                       out_pred, partials);
+  const int kf = (c->k + 31) / 32;
+#define FMB_PREDICT64(KF)                                                                          \
+  fm_predict64_kernel<KF><<<n_blocks, 256, 0, c->stream>>>(c->p64, c->k, c->k0, c->k1, c->hp,      \
+                                                           transform, d.n_rows, d.row_ptr, d.col, \
+                                                           d.val, d.target, out_pred, partials)
+  if (kf <= 1) FMB_PREDICT64(1);
+  else if (kf <= 2) FMB_PREDICT64(2);
+  else if (kf <= 4) FMB_PREDICT64(4);
+  else FMB_PREDICT64(8);
+#undef FMB_PREDICT64
   c->launches++;
   return cudaGetLastError();
 }
