@@ -368,3 +368,33 @@ def test_c3_full_size_properties(built_lib):
     assert np.isfinite(l.fm.v).all() and np.isfinite(l.fm.w).all() and np.isfinite(l.fm.w0)
     assert min(secs) < 0.2  # 10M rows: tens of milliseconds, not seconds
     l.close()
+
+
+@pytest.mark.parametrize("k,maxnnz", [(8, 2), (16, 3), (0, 3), (64, 12)])
+def test_launch_geometry_matrix(k, maxnnz, built_lib):
+    """Every tuning knob (CTAs/SM, rows per tile, threads, kernel variant) must leave the
+    result unchanged on rows that share no feature: oracle equality for all of them."""
+    n_rows = 1500
+    r = np.random.default_rng(k + maxnnz)
+    lens = r.integers(0, maxnnz + 1, n_rows)
+    rp = np.zeros(n_rows + 1, dtype=np.uint64)
+    rp[1:] = np.cumsum(lens)
+    n = int(rp[-1]) + 3
+    d = Data(rp, r.permutation(n)[: int(rp[-1])].astype(np.uint32),
+             r.standard_normal(int(rp[-1])).astype(np.float32),
+             r.integers(1, 6, n_rows).astype(np.float32), n)
+    cfg = _cfg(n, k, k0=0, lr=0.05, regs=(0, 0.01, 0.02))
+    init = _rand_init(n, k, 5, stdev=0.3)
+    p = _port(cfg, tuple(np.float32(x).astype(np.float64) for x in init))
+    p.sgd_epoch(d, 0, 0.05, 1.0, 5.0)
+    for ctas, rows, threads, variant in [(0, 0, 0, 0), (1, 32, 32, 0), (2, 64, 64, 1), (0, 128, 128, 2),
+                                         (1, 0, 256, 3), (0, 512, 256, 1), (3, 32, 96, 0)]:
+        l = make_learner(cfg, init, mode=MODE_HOGWILD)
+        l.set_tuning(ctas_per_sm=ctas, rows_per_tile=rows, threads=threads, variant=variant)
+        l.sgd_epoch(d)
+        l.sgd_epoch(Data(np.zeros(1, dtype=np.uint64), np.zeros(0, np.uint32), np.zeros(0, np.float32),
+                         np.zeros(0, np.float32), n))  # an empty data set between real ones
+        l.pull_params()
+        np.testing.assert_allclose(l.fm.w, p.w, atol=2e-6, err_msg=str((ctas, rows, threads, variant)))
+        np.testing.assert_allclose(l.fm.v, p.v, atol=2e-6, err_msg=str((ctas, rows, threads, variant)))
+        l.close()
