@@ -395,6 +395,7 @@ def test_launch_geometry_matrix(k, maxnnz, built_lib):
         l.sgd_epoch(Data(np.zeros(1, dtype=np.uint64), np.zeros(0, np.uint32), np.zeros(0, np.float32),
                          np.zeros(0, np.float32), n))  # an empty data set between real ones
         l.pull_params()
-        np.testing.assert_allclose(l.fm.w, p.w, atol=2e-6, err_msg=str((ctas, rows, threads, variant)))
-        np.testing.assert_allclose(l.fm.v, p.v, atol=2e-6, err_msg=str((ctas, rows, threads, variant)))
+        tol = 2e-6 * max(1, k // 8)  # fp32 sums over k*nnz terms vs the fp64 oracle
+        np.testing.assert_allclose(l.fm.w, p.w, atol=tol, err_msg=str((ctas, rows, threads, variant)))
+        np.testing.assert_allclose(l.fm.v, p.v, atol=tol, err_msg=str((ctas, rows, threads, variant)))
         l.close()
