@@ -376,6 +376,7 @@ static HogwildArgs make_args(fmb200_ctx* c, const DataSlot& d, uint64_t n_tiles,
   a.feat_cnt = d.feat_cnt;
   a.conc_scale = 1.f;
   a.w0_conc = 1.f;
+  a.hot_thr = 3.0e38f;
   a.sched = c->d_sched;
   return a;
 }
@@ -406,7 +407,8 @@ static cudaError_t launch_rowlane(fmb200_ctx* c, const DataSlot& d, bool* handle
                           : pick_rowlane_kernel(gp, (int)d.max_row_nnz, damp, combine);
   if (fn == nullptr) return cudaSuccess;
   const int hdr = ws ? 512 : HW_HDR_BYTES;
-  const int smem_ws = hdr + HW_NSTAGE * (int)sbytes;
+  // COMBINE (non-WS): two 128-slot hot-feature tables of 64-byte entries behind the ring
+  const int smem_ws = hdr + HW_NSTAGE * (int)sbytes + ((combine && !ws) ? 2 * 128 * 64 : 0);
   const int launch_threads = ws ? threads + 32 : threads;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ws);
   if (e != cudaSuccess) return e;
@@ -421,6 +423,8 @@ static cudaError_t launch_rowlane(fmb200_ctx* c, const DataSlot& d, bool* handle
   a.conc_scale = (float)(std::min<double>((double)d.n_rows, (double)grid * TR) / (double)d.n_rows);
   // the warp-specialised kernel reads the bias when a stage is filled: HW_NSTAGE tiles ahead
   a.w0_conc = (float)std::min<double>((double)d.n_rows, (double)grid * TR * (ws ? HW_NSTAGE : 1));
+  // park a feature in the CTA's hot table when it is expected at least twice per tile
+  a.hot_thr = (float)std::max(4.0, 2.0 * (double)d.n_rows / (double)TR);
   fn<<<grid, launch_threads, smem_ws, c->stream>>>(a);
   c->launches++;
   c->last_cfg = EpochConfig{1, (int)std::max<uint32_t>(1, d.max_row_nnz), TR, grid, launch_threads, smem_ws, damp ? 1 : 0};

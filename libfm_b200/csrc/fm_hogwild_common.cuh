@@ -32,6 +32,7 @@ struct HogwildArgs {
   const float* feat_cnt;  // occurrences of each feature in this data set (DAMP)
   float conc_scale;       // rows processed concurrently / n_rows: count -> concurrency
   float w0_conc;          // rows in flight w.r.t. the bias (tile granularity)
+  float hot_thr;          // COMBINE: occurrence count from which a feature is parked in the CTA's hot table
   unsigned int* sched;    // [0] next unclaimed tile, [1] CTAs that ran dry (both 0 between launches)
 };
 

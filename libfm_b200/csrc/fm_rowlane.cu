@@ -32,6 +32,48 @@ struct FactorRow {
   float v[4 * GP];
 };
 
+// CTA-level write combining for the hottest features of skewed data (COMBINE kernels).
+// Same-address L2 reductions serialise: a feature that appears in 11% of the rows costs
+// the whole chip ~4 ns per reduction.  After the in-warp merge, steps for features with
+// at least `hot_thr` occurrences are parked in a small direct-mapped shared-memory table
+// (tag = feature id) and leave the CTA as ONE reduction per feature and tile.  A slot that
+// is taken by another feature simply sends the step to L2 as before.
+constexpr int HOT_SLOTS = 128;
+struct HotEntry {
+  uint32_t tag;   // feature id, HOT_EMPTY when free
+  float dw;
+  float dv[8];
+  uint32_t pad[6];  // 64 bytes: one entry per pair of banks rows, no false sharing of tags
+};
+constexpr uint32_t HOT_EMPTY = 0xffffffffu;
+
+// returns true when the step was parked in the table
+template <int K>
+__device__ __forceinline__ bool hot_park(HotEntry* tab, uint32_t id, const float (&d)[K], float dw) {
+  HotEntry* e = tab + (id & (HOT_SLOTS - 1));
+  const uint32_t prev = atomicCAS(&e->tag, HOT_EMPTY, id);
+  if (prev != HOT_EMPTY && prev != id) return false;
+#pragma unroll
+  for (int f = 0; f < K; ++f) atomicAdd(&e->dv[f], d[f]);
+  atomicAdd(&e->dw, dw);
+  return true;
+}
+
+// flush one table: thread t handles slot t (call with t < HOT_SLOTS after a barrier)
+template <int GP>
+__device__ __forceinline__ void hot_flush(const HogwildArgs& a, HotEntry* tab, int t) {
+  HotEntry* e = tab + t;
+  const uint32_t id = e->tag;
+  if (id == HOT_EMPTY) return;
+  red_add_f4(a.v + (size_t)id * GP * 4, e->dv[0], e->dv[1], e->dv[2], e->dv[3]);
+  if (GP == 2) red_add_f4(a.v + (size_t)id * GP * 4 + 4, e->dv[4], e->dv[5], e->dv[6], e->dv[7]);
+  if (a.use_w) red_add_f(a.w + (size_t)id * a.ws, e->dw);
+  e->tag = HOT_EMPTY;
+  e->dw = 0.f;
+#pragma unroll
+  for (int f = 0; f < 8; ++f) e->dv[f] = 0.f;
+}
+
 // One tile, one lane per row: gather, score, multiplier, write-back.  `get_w0` is called
 // once the gathers are in flight and returns the tile's bias.  Returns this lane's loss
 // multiplier and joint curvature (zero for lanes without a row) for the bias step.
@@ -39,7 +81,8 @@ template <int GP, int Z, bool DAMP, bool COMBINE, typename W0F>
 __device__ __forceinline__ void rowlane_tile(const HogwildArgs& a, const uint64_t* rp,
                                              const float* ys, const uint32_t* ids,
                                              const float* xs, int rows_here, int tid, W0F get_w0,
-                                             float& mult_out, float& hjoint_out) {
+                                             float& mult_out, float& hjoint_out,
+                                             HotEntry* hot_tab = nullptr) {
   constexpr int K = 4 * GP;
   const int lane = tid & 31;
   const int odd = lane & 1;
@@ -184,6 +227,10 @@ __device__ __forceinline__ void rowlane_tile(const HogwildArgs& a, const uint64_
         }
         on_c = on && (lane == first);
       }
+      // hot features leave the CTA once per tile
+      if (hot_tab != nullptr && on_c && __ldg(a.feat_cnt + id[e]) >= a.hot_thr) {
+        if (hot_park<K>(hot_tab, id[e], d, dw)) on_c = false;
+      }
     }
     if (GP == 2) {
       // swap halves inside the lane pair so that each reduction covers a full sector
@@ -240,6 +287,16 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
     fence_mbar_init();
   }
   if (tid == (int)blockDim.x - 32) policy = policy_evict_first();
+  // COMBINE: two hot-feature tables (ping-pong by tile parity) behind the staging ring
+  HotEntry* hot = reinterpret_cast<HotEntry*>(smem + HW_HDR_BYTES + (size_t)HW_NSTAGE * a.stage_bytes);
+  if (COMBINE) {
+    for (int i = tid; i < 2 * HOT_SLOTS; i += blockDim.x) {
+      hot[i].tag = HOT_EMPTY;
+      hot[i].dw = 0.f;
+#pragma unroll
+      for (int f = 0; f < 8; ++f) hot[i].dv[f] = 0.f;
+    }
+  }
   __syncthreads();
   uint32_t* s_tile = reinterpret_cast<uint32_t*>(smem + 208);  // [HW_NSTAGE] tile staged per stage
   TileSched sched{a.sched, a.n_tiles, false};
@@ -300,7 +357,8 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
     float mult, hj, w0 = 0.f;
     rowlane_tile<GP, Z, DAMP, COMBINE>(
         a, rp, ys, ids, xs, rows_here, tid,
-        [&]() { return w0 = bias.get(use_w0, tid, it, (int)blockDim.x); }, mult, hj);
+        [&]() { return w0 = bias.get(use_w0, tid, it, (int)blockDim.x); }, mult, hj,
+        COMBINE ? hot + (it & 1) * HOT_SLOTS : nullptr);
     // ---- bias: one damped reduction into the global w0 per tile ----
     float2* s_part = reinterpret_cast<float2*>(s_acc) + (it & 1) * 8;  // [2 slots][8 warps]
     if (use_w0) {
@@ -309,6 +367,11 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const
       if (lane == 0) s_part[tid >> 5] = make_float2(msum, hsum);
     }
     __syncthreads();
+    // this tile's hot table is complete: one reduction per parked feature, while the next
+    // tile already accumulates into the other table
+    if (COMBINE) {
+      for (int i = tid; i < HOT_SLOTS; i += blockDim.x) hot_flush<GP>(a, hot + (it & 1) * HOT_SLOTS, i);
+    }
     if (tid == ptid) {
       s_tile[stage] = nt;
       if (nt != HW_NO_TILE) issue_tile(a, smem, bars, nt, stage, policy, nt_nb, nt_ne);
