@@ -96,7 +96,7 @@ def build_cli(force: bool = False) -> str | None:
     out = cli_path()
     if force or _newer(out, deps):
         cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), *srcs,
-               "-o", out, "-L", LIBDIR, "-lfmb200", "-Wl,-rpath,$ORIGIN/../libfm_b200/lib"]
+               "-o", out, "-pthread", "-L", LIBDIR, "-lfmb200", "-Wl,-rpath,$ORIGIN/../libfm_b200/lib"]
         nccl = os.environ.get("FMB200_NCCL", "1") == "1" and os.path.exists("/usr/include/nccl.h")
         cuda_inc = "/usr/local/cuda/include"
         if nccl:

@@ -8,7 +8,8 @@
 //     reference's `convert` tool writes (src/libfm/tools/convert.cpp:143-198,
 //     util/fmatrix.h:44-50, util/matrix.h:364-380)
 // Ordering (rows in file order, entries in line order) and the derived numbers
-// (num_feature = max id + 1, min/max target) are bit-exact contracts.
+// (num_feature = max id + 1, min/max target) are bit-exact contracts.  Text files are
+// parsed by all host cores (the reference: two sscanf passes on one core).
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -17,7 +18,9 @@
 #include <fstream>
 #include <iostream>
 #include <limits>
+#include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace host {
@@ -62,43 +65,132 @@ struct SparseData {
     return "cannot parse line \"" + line + "\" at character " + at;
   }
 
+  // One contiguous piece of the file, parsed by one thread.
+  struct TextChunk {
+    std::vector<uint64_t> row_end;  // entries so far after each row (chunk-local)
+    std::vector<uint32_t> col;
+    std::vector<float> val, target;
+    int max_id = 0;
+    bool has_feature = false;
+    float min_target = +std::numeric_limits<float>::max();
+    float max_target = -std::numeric_limits<float>::max();
+    std::string error;  // first parse error of the chunk, in file order
+  };
+
+  // Parse the lines in [begin, end) (each made NUL-terminated in place).  Same grammar
+  // as Data::load (Data.h:192-225): "%f" then repeated "%d:%f", '#' comments.
+  static void parse_chunk(char* begin, char* end, TextChunk& out) {
+    char* line = begin;
+    while (line < end) {
+      char* nl = static_cast<char*>(memchr(line, '\n', (size_t)(end - line)));
+      char* line_end = nl ? nl : end;
+      *line_end = 0;
+      const char* p = line;
+      while (*p == ' ' || *p == '\t') p++;
+      if (*p != 0 && *p != '#') {  // Data.h:200-201: blank and comment lines are skipped
+        char* e0 = nullptr;
+        const float y = strtof(p, &e0);  // "%f"
+        if (e0 == p) {
+          out.error = parse_error(line, p[0]);
+          return;
+        }
+        p = e0;
+        out.target.push_back(y);
+        if (y < out.min_target) out.min_target = y;
+        if (y > out.max_target) out.max_target = y;
+        for (;;) {
+          // "%d:%f" -- %d skips white space, ':' must follow the digits directly,
+          // %f skips white space again
+          const char* q = p;
+          while (*q == ' ' || *q == '\t') q++;
+          char* e1 = nullptr;
+          const long id = strtol(q, &e1, 10);
+          if (e1 == q || *e1 != ':') break;
+          char* e2 = nullptr;
+          const float x = strtof(e1 + 1, &e2);
+          if (e2 == e1 + 1) break;
+          out.col.push_back((uint32_t)(int)id);
+          out.val.push_back(x);
+          if ((int)id > out.max_id) out.max_id = (int)id;
+          out.has_feature = true;
+          p = e2;
+        }
+        while (*p == ' ' || *p == '\t') p++;
+        if (*p != 0 && *p != '#') {  // Data.h:218-220
+          out.error = parse_error(line, p[0]);
+          return;
+        }
+        out.row_end.push_back(out.col.size());
+      }
+      line = line_end + 1;
+    }
+  }
+
+  // The reference parses the file twice with sscanf on one core (Data.h:180-290) and
+  // that dominates its wall time on large inputs.  Here the
+  // file is read once, cut at line boundaries and parsed by all host cores; the chunks
+  // are concatenated in file order, so the CSR is identical to the sequential result.
   void load_text(const std::string& filename) {
-    std::ifstream in(filename.c_str());
-    if (!in.is_open()) throw "unable to open " + filename;
+    std::string buf;
+    {
+      std::ifstream in(filename.c_str(), std::ios::binary);
+      if (!in.is_open()) throw "unable to open " + filename;
+      in.seekg(0, std::ios::end);
+      const std::streamoff len = in.tellg();
+      in.seekg(0, std::ios::beg);
+      buf.resize((size_t)(len > 0 ? len : 0) + 1);
+      if (len > 0) in.read(&buf[0], len);
+      buf[buf.size() - 1] = 0;
+    }
+    char* base = &buf[0];
+    char* stop = base + buf.size() - 1;
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t n_chunks = hw ? hw : 4;
+    if (n_chunks > 32) n_chunks = 32;
+    if ((size_t)(stop - base) < (1u << 20)) n_chunks = 1;  // small files: not worth a thread
+    std::vector<char*> cut(n_chunks + 1);
+    cut[0] = base;
+    cut[n_chunks] = stop;
+    for (size_t i = 1; i < n_chunks; i++) {
+      char* guess = base + (size_t)(stop - base) * i / n_chunks;
+      if (guess < cut[i - 1]) guess = cut[i - 1];
+      char* nl = static_cast<char*>(memchr(guess, '\n', (size_t)(stop - guess)));
+      cut[i] = nl ? nl + 1 : stop;
+    }
+    std::vector<TextChunk> chunks(n_chunks);
+    std::vector<std::thread> workers;
+    for (size_t i = 1; i < n_chunks; i++)
+      workers.emplace_back(parse_chunk, cut[i], cut[i + 1], std::ref(chunks[i]));
+    parse_chunk(cut[0], cut[1], chunks[0]);
+    for (auto& w : workers) w.join();
+
+    uint64_t rows = 0, entries = 0;
+    for (const auto& c : chunks) {
+      if (!c.error.empty()) throw c.error;  // the first error in file order
+      rows += c.target.size();
+      entries += c.col.size();
+    }
+    row_ptr.assign(1, 0);
+    row_ptr.reserve(rows + 1);
+    col.resize(entries);
+    val.resize(entries);
+    target.resize(rows);
     bool has_feature = false;
     int max_id = 0;
-    std::string line;
-    while (std::getline(in, line)) {
-      const char* p = line.c_str();
-      while (*p == ' ' || *p == '\t') p++;
-      if (*p == 0 || *p == '#') continue;  // Data.h:200-201
-      char* end = nullptr;
-      float y = strtof(p, &end);  // "%f"
-      if (end == p) throw parse_error(line, p[0]);
-      p = end;
-      target.push_back(y);
-      if (y < min_target) min_target = y;
-      if (y > max_target) max_target = y;
-      for (;;) {
-        // "%d:%f" -- %d skips white space, ':' must follow the digits directly,
-        // %f skips white space again
-        const char* q = p;
-        while (*q == ' ' || *q == '\t') q++;
-        char* e1 = nullptr;
-        long id = strtol(q, &e1, 10);
-        if (e1 == q || *e1 != ':') break;
-        char* e2 = nullptr;
-        float x = strtof(e1 + 1, &e2);
-        if (e2 == e1 + 1) break;
-        col.push_back((uint32_t)(int)id);
-        val.push_back(x);
-        if ((int)id > max_id) max_id = (int)id;
-        has_feature = true;
-        p = e2;
+    uint64_t r0 = 0, e0 = 0;
+    for (const auto& c : chunks) {
+      for (uint64_t re : c.row_end) row_ptr.push_back(e0 + re);
+      if (!c.col.empty()) {
+        memcpy(&col[e0], c.col.data(), c.col.size() * sizeof(uint32_t));
+        memcpy(&val[e0], c.val.data(), c.val.size() * sizeof(float));
       }
-      while (*p == ' ' || *p == '\t') p++;
-      if (*p != 0 && *p != '#') throw parse_error(line, p[0]);  // Data.h:218-220
-      row_ptr.push_back(col.size());
+      if (!c.target.empty()) memcpy(&target[r0], c.target.data(), c.target.size() * sizeof(float));
+      r0 += c.target.size();
+      e0 += c.col.size();
+      has_feature |= c.has_feature;
+      if (c.max_id > max_id) max_id = c.max_id;
+      if (c.min_target < min_target) min_target = c.min_target;
+      if (c.max_target > max_target) max_target = c.max_target;
     }
     num_feature = has_feature ? max_id + 1 : 0;  // Data.h:227-229
     std::cout << "num_rows=" << num_cases() << "\tnum_values=" << num_values()

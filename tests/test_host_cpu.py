@@ -182,3 +182,61 @@ def test_bench_reference_arm_line(tmp_path):
     assert line["cpu_baseline"]["cores"] == 1 and line["cpu_baseline"]["kind"] in ("reference", "port")
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert 1e6 < line["value"] < 1e9  # a single CPU core: tens of millions of examples/s
+
+
+@pytest.fixture(scope="module")
+def loader_dump(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("bin") / "loader_dump")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "libfm_b200", "host"),
+                    os.path.join(ROOT, "tests", "loader_dump.cpp"), "-o", exe], check=True)
+    return exe
+
+
+def _read_dump(path):
+    raw = open(path, "rb").read()
+    n, nnz, nf = np.frombuffer(raw, np.uint64, 2, 0).tolist() + [int(np.frombuffer(raw, np.int64, 1, 16)[0])]
+    mn, mx = np.frombuffer(raw, np.float32, 2, 24)
+    o = 32
+    rp = np.frombuffer(raw, np.uint64, n + 1, o); o += 8 * (n + 1)
+    col = np.frombuffer(raw, np.uint32, nnz, o); o += 4 * nnz
+    val = np.frombuffer(raw, np.float32, nnz, o); o += 4 * nnz
+    tgt = np.frombuffer(raw, np.float32, n, o)
+    return rp, col, val, tgt, nf, float(mn), float(mx)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_cli_loader_threaded_text_equals_reference(loader_dump, tmp_path):
+    """A > 1 MB text file takes the multi-threaded path of host/sparse_data.h (cut at
+    line boundaries, parsed by all cores, concatenated in file order): the CSR must be
+    bit-identical to what the reference's two-pass sscanf loader builds."""
+    r = np.random.default_rng(5)
+    path = str(tmp_path / "big.libfm")
+    with open(path, "w") as f:
+        f.write("# header comment\n\n")
+        for i in range(60_000):
+            z = int(r.integers(0, 7))
+            ids = r.integers(0, 5000, z)
+            vals = r.standard_normal(z)
+            lead = "  " if i % 97 == 0 else ""
+            tail = "   # c" if i % 53 == 0 else ("\t" if i % 31 == 0 else "")
+            f.write(lead + "%g" % r.integers(-3, 6) + "".join(" %d:%.6g" % (a, b) for a, b in zip(ids, vals)) + tail + "\n")
+            if i % 1000 == 0:
+                f.write("\n# interleaved comment\n")
+        f.write("4 7:1")  # last line without a newline
+    assert os.path.getsize(path) > (1 << 20)
+    out = str(tmp_path / "dump.bin")
+    subprocess.run([loader_dump, path, out], check=True)
+    got = _read_dump(out)
+    want = Ref.load_data(path)
+    for a, b in zip(got[:4], want[:4]):
+        assert np.array_equal(a, b)
+    assert got[4:] == (want[4], want[5], want[6])
+
+
+def test_cli_loader_reports_first_error_in_file_order(loader_dump, tmp_path):
+    path = str(tmp_path / "bad.libfm")
+    with open(path, "w") as f:
+        for i in range(120_000):
+            f.write("1 3:1 4:2\n" if i not in (70_000, 110_000) else "1 3:1 oops%d\n" % i)
+    r = subprocess.run([loader_dump, path, str(tmp_path / "x.bin")], capture_output=True, text=True)
+    assert r.returncode == 1 and 'cannot parse line "1 3:1 oops70000" at character o' in r.stderr
