@@ -228,3 +228,39 @@ def test_async_upload_ping_pong(built_lib):
     assert l.lib.fmb200_sgd_epoch(l._ctx, 4, None) != 0  # ... the verdict arrives at first use
     assert b"out of range" in l.lib.fmb200_last_error()
     l.close()
+
+
+def test_error_paths_report_and_do_not_crash(built_lib):
+    """Every misuse returns non-zero with a message (nothing throws across the C ABI,
+    nothing falls back to a CPU path)."""
+    import ctypes as C
+    lib = built_lib
+    err = lambda: lib.fmb200_last_error().decode()  # noqa: E731
+    ctx = C.c_void_p()
+    assert lib.fmb200_create(C.byref(ctx), 99, 10, 4, 1, 1) != 0 and "out of range" in err()
+    assert lib.fmb200_create(C.byref(ctx), 0, 10, -1, 1, 1) != 0 and "num_factor" in err()
+    assert lib.fmb200_create(C.byref(ctx), 0, 50, 130, 1, 1) == 0  # k = 130: INORDER only
+    assert lib.fmb200_set_mode(ctx, 7) != 0 and "unknown mode" in err()
+    assert lib.fmb200_set_hparams(ctx, 5, 0.1, 0, 0, 0, 0, 1) != 0 and "unknown task" in err()
+    assert lib.fmb200_sgd_epoch(ctx, 0, None) != 0 and "holds no data" in err()
+    assert lib.fmb200_sgd_epoch(ctx, 99, None) != 0 and "out of range" in err()
+    d = synth.two_field(200, 20, 20, 1)
+    P = lambda a, t: a.ctypes.data_as(C.POINTER(t))  # noqa: E731
+    up = lambda rp: lib.fmb200_upload_data(ctx, 0, d.num_cases, d.num_values, P(rp, C.c_uint64),  # noqa: E731
+                                           P(d.col, C.c_uint32), P(d.val, C.c_float), P(d.target, C.c_float))
+    bad = d.row_ptr.copy()
+    bad[5], bad[6] = bad[6], bad[5] + 1
+    assert up(bad) != 0 and "monotone" in err()
+    bad = d.row_ptr.copy()
+    bad[0] = 1
+    assert up(bad) != 0 and "row_ptr[0]" in err()
+    assert up(d.row_ptr) == 0
+    assert lib.fmb200_set_mode(ctx, MODE_HOGWILD) == 0
+    assert lib.fmb200_sgd_epoch(ctx, 0, None) != 0 and "128" in err()  # k = 130 > 128 in HOGWILD mode
+    assert lib.fmb200_set_mode(ctx, MODE_INORDER) == 0
+    assert lib.fmb200_sgd_epoch(ctx, 0, None) == 0
+    assert lib.fmb200_params_device(ctx, None, None) != 0 and "HOGWILD" in err()
+    assert lib.fmb200_peer_attach_local(ctx, 2, 5, None) != 0
+    assert lib.fmb200_set_tuning(ctx, 0, 0, 100, 0, 0) != 0 and "multiple of 32" in err()
+    lib.fmb200_destroy(ctx)
+    assert lib.fmb200_set_mode(None, 0) != 0 and "null context" in err()
