@@ -86,22 +86,25 @@ def build_lib(force: bool = False) -> str:
 
 
 def build_cli(force: bool = False) -> str | None:
-    """The drop-in command line: plain C++ host code over the C ABI."""
+    """The drop-in command lines: plain C++ host code (bin/libFM over the C ABI, bin/convert)."""
     main = os.path.join(HOST, "libfm_main.cpp")
     if not os.path.exists(main):
         return None
     os.makedirs(BINDIR, exist_ok=True)
-    srcs = [os.path.join(HOST, f) for f in sorted(os.listdir(HOST)) if f.endswith(".cpp")]
-    deps = srcs + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".h")] + [lib_path()]
+    hdrs = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".h")]
     out = cli_path()
-    if force or _newer(out, deps):
-        cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), *srcs,
+    if force or _newer(out, [main] + hdrs + [lib_path()]):
+        cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), main,
                "-o", out, "-pthread", "-L", LIBDIR, "-lfmb200", "-Wl,-rpath,$ORIGIN/../libfm_b200/lib"]
         nccl = os.environ.get("FMB200_NCCL", "1") == "1" and os.path.exists("/usr/include/nccl.h")
         cuda_inc = "/usr/local/cuda/include"
         if nccl:
             cmd += ["-DFMB200_WITH_NCCL", "-I", cuda_inc, "-lnccl", "-L/usr/local/cuda/lib64", "-lcudart"]
         _run(cmd)
+    conv_src = os.path.join(HOST, "convert_main.cpp")
+    conv = os.path.join(BINDIR, "convert")
+    if os.path.exists(conv_src) and (force or _newer(conv, [conv_src] + hdrs)):
+        _run(["g++", "-O2", "-std=c++17", "-Wall", conv_src, "-o", conv, "-pthread"])
     return out
 
 

@@ -55,6 +55,9 @@ struct SparseData {
     }
   }
 
+  // text input only (the `convert` tool never looks for binary siblings of its input)
+  void load_text_file(const std::string& filename) { load_text(filename); }
+
   // libfm.cpp:302-303
   void binarize_targets() {
     for (auto& t : target) t = (t <= 0.0f) ? -1.0f : 1.0f;

@@ -240,3 +240,22 @@ def test_cli_loader_reports_first_error_in_file_order(loader_dump, tmp_path):
             f.write("1 3:1 4:2\n" if i not in (70_000, 110_000) else "1 3:1 oops%d\n" % i)
     r = subprocess.run([loader_dump, path, str(tmp_path / "x.bin")], capture_output=True, text=True)
     assert r.returncode == 1 and 'cannot parse line "1 3:1 oops70000" at character o' in r.stderr
+
+
+def test_convert_tool_output_is_byte_identical_to_reference(tricky_file, tmp_path):
+    """bin/convert (host/convert_main.cpp) vs the reference's convert tool: same flags,
+    byte-identical .x / .y files -- also on a file large enough for the threaded parser."""
+    from oracle.binding import REF_CONVERT
+    ours = os.path.join(ROOT, "bin", "convert")
+    if not (os.path.exists(ours) and os.path.exists(REF_CONVERT)):
+        pytest.skip("convert binaries not built")
+    big = str(tmp_path / "big.libfm")
+    synth.to_libfm_text(synth.ragged(80_000, 3000, 6, seed=4), big)
+    assert os.path.getsize(big) > (1 << 20)
+    for src in (tricky_file, big):
+        for tool, tag in ((ours, "a"), (REF_CONVERT, "b")):
+            r = subprocess.run([tool, "--ifile", src, "--ofilex", str(tmp_path / (tag + ".x")),
+                                "--ofiley", str(tmp_path / (tag + ".y"))], capture_output=True, text=True)
+            assert os.path.exists(tmp_path / (tag + ".x")), r.stderr
+        assert open(tmp_path / "a.x", "rb").read() == open(tmp_path / "b.x", "rb").read()
+        assert open(tmp_path / "a.y", "rb").read() == open(tmp_path / "b.y", "rb").read()
