@@ -12,6 +12,8 @@
 //   -device D               first CUDA ordinal
 #include <algorithm>
 #include <cassert>
+#include <chrono>
+#include <cstdlib>
 #include <ctime>
 #include <iostream>
 #include <string>
@@ -23,6 +25,10 @@
 using namespace host;
 
 int main(int argc, char** argv) {
+  const auto t_start = std::chrono::steady_clock::now();
+  auto since = [&](std::chrono::steady_clock::time_point t) {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count();
+  };
   try {
     CmdLine cmd(argc, argv);
     const char* bar = "----------------------------------------------------------------------------";
@@ -146,7 +152,15 @@ int main(int argc, char** argv) {
       rlog = new RLog(rlog_file);
     }
     fml.log = rlog;
+    // A single-GPU run on a multi-GPU host: expose only that device to the CUDA driver
+    // (initialising eight 180 GB devices costs seconds a short job never earns back).
+    if (fml.num_gpus == 1 && getenv("CUDA_VISIBLE_DEVICES") == nullptr) {
+      setenv("CUDA_VISIBLE_DEVICES", std::to_string(fml.first_device).c_str(), 1);
+      fml.first_device = 0;
+    }
+    const double t_loaded = since(t_start);
     fml.init();
+    const double t_init = since(t_start);
 
     // regularisation, libfm.cpp:366-384
     {
@@ -181,8 +195,12 @@ int main(int argc, char** argv) {
 
     // learn, libfm.cpp:414-420
     fml.attach(train, test);
+    const double t_attached = since(t_start);
     fml.push_state();
     fml.learn();
+    if (cmd.integer(p_verb, 0) > 0)
+      std::cout << "time: load " << t_loaded << " s, gpu init " << (t_init - t_loaded) << " s, upload "
+                << (t_attached - t_init) << " s, learn+evaluate " << (since(t_start) - t_attached) << " s" << std::endl;
     std::cout << "Final\t" << "Train=" << fml.evaluate(0) << "\tTest=" << fml.evaluate(1) << std::endl;
 
     // -out, libfm.cpp:422-428 (DVector::save: one value per line, matrix.h:332-342)

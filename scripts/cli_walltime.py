@@ -9,12 +9,12 @@ synth.to_libfm_text(d.rows(0, 900000), "/tmp/tr.libfm")
 synth.to_libfm_text(d.rows(900000, d.num_cases), "/tmp/te.libfm")
 base = ["-task", "r", "-train", "/tmp/tr.libfm", "-test", "/tmp/te.libfm", "-method", "sgd", "-dim", "1,1,8",
         "-learn_rate", "0.01", "-seed", "42"]
-for name, exe, extra in [("ours hogwild 20 iters", "bin/libFM", ["-iter", "20"]),
+for name, exe, extra in [("ours hogwild 20 iters", "bin/libFM", ["-iter", "20", "-verbosity", "1"]),
                          ("ours inorder  2 iters", "bin/libFM", ["-iter", "2", "-mode", "inorder"]),
                          ("reference    20 iters", "oracle/_ref/libFM", ["-iter", "20"]),
                          ("reference     2 iters", "oracle/_ref/libFM", ["-iter", "2"])]:
     t0 = time.time()
     r = subprocess.run([os.path.join(ROOT, exe)] + base + extra, capture_output=True, text=True)
     dt = time.time() - t0
-    fin = [l for l in (r.stdout + r.stderr).splitlines() if l.startswith("Final") or "ERROR" in l]
+    fin = [l for l in (r.stdout + r.stderr).splitlines() if l.startswith(("Final", "time:")) or "ERROR" in l]
     print("%s: rc=%d wall %.2f s :: %s" % (name, r.returncode, dt, " ".join(fin).replace("\t", " ")), flush=True)
