@@ -259,3 +259,46 @@ def test_convert_tool_output_is_byte_identical_to_reference(tricky_file, tmp_pat
             assert os.path.exists(tmp_path / (tag + ".x")), r.stderr
         assert open(tmp_path / "a.x", "rb").read() == open(tmp_path / "b.x", "rb").read()
         assert open(tmp_path / "a.y", "rb").read() == open(tmp_path / "b.y", "rb").read()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_cli_loader_fuzz_against_reference(loader_dump, tmp_path):
+    """Randomised libfm text (odd spacing, signs, exponents, comments, blank lines, empty
+    rows, garbage) through host/sparse_data.h and through the reference's Data::load:
+    identical CSR, or the same `cannot parse line` error."""
+    r = np.random.default_rng(2024)
+
+    def num(x):
+        return r.choice(["%g", "%.3f", "%e", "%+g"]) % x
+
+    def line():
+        kind = r.random()
+        if kind < 0.05:
+            return r.choice(["", "   ", "\t", "# only a comment", "  # indented comment"])
+        y = num(r.normal() * 3)
+        ents = " ".join("%s%d:%s" % ("" if r.random() < 0.8 else " ", int(r.integers(0, 300)), num(r.normal()))
+                        for _ in range(int(r.integers(0, 6))))
+        s = r.choice(["", " ", "\t"]) + y + (" " + ents if ents else "") + r.choice(["", " ", "  # tail", "\t\t"])
+        return s
+
+    bad_tails = ["1 3:1 x", "abc", "1 3 :1", "2 4:", "1 5:1 6", "3 7:1e", "1 2:3:4"]
+    for trial in range(40):
+        lines = [line() for _ in range(int(r.integers(1, 60)))]
+        if trial % 4 == 3:
+            lines.insert(int(r.integers(0, len(lines) + 1)), str(r.choice(bad_tails)))
+        path = str(tmp_path / ("f%d.libfm" % trial))
+        with open(path, "w") as f:
+            f.write("\n".join(lines) + ("\n" if r.random() < 0.7 else ""))
+        out = str(tmp_path / "d.bin")
+        ours = subprocess.run([loader_dump, path, out], capture_output=True, text=True)
+        try:
+            want = Ref.load_data(path)
+        except RuntimeError as e:
+            assert ours.returncode == 1, (trial, lines, str(e))
+            assert str(e).strip() in ours.stderr, (str(e), ours.stderr)
+            continue
+        assert ours.returncode == 0, (trial, ours.stderr, lines)
+        got = _read_dump(out)
+        for a, b in zip(got[:4], want[:4]):
+            assert np.array_equal(a, b), (trial, lines)
+        assert got[4:] == (want[4], want[5], want[6]), (trial, got[4:], want[4:])
