@@ -1,4 +1,4 @@
-// cmdline.h -- command-line flags with the semantics of the reference's CMDLine
+// cli_flags.h -- command-line flags with the semantics of the reference's CMDLine
 // (reference src/util/cmdline.h:67-237): every flag is `-name [value]` or
 // `--name [value]`, values never start with '-', lists split on ';' or ','.
 // Error texts match the reference so wrapper scripts keep working.

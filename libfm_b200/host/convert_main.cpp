@@ -11,7 +11,7 @@
 #include <iostream>
 #include <string>
 
-#include "cmdline.h"
+#include "cli_flags.h"
 #include "sparse_data.h"
 
 int main(int argc, char** argv) {

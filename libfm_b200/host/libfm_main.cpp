@@ -19,7 +19,7 @@
 #include <string>
 #include <vector>
 
-#include "cmdline.h"
+#include "cli_flags.h"
 #include "fm_host.h"
 
 using namespace host;
