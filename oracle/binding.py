@@ -12,6 +12,7 @@ PORT_SO = os.path.join(HERE, "libfm_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libfm_ref.so")
 REF_CLI = os.path.join(HERE, "_ref", "libFM")
 REF_CONVERT = os.path.join(HERE, "_ref", "convert")
+REF_CLI_B200 = os.path.join(HERE, "_ref", "libFM_b200")  # reference main() + integration/fm_learn_sgd_b200.h
 
 
 def build() -> None:

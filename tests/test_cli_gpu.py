@@ -10,7 +10,7 @@ import pytest
 
 from conftest import ROOT
 from libfm_b200 import synth
-from oracle.binding import REF_CLI, REF_CONVERT
+from oracle.binding import REF_CLI, REF_CLI_B200, REF_CONVERT
 
 pytestmark = pytest.mark.gpu
 CLI = os.path.join(ROOT, "bin", "libFM")
@@ -107,3 +107,42 @@ def test_cli_load_model_roundtrip(c1_files):
     r = _run(REF_CLI, [x for x in base if x not in ("-mode", "inorder")] + ["-iter", "0", "-load_model", "m2.txt"], c1_files)
     assert b.returncode == 0, b.stderr
     assert _iters(b.stdout) == _iters(r.stdout)
+
+
+@pytest.mark.parametrize("task,fmt", [("r", "text"), ("c", "text"), ("r", "binary")])
+def test_reference_main_with_b200_learner(c1_files, task, fmt):
+    """The maintainer's binding (integration/fm_learn_sgd_b200.h) compiled INTO the reference's own
+    main(): its loader, CMDLine, RLog and writers are untouched, only the passes over the data run
+    in libfmb200.  In-order mode must reproduce the stock binary's stdout and files."""
+    _need()
+    if not os.path.exists(REF_CLI_B200):
+        pytest.skip("oracle/_ref/libFM_b200 not built")
+    train, test = "train.libfm", "test.libfm"
+    if fmt == "binary":  # LargeSparseMatrixHD path -> row-cursor upload
+        if not os.path.exists(REF_CONVERT):
+            pytest.skip("convert not built")
+        for stem in ("train", "test"):
+            _run(REF_CONVERT, ["--ifile", stem + ".libfm", "--ofilex", stem + ".hd.x", "--ofiley", stem + ".hd.y"], c1_files)
+        train, test = "train.hd", "test.hd"
+    base = ["-task", task, "-train", train, "-test", test, "-method", "sgd", "-dim", "1,1,8",
+            "-iter", "3", "-learn_rate", "0.01", "-init_stdev", "0.1", "-seed", "42"]
+    ref = _run(REF_CLI, base + ["-out", "s_pred.txt", "-save_model", "s_model.txt"], c1_files)
+    env = dict(os.environ, FMB200_MODE="inorder")
+    ours = subprocess.run([REF_CLI_B200] + base + ["-out", "p_pred.txt", "-save_model", "p_model.txt", "-rlog", "p_log.tsv"],
+                          capture_output=True, text=True, cwd=c1_files, timeout=600, env=env)
+    assert ours.returncode == 0 and "ERROR" not in ours.stderr, ours.stderr
+    assert _iters(ours.stdout) == _iters(ref.stdout) and len(_iters(ref.stdout)) == 4
+    rd = lambda f: open(os.path.join(c1_files, f)).read()  # noqa: E731
+    if task == "r":
+        assert rd("p_pred.txt") == rd("s_pred.txt")
+        assert rd("p_model.txt") == rd("s_model.txt")
+    else:
+        np.testing.assert_allclose(np.loadtxt(os.path.join(c1_files, "p_pred.txt")),
+                                   np.loadtxt(os.path.join(c1_files, "s_pred.txt")), atol=2e-6)
+    assert len(rd("p_log.tsv").splitlines()) == 4
+    # hogwild (the default) through the same binding: tracks the reference
+    hw = subprocess.run([REF_CLI_B200] + base, capture_output=True, text=True, cwd=c1_files, timeout=600)
+    assert hw.returncode == 0 and "ERROR" not in hw.stderr, hw.stderr
+    val = lambda l: [float(t.split("=")[1]) for t in l.split("\t") if t.startswith(("Train", "Test"))]  # noqa: E731
+    a, b = val(_iters(hw.stdout)[-1]), val(_iters(ref.stdout)[-1])
+    assert abs(a[0] - b[0]) < 0.05 and abs(a[1] - b[1]) < 0.05, (a, b)

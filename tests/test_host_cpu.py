@@ -92,6 +92,22 @@ def test_cli_loader_lines_match_reference(tricky_file, tmp_path):
         assert ours.returncode != 0 and "no CPU path" in ours.stderr
 
 
+def test_reference_main_links_against_the_c_abi(tricky_file):
+    """integration/fm_learn_sgd_b200.h compiled into the reference's own main() (oracle/_ref/libFM_b200):
+    the C ABI binds to the reference's Data / DVector / sparse_row types, the binary resolves
+    libfmb200.so through its rpath, and without a GPU it refuses loudly instead of training on the CPU."""
+    from oracle.binding import REF_CLI_B200
+    if not os.path.exists(REF_CLI_B200):
+        pytest.skip("oracle/_ref/libFM_b200 not built (no /root/reference here)")
+    args = ["-task", "r", "-train", tricky_file, "-test", tricky_file, "-method", "sgd",
+            "-iter", "1", "-learn_rate", "0.01", "-seed", "1"]
+    r = subprocess.run([REF_CLI_B200] + args, capture_output=True, text=True)
+    assert "num_rows=" in r.stdout  # the reference's loader ran
+    import torch
+    if not torch.cuda.is_available():
+        assert "no CPU path" in r.stderr and "#Iter" not in r.stdout
+
+
 def test_cli_flag_errors_match_reference_text(tmp_path):
     cli = os.path.join(ROOT, "bin", "libFM")
     if not os.path.exists(cli):
