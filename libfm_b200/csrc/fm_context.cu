@@ -36,6 +36,19 @@ int fail(const char* fmt, ...) {
 #define NEED_CTX(c) \
   if ((c) == nullptr) return fail("null context")
 
+// No C++ exception may cross the C ABI: entry points that allocate host staging run
+// their body through this.
+template <class F>
+int guarded(F&& body) {
+  try {
+    return body();
+  } catch (const std::bad_alloc&) {
+    return fail("out of host memory");
+  } catch (...) {
+    return fail("unexpected C++ exception");
+  }
+}
+
 int bind(fmb200_ctx* c) {
   CK(cudaSetDevice(c->device));
   return 0;
@@ -163,28 +176,10 @@ int metric_blocks(fmb200_ctx* c, const DataSlot& s) {
 
 }  // namespace
 
-extern "C" {
-
-const char* fmb200_last_error(void) { return g_err; }
-
-int fmb200_create(fmb200_ctx** out, int device, uint32_t n_attr, int num_factor, int use_w0,
-                  int use_w) {
-  if (out == nullptr) return fail("null out pointer");
-  *out = nullptr;
-  if (num_factor < 0) return fail("num_factor must be >= 0");
-  int count = 0;
-  cudaError_t e = cudaGetDeviceCount(&count);
-  if (e != cudaSuccess || count == 0)
-    return fail("no CUDA device available (%s): libfmb200 has no CPU path",
-                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
-  if (device < 0 || device >= count) return fail("device %d out of range (count %d)", device, count);
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10)
-    return fail("device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major,
-                prop.minor);
-  fmb200_ctx* c = new (std::nothrow) fmb200_ctx();
-  if (!c) return fail("out of host memory");
+// Everything of fmb200_create that can fail after the context object exists; the caller
+// destroys the partially built context on a non-zero return.
+static int create_resources(fmb200_ctx* c, int device, const cudaDeviceProp& prop, uint32_t n_attr,
+                            int num_factor, int use_w0, int use_w) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
@@ -224,6 +219,35 @@ int fmb200_create(fmb200_ctx** out, int device, uint32_t n_attr, int num_factor,
     }
   }
   CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" {
+
+const char* fmb200_last_error(void) { return g_err; }
+
+int fmb200_create(fmb200_ctx** out, int device, uint32_t n_attr, int num_factor, int use_w0,
+                  int use_w) {
+  if (out == nullptr) return fail("null out pointer");
+  *out = nullptr;
+  if (num_factor < 0) return fail("num_factor must be >= 0");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail("no CUDA device available (%s): libfmb200 has no CPU path",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail("device %d out of range (count %d)", device, count);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail("device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major,
+                prop.minor);
+  fmb200_ctx* c = new (std::nothrow) fmb200_ctx();
+  if (!c) return fail("out of host memory");
+  if (create_resources(c, device, prop, n_attr, num_factor, use_w0, use_w)) {
+    fmb200_destroy(c);  // releases whatever was allocated; g_err keeps the cause
+    return 1;
+  }
   *out = c;
   return 0;
 }
@@ -311,32 +335,34 @@ int fmb200_upload_data_aos(fmb200_ctx* c, int slot, uint64_t n_rows, const void*
   if (slot < 0 || slot >= FMB200_MAX_SLOTS) return fail("slot %d out of range", slot);
   if (n_rows && (!rows || !target)) return fail("null data pointer");
   if (bind(c)) return 1;
-  // reference layout, util/fmatrix.h:34-42
-  struct Entry {
-    uint32_t id;
-    float value;
-  };
-  struct Row {
-    const Entry* data;
-    uint32_t size;
-  };
-  static_assert(sizeof(Row) == 16 && sizeof(Entry) == 8, "LP64 layout of sparse_row/sparse_entry");
-  const Row* r = static_cast<const Row*>(rows);
-  std::vector<uint64_t> rp(n_rows + 1);
-  rp[0] = 0;
-  for (uint64_t i = 0; i < n_rows; i++) rp[i + 1] = rp[i] + r[i].size;
-  const uint64_t nnz = rp[n_rows];
-  std::vector<uint32_t> col(nnz ? nnz : 1);
-  std::vector<float> val(nnz ? nnz : 1);
-  for (uint64_t i = 0; i < n_rows; i++) {
-    const Entry* e = r[i].data;
-    uint64_t o = rp[i];
-    for (uint32_t j = 0; j < r[i].size; j++) {
-      col[o + j] = e[j].id;
-      val[o + j] = e[j].value;
+  return guarded([&]() -> int {
+    // reference layout, util/fmatrix.h:34-42
+    struct Entry {
+      uint32_t id;
+      float value;
+    };
+    struct Row {
+      const Entry* data;
+      uint32_t size;
+    };
+    static_assert(sizeof(Row) == 16 && sizeof(Entry) == 8, "LP64 layout of sparse_row/sparse_entry");
+    const Row* r = static_cast<const Row*>(rows);
+    std::vector<uint64_t> rp(n_rows + 1);
+    rp[0] = 0;
+    for (uint64_t i = 0; i < n_rows; i++) rp[i + 1] = rp[i] + r[i].size;
+    const uint64_t nnz = rp[n_rows];
+    std::vector<uint32_t> col(nnz ? nnz : 1);
+    std::vector<float> val(nnz ? nnz : 1);
+    for (uint64_t i = 0; i < n_rows; i++) {
+      const Entry* e = r[i].data;
+      uint64_t o = rp[i];
+      for (uint32_t j = 0; j < r[i].size; j++) {
+        col[o + j] = e[j].id;
+        val[o + j] = e[j].value;
+      }
     }
-  }
-  return upload_common(c, slot, n_rows, nnz, rp.data(), col.data(), val.data(), target);
+    return upload_common(c, slot, n_rows, nnz, rp.data(), col.data(), val.data(), target);
+  });
 }
 
 int fmb200_host_alloc(void** out, uint64_t bytes) {
@@ -365,59 +391,63 @@ int fmb200_set_params(fmb200_ctx* c, double w0, const double* w, const double* v
   NEED_CTX(c);
   if ((c->n && !w) || ((uint64_t)c->n * c->k && !v)) return fail("null parameter pointer");
   if (bind(c)) return 1;
+  return guarded([&]() -> int {
   const uint32_t n = c->n;
-  const int k = c->k, kp = c->kp;
-  // fp64 image: [w0 | w | V attribute-major]
-  std::vector<double> h64(c->p64.n_doubles);
-  h64[0] = w0;
-  for (uint32_t i = 0; i < n; i++) h64[1 + i] = w[i];
-  double* hv = h64.data() + c->p64.off_v;
-  for (int f = 0; f < k; f++)
-    for (uint32_t i = 0; i < n; i++) hv[(size_t)i * k + f] = v[(size_t)f * n + i];
-  // fp32 packed image
-  std::vector<float> h32(c->p32.n_floats, 0.f);
-  h32[0] = (float)w0;
-  for (uint32_t i = 0; i < n; i++) h32[c->p32.off_w + (size_t)i * c->p32.ws] = (float)w[i];
-  float* hv32 = h32.data() + c->p32.off_v;
-  for (int f = 0; f < k; f++)
-    for (uint32_t i = 0; i < n; i++) hv32[(size_t)i * kp + f] = (float)v[(size_t)f * n + i];
-  CK(cudaMemcpyAsync(c->p64.base, h64.data(), h64.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->p32.base, h32.data(), h32.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  return 0;
+    const int k = c->k, kp = c->kp;
+    // fp64 image: [w0 | w | V attribute-major]
+    std::vector<double> h64(c->p64.n_doubles);
+    h64[0] = w0;
+    for (uint32_t i = 0; i < n; i++) h64[1 + i] = w[i];
+    double* hv = h64.data() + c->p64.off_v;
+    for (int f = 0; f < k; f++)
+      for (uint32_t i = 0; i < n; i++) hv[(size_t)i * k + f] = v[(size_t)f * n + i];
+    // fp32 packed image
+    std::vector<float> h32(c->p32.n_floats, 0.f);
+    h32[0] = (float)w0;
+    for (uint32_t i = 0; i < n; i++) h32[c->p32.off_w + (size_t)i * c->p32.ws] = (float)w[i];
+    float* hv32 = h32.data() + c->p32.off_v;
+    for (int f = 0; f < k; f++)
+      for (uint32_t i = 0; i < n; i++) hv32[(size_t)i * kp + f] = (float)v[(size_t)f * n + i];
+    CK(cudaMemcpyAsync(c->p64.base, h64.data(), h64.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->p32.base, h32.data(), h32.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+  });
 }
 
 int fmb200_get_params(fmb200_ctx* c, double* w0, double* w, double* v) {
   NEED_CTX(c);
   if (!w0 || (c->n && !w) || ((uint64_t)c->n * c->k && !v)) return fail("null parameter pointer");
   if (bind(c)) return 1;
+  return guarded([&]() -> int {
   const uint32_t n = c->n;
-  const int k = c->k, kp = c->kp;
-  if (c->mode == FMB200_MODE_INORDER) {
-    std::vector<double> h(c->p64.n_doubles);
-    CK(cudaMemcpyAsync(h.data(), c->p64.base, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    *w0 = h[0];
-    for (uint32_t i = 0; i < n; i++) w[i] = h[1 + i];
-    const double* hv = h.data() + c->p64.off_v;
-    for (int f = 0; f < k; f++)
-      for (uint32_t i = 0; i < n; i++) v[(size_t)f * n + i] = hv[(size_t)i * k + f];
-  } else {
-    std::vector<float> pageable;
-    float* h = static_cast<float*>(c->h_stage);
-    if (h == nullptr) {
-      pageable.resize(c->p32.n_floats);
-      h = pageable.data();
+    const int k = c->k, kp = c->kp;
+    if (c->mode == FMB200_MODE_INORDER) {
+      std::vector<double> h(c->p64.n_doubles);
+      CK(cudaMemcpyAsync(h.data(), c->p64.base, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      *w0 = h[0];
+      for (uint32_t i = 0; i < n; i++) w[i] = h[1 + i];
+      const double* hv = h.data() + c->p64.off_v;
+      for (int f = 0; f < k; f++)
+        for (uint32_t i = 0; i < n; i++) v[(size_t)f * n + i] = hv[(size_t)i * k + f];
+    } else {
+      std::vector<float> pageable;
+      float* h = static_cast<float*>(c->h_stage);
+      if (h == nullptr) {
+        pageable.resize(c->p32.n_floats);
+        h = pageable.data();
+      }
+      CK(cudaMemcpyAsync(h, c->p32.base, c->p32.n_floats * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      *w0 = h[0];
+      for (uint32_t i = 0; i < n; i++) w[i] = h[c->p32.off_w + (size_t)i * c->p32.ws];
+      const float* hv = h + c->p32.off_v;
+      for (uint32_t i = 0; i < n; i++)
+        for (int f = 0; f < k; f++) v[(size_t)f * n + i] = hv[(size_t)i * kp + f];
     }
-    CK(cudaMemcpyAsync(h, c->p32.base, c->p32.n_floats * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    *w0 = h[0];
-    for (uint32_t i = 0; i < n; i++) w[i] = h[c->p32.off_w + (size_t)i * c->p32.ws];
-    const float* hv = h + c->p32.off_v;
-    for (uint32_t i = 0; i < n; i++)
-      for (int f = 0; f < k; f++) v[(size_t)f * n + i] = hv[(size_t)i * kp + f];
-  }
-  return 0;
+    return 0;
+  });
 }
 
 int fmb200_sgd_epoch_async(fmb200_ctx* c, int slot) {
@@ -472,7 +502,12 @@ int fmb200_evaluate(fmb200_ctx* c, int slot, double* sum_sq_err, double* sum_abs
     } else {
       CK(launch_predict32(c, d, 0, nullptr, c->d_partials, nb));
     }
-    std::vector<double> h(3 * (size_t)nb);
+    std::vector<double> h;
+    try {
+      h.resize(3 * (size_t)nb);
+    } catch (const std::bad_alloc&) {
+      return fail("out of host memory");
+    }
     CK(cudaMemcpyAsync(h.data(), c->d_partials, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     for (int b = 0; b < nb; b++) {  // fixed order: deterministic result
