@@ -141,7 +141,12 @@ int fmb200_last_epoch_config(fmb200_ctx* ctx, int* lanes_per_row, int* slots, in
  * on, -1 = force off (plain summed Hogwild on w/V).  variant: 0 = automatic choice
  * of the epoch kernel, 1 = sub-warp row-group kernel, 2 = one-lane-per-row kernel
  * (k <= 8, rows of <= 4 entries; ignored when not applicable), 3 = its warp-specialised
- * form (producer warp + mbarrier hand-offs; bias read three tiles ahead). */
+ * form (producer warp + mbarrier hand-offs; bias read three tiles ahead).
+ * In INORDER mode variant 4 selects the wavefront schedule of the sequential epoch
+ * (k <= 8, rows of <= 4 entries; ignored otherwise): conflict-free runs of examples
+ * gather and scatter in parallel and only the bias chain stays serial.  Bit-identical
+ * to the row-at-a-time kernel by construction (tests/test_oracle.py proves the schedule
+ * on the CPU); opt-in until measured on a device. */
 int fmb200_set_tuning(fmb200_ctx* ctx, int ctas_per_sm, int rows_per_tile, int threads, int damp,
                       int variant);
 

@@ -66,6 +66,15 @@ class Port:
                                C.c_double(self.reg0), C.c_double(self.regw), C.c_double(self.regv),
                                task, C.c_double(min_target), C.c_double(max_target), *_csr(data))
 
+    def sgd_epoch_wavefront(self, data, task, lr, min_target, max_target):
+        """wavefront_emul.c: the schedule of fm_sgd_inorder_wavefront_kernel; returns its step count
+        (0 = shape not eligible, nothing done)."""
+        self.lib.fmo_sgd_epoch_wavefront.restype = C.c_uint64
+        return self.lib.fmo_sgd_epoch_wavefront(
+            C.c_uint32(self.n), self.k, self.k0, self.k1, C.byref(self.w0), _p(self.w, C.c_double),
+            _p(self.v, C.c_double), C.c_double(lr), C.c_double(self.reg0), C.c_double(self.regw),
+            C.c_double(self.regv), task, C.c_double(min_target), C.c_double(max_target), *_csr(data))
+
     def evaluate(self, data, task, min_target, max_target):
         sq, ab, ok = C.c_double(), C.c_double(), C.c_uint64()
         self.lib.fmo_evaluate(C.c_uint32(self.n), self.k, self.k0, self.k1, self.w0,

@@ -83,3 +83,74 @@ def test_port_predict_row_edge_cases():
         pr, sr, ssr = ref.predict_row(col, val)
         pp, sp, ssp = port.predict_row(col, val)
         assert pr == pp and np.array_equal(sr, sp) and np.array_equal(ssr, ssp)
+
+
+def _ragged_short_rows(n_rows, n_feat, seed, dup_every=0):
+    """rows of 0..4 entries with real-valued x, Zipf-ish ids (many collisions inside 32 rows),
+    optionally a repeated id inside a row every `dup_every` rows."""
+    from libfm_b200.model import Data
+    r = np.random.default_rng(seed)
+    sizes = r.integers(0, 5, size=n_rows)
+    row_ptr = np.zeros(n_rows + 1, dtype=np.uint64)
+    row_ptr[1:] = np.cumsum(sizes)
+    nnz = int(row_ptr[-1])
+    p = 1.0 / np.arange(1, n_feat + 1) ** 0.8
+    col = r.choice(n_feat, size=nnz, p=p / p.sum()).astype(np.uint32)
+    if dup_every:
+        for i in range(0, n_rows, dup_every):
+            b, e = int(row_ptr[i]), int(row_ptr[i + 1])
+            if e - b >= 2:
+                col[e - 1] = col[b]
+    val = (r.standard_normal(nnz) * 0.7).astype(np.float32)
+    y = r.integers(1, 6, size=n_rows).astype(np.float32)
+    return Data(row_ptr, col, val, y, n_feat)
+
+
+@pytest.mark.parametrize("case", ["c2_shape", "zipf", "ragged", "dups", "classification", "no_bias", "k3_reg"])
+def test_wavefront_schedule_is_sequentially_equivalent(case):
+    """oracle/wavefront_emul.c replays the schedule of fm_sgd_inorder_wavefront_kernel (conflict-free
+    prefixes of 32 examples, addends formed in parallel, bias chain in order, cached scatter).  It must
+    leave w0 / w / V bit-identical to the sequential loop -- otherwise the kernel's claim is void."""
+    task, k, k0, k1, regs = 0, 8, 1, 1, (0.0, 0.0, 0.0)
+    if case == "c2_shape":
+        tr = synth.two_field(60_000, 6040, 3706, seed=3)
+    elif case == "zipf":
+        tr = synth.two_field(40_000, 600, 400, seed=4, zipf=1.1)
+    elif case == "ragged":
+        tr = _ragged_short_rows(30_000, 500, seed=5)
+    elif case == "dups":
+        tr = _ragged_short_rows(30_000, 300, seed=6, dup_every=7)
+    elif case == "classification":
+        tr = synth.two_field(30_000, 800, 500, seed=7)
+        tr.target[:] = np.where(tr.target > 3, 1.0, -1.0)
+        task = 1
+    elif case == "no_bias":
+        tr = synth.two_field(30_000, 800, 500, seed=8)
+        k0, k1 = 0, 0
+    else:
+        tr = _ragged_short_rows(20_000, 400, seed=9)
+        k, regs = 3, (0.01, 0.02, 0.03)
+    n = tr.num_feature
+    a, b = Port(n, k, k0, k1), Port(n, k, k0, k1)
+    a.init(11, 0.0, 0.1)
+    b.set_params(a.w0.value, a.w, a.v)
+    a.reg0, a.regw, a.regv = regs
+    b.reg0, b.regw, b.regv = regs
+    mn, mx = float(tr.target.min()), float(tr.target.max())
+    for _ in range(2):
+        a.sgd_epoch(tr, task, 0.02, mn, mx)
+        steps = b.sgd_epoch_wavefront(tr, task, 0.02, mn, mx)
+        assert steps > 0
+        assert a.w0.value == b.w0.value
+        assert np.array_equal(a.w, b.w) and np.array_equal(a.v, b.v)
+    # the schedule is worth having only if prefixes are long: report-level sanity
+    if case == "c2_shape":
+        assert tr.num_cases / steps > 12, tr.num_cases / steps
+
+
+def test_wavefront_schedule_refuses_ineligible_shapes():
+    tr = synth.multi_field(2000, 6, 300, seed=1)  # 6 entries per row > 4
+    p = Port(tr.num_feature, 8)
+    assert p.sgd_epoch_wavefront(tr, 0, 0.01, 1.0, 5.0) == 0
+    q = Port(100, 16)
+    assert q.sgd_epoch_wavefront(synth.two_field(100, 50, 50, seed=1), 0, 0.01, 1.0, 5.0) == 0
