@@ -214,6 +214,7 @@ __device__ __forceinline__ uint32_t wf_hash(uint32_t id) {
 }
 static_assert(WF_HASH == (1 << 11), "wf_hash produces 11 bits");
 
+template <bool K0, int TASK>
 __global__ void __launch_bounds__(32, 1)
     fm_sgd_inorder_wavefront_kernel(Params64 p, int n_factor, int use_w0, int use_w, HParams hp,
                                     uint64_t n_rows, const uint64_t* __restrict__ row_ptr,
@@ -228,11 +229,14 @@ __global__ void __launch_bounds__(32, 1)
   const int lane = threadIdx.x;
   const unsigned full = 0xffffffffu;
   const int k = n_factor;
-  const bool k0 = use_w0 != 0, k1 = use_w != 0;
+  constexpr bool k0 = K0;
+  const bool k1 = use_w != 0;
   double* w = p.w();
   double* v = p.v();
   double w0 = k0 ? *p.w0() : 0.0;
   const double lr = hp.lr, reg0 = hp.reg0, regw = hp.regw, regv = hp.regv;
+
+  const bool clamp_inverted = hp.max_target < hp.min_target;  // degenerate bounds: still fmin-then-fmax
 
   for (int i = lane; i < WF_HASH; i += 32) s_hash[i] = 0;
   __syncwarp();
@@ -359,6 +363,7 @@ __global__ void __launch_bounds__(32, 1)
 #pragma unroll
       for (int a = 0; a < NA; a++) nxt[a] = s_add[tn][a];
       const double y = (double)s_y[t];
+      const double m_lo = -(y - hp.min_target), m_hi = -(y - hp.max_target);  // off the chain
       // Unused addend slots hold -0.0, the exact identity of IEEE addition (x + -0.0 == x
       // for every x, signed zeros included): no select sits in the dependent chain.  A
       // model without bias keeps the local w0 at +0.0, so 0.0 + w0 is the reference's
@@ -367,10 +372,16 @@ __global__ void __launch_bounds__(32, 1)
 #pragma unroll
       for (int a = 0; a < NA; a++) pr += cur[a];
       double mult = 0;  // fm_learn_sgd_element.h:58-65
-      if (hp.task == FMB200_TASK_REGRESSION) {
-        pr = fmin(hp.max_target, pr);
-        pr = fmax(hp.min_target, pr);
-        mult = -(y - pr);
+      if (TASK == FMB200_TASK_REGRESSION) {
+        // mult = -(y - clamp(pr)).  The two comparisons and the unclamped difference all
+        // start from pr at once and one select picks among three candidates (two of them
+        // known before the chain), instead of compare -> select -> compare -> select ->
+        // subtract in series.  Same values as fmin(max, .) then fmax(min, .): a NaN or
+        // too-large score takes max_target, then anything below min_target takes it.
+        const bool hi = !(pr <= hp.max_target);
+        const bool lo = hi ? clamp_inverted : (pr < hp.min_target);
+        const double m_mid = -(y - pr);
+        mult = lo ? m_lo : (hi ? m_hi : m_mid);
       } else {
         mult = -y * (1.0 - 1.0 / (1.0 + exp(-y * pr)));
       }
@@ -492,8 +503,16 @@ cudaError_t launch_sgd_inorder(fmb200_ctx* c, const DataSlot& d) {
   if (c->k > 32 * KF_MAX) return cudaErrorInvalidValue;
   // Opt-in (fmb200_set_tuning variant 4) until it has been measured on the device.
   if (c->tune_variant == 4 && c->k <= WF_K && d.max_row_nnz <= (uint32_t)WF_Z && d.n_rows > 0) {
-    fm_sgd_inorder_wavefront_kernel<<<1, 32, 0, c->stream>>>(c->p64, c->k, c->k0, c->k1, c->hp, d.n_rows,
-                                                             d.row_ptr, d.col, d.val, d.target);
+#define FMB_WAVEFRONT(K0, TASK)                                                                       \
+  fm_sgd_inorder_wavefront_kernel<K0, TASK><<<1, 32, 0, c->stream>>>(c->p64, c->k, c->k0, c->k1, c->hp, \
+                                                                     d.n_rows, d.row_ptr, d.col, d.val, \
+                                                                     d.target)
+    const bool reg = c->hp.task == FMB200_TASK_REGRESSION;
+    if (c->k0 && reg) FMB_WAVEFRONT(true, FMB200_TASK_REGRESSION);
+    else if (c->k0) FMB_WAVEFRONT(true, FMB200_TASK_CLASSIFICATION);
+    else if (reg) FMB_WAVEFRONT(false, FMB200_TASK_REGRESSION);
+    else FMB_WAVEFRONT(false, FMB200_TASK_CLASSIFICATION);
+#undef FMB_WAVEFRONT
     c->launches++;
     c->last_cfg = EpochConfig{32, WF_Z, 32, 1, 32, 0};
     return cudaGetLastError();

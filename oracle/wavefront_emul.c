@@ -105,10 +105,11 @@ uint64_t fmo_sgd_epoch_wavefront(uint32_t n, int k, int k0, int k1, double* w0p,
       double pr = 0.0 + w0;
       for (int a = 0; a < WF_Z + WF_K; a++) pr += add[t][a];
       double mult = 0;
-      if (task == 0) {
-        pr = fmin(max_target, pr);
-        pr = fmax(min_target, pr);
-        mult = -(y - pr);
+      if (task == 0) { /* the kernel's select form of -(y - fmax(min, fmin(max, pr))) */
+        double m_lo = -(y - min_target), m_hi = -(y - max_target), m_mid = -(y - pr);
+        int hi = !(pr <= max_target);
+        int lo = hi ? (max_target < min_target) : (pr < min_target);
+        mult = lo ? m_lo : (hi ? m_hi : m_mid);
       } else {
         mult = -y * (1.0 - 1.0 / (1.0 + exp(-y * pr)));
       }
