@@ -35,7 +35,8 @@ CU_SOURCES = {
     "fm_predict.cu": [],
     "fm_inorder.cu": ["--fmad=false"],
 }
-CU_HEADERS = ["fm_device.cuh", "fm_rowgroup.cuh", "fm_hogwild_common.cuh", "fmb200_internal.h"]
+CU_HEADERS = ["fm_device.cuh", "fm_rowgroup.cuh", "fm_hogwild_common.cuh", "fmb200_internal.h",
+              "fm_inorder_wavefront.cuh"]
 
 
 def _newer(target: str, deps: list[str]) -> bool:
