@@ -6,6 +6,7 @@ state theta0; the exchange then forms  theta = theta0 + gamma * sum_g (theta_g -
   average     gamma = 1/G                      (what fmb200_allreduce_mean does today)
   sum         gamma = 1                        (Hogwild across GPUs; overshoots saturated parameters)
   saturation  gamma_i = 1 / (1 + (G-1) s_i),   s_i = 1 - exp(-lr * h_i * count_i)
+  meanfield   gamma_i = (1 - (1-s_i)^G) / (G s_i), same s_i
               count_i = occurrences of feature i in the shard (the per-slot table the library already
               builds for its in-GPU damping), h_i = 1 for w0 / w (x = 1), mean |v|^2 for V rows.
               A parameter whose shard-epoch has already converged it (s -> 1: the bias, hot features)
@@ -62,7 +63,7 @@ def main():
         return p
 
     seq = fresh()
-    rules = ["average", "sum", "saturation"]
+    rules = ["average", "sum", "saturation", "meanfield"]
     state = {r: fresh() for r in rules}
     print("epoch  sequential " + " ".join("%11s" % r for r in rules))
     for e in range(a.epochs):
@@ -84,12 +85,19 @@ def main():
             elif r == "sum":
                 g0 = gw = gv = 1.0
             else:
+                # meanfield: the factor that makes G summed shard-steps of relative size s equal G such
+                # steps taken one after the other on a quadratic: (1 - (1-s)^G) / (G s) -- the same
+                # closed form the HOGWILD kernels use inside one GPU
                 cnt = np.mean(counts, axis=0)
                 sat = lambda h, c: 1.0 - np.exp(-a.lr * h * c)  # noqa: E731
-                g0 = 1.0 / (1.0 + (G - 1) * sat(1.0, tr.num_cases / G))
-                gw = 1.0 / (1.0 + (G - 1) * sat(1.0, cnt))
+                if r == "saturation":
+                    gam = lambda s_: 1.0 / (1.0 + (G - 1) * s_)  # noqa: E731
+                else:
+                    gam = lambda s_: np.where(s_ > 1e-9, (1.0 - (1.0 - s_) ** G) / (G * np.maximum(s_, 1e-9)), 1.0)  # noqa: E731
+                g0 = float(gam(np.float64(sat(1.0, tr.num_cases / G))))
+                gw = gam(sat(1.0, cnt))
                 hv = float(np.mean(np.sum(v_0 * v_0, axis=0)))  # mean squared norm of a factor row
-                gv = (1.0 / (1.0 + (G - 1) * sat(hv, cnt)))[None, :]
+                gv = gam(sat(hv, cnt))[None, :]
             p0.set_params(w0_0 + g0 * d_w0, w_0 + gw * d_w, v_0 + gv * d_v)
             row.append(p0.metric(te, 0, mn, mx))
         print("%5d  %10.5f " % (e + 1, row[0]) + " ".join("%11.5f" % x for x in row[1:]), flush=True)
