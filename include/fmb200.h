@@ -39,6 +39,13 @@ typedef struct fmb200_ctx fmb200_ctx;
 #define FMB200_MODE_HOGWILD 1 /* throughput: rows in parallel, fp32 state, red.global.add
                                  write-back, damped per-tile bias step */
 
+#define FMB200_MODE_ORDERED 2 /* sequentially consistent: every example reads all parameters as
+                                 the examples before it left them (the reference's order), fp64
+                                 state; conflict-free runs of rows execute in parallel and the bias
+                                 chain is solved by an affine prefix scan, so sums associate
+                                 differently: deterministic, within ~1e-12 of the reference (not
+                                 bit-exact; the <=1e-5 RMSE gate with margin), and fast */
+
 #define FMB200_MAX_SLOTS 8
 #define FMB200_MAX_PEERS 16
 #define FMB200_IPC_HANDLE_BYTES 64
@@ -149,6 +156,12 @@ int fmb200_last_epoch_config(fmb200_ctx* ctx, int* lanes_per_row, int* slots, in
  * on the CPU); opt-in until measured on a device. */
 int fmb200_set_tuning(fmb200_ctx* ctx, int ctas_per_sm, int rows_per_tile, int threads, int damp,
                       int variant);
+/* The dependency index ORDERED mode builds per data set (bit-exact index work, tested against a
+ * host restatement): link[e] = e - (previous entry naming the same feature), rowdep[r] = r -
+ * (nearest earlier row sharing a feature; 0 = the row names a feature twice); 0xffffffff = none.
+ * Builds the index if the slot does not have it yet.  Either pointer may be NULL. */
+int fmb200_ordered_index(fmb200_ctx* ctx, int slot, uint32_t* link /* [nnz] */,
+                         uint32_t* rowdep /* [n_rows] */);
 
 #ifdef __cplusplus
 }

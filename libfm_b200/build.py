@@ -34,9 +34,10 @@ CU_SOURCES = {
     "fm_peer.cu": [],
     "fm_predict.cu": [],
     "fm_inorder.cu": ["--fmad=false"],
+    "fm_ordered.cu": [],
 }
 CU_HEADERS = ["fm_device.cuh", "fm_rowgroup.cuh", "fm_hogwild_common.cuh", "fmb200_internal.h",
-              "fm_inorder_wavefront.cuh"]
+              "fm_inorder_wavefront.cuh", "fm_ordered.cuh"]
 
 
 def _newer(target: str, deps: list[str]) -> bool:

@@ -60,6 +60,8 @@ void free_slot(DataSlot& s) {
   if (s.val) cudaFree(s.val);
   if (s.target) cudaFree(s.target);
   if (s.feat_cnt) cudaFree(s.feat_cnt);
+  if (s.link) cudaFree(s.link);
+  if (s.rowdep) cudaFree(s.rowdep);
   if (s.d_flag) cudaFree(s.d_flag);
   if (s.h_flag) cudaFreeHost(s.h_flag);
   if (s.ready) cudaEventDestroy(s.ready);
@@ -100,6 +102,7 @@ int upload_enqueue(fmb200_ctx* c, int slot, uint64_t n_rows, uint64_t nnz, const
     s.cap_nnz = nnz;
   }
   s.present = false;
+  s.links_ready = false;
   s.n_rows = n_rows;
   s.nnz = nnz;
   CK(cudaMemcpyAsync(s.row_ptr, row_ptr, (n_rows + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
@@ -197,8 +200,8 @@ static int create_resources(fmb200_ctx* c, int device, const cudaDeviceProp& pro
   c->p32.off_w = 4;
   c->p32.off_v = 4 + n4;
   c->p32.n_floats = 4 + n4 + (uint64_t)n_attr * c->kp;
-  c->p64.off_v = 1 + (uint64_t)n_attr;
-  c->p64.n_doubles = 1 + (uint64_t)n_attr + (uint64_t)n_attr * num_factor;
+  c->p64.off_v = Params64::off_w + (((uint64_t)n_attr + 1) & ~1ull);
+  c->p64.n_doubles = c->p64.off_v + (uint64_t)n_attr * num_factor + 2;
   c->comm_buf_bytes = (c->p32.n_floats * sizeof(float) + 255) & ~(size_t)255;
   CK(cudaMalloc(&c->comm_base, c->comm_hdr + 2 * c->comm_buf_bytes));
   CK(cudaMemsetAsync(c->comm_base, 0, c->comm_hdr + 2 * c->comm_buf_bytes, c->stream));
@@ -291,14 +294,17 @@ int fmb200_set_hparams(fmb200_ctx* c, int task, double learn_rate, double reg0, 
 
 int fmb200_set_mode(fmb200_ctx* c, int mode) {
   NEED_CTX(c);
-  if (mode != FMB200_MODE_INORDER && mode != FMB200_MODE_HOGWILD) return fail("unknown mode %d", mode);
+  if (mode != FMB200_MODE_INORDER && mode != FMB200_MODE_HOGWILD && mode != FMB200_MODE_ORDERED)
+    return fail("unknown mode %d", mode);
   if (mode == c->mode) return 0;
   if (bind(c)) return 1;
-  // carry the live state into the representation of the new mode
-  if (mode == FMB200_MODE_HOGWILD) {
+  // carry the live state into the representation of the new mode (INORDER and ORDERED share
+  // the fp64 state)
+  const bool was64 = c->mode != FMB200_MODE_HOGWILD, is64 = mode != FMB200_MODE_HOGWILD;
+  if (is64 && c->k > 256) return fail("num_factor > 256 is not supported in the fp64 modes");
+  if (was64 && !is64) {
     CK(launch_p64_to_p32(c));
-  } else {
-    if (c->k > 256) return fail("num_factor > 256 is not supported in INORDER mode");
+  } else if (!was64 && is64) {
     CK(launch_p32_to_p64(c));
   }
   CK(cudaStreamSynchronize(c->stream));
@@ -397,7 +403,7 @@ int fmb200_set_params(fmb200_ctx* c, double w0, const double* w, const double* v
     // fp64 image: [w0 | w | V attribute-major]
     std::vector<double> h64(c->p64.n_doubles);
     h64[0] = w0;
-    for (uint32_t i = 0; i < n; i++) h64[1 + i] = w[i];
+    for (uint32_t i = 0; i < n; i++) h64[Params64::off_w + i] = w[i];
     double* hv = h64.data() + c->p64.off_v;
     for (int f = 0; f < k; f++)
       for (uint32_t i = 0; i < n; i++) hv[(size_t)i * k + f] = v[(size_t)f * n + i];
@@ -422,12 +428,12 @@ int fmb200_get_params(fmb200_ctx* c, double* w0, double* w, double* v) {
   return guarded([&]() -> int {
   const uint32_t n = c->n;
     const int k = c->k, kp = c->kp;
-    if (c->mode == FMB200_MODE_INORDER) {
+    if (c->mode != FMB200_MODE_HOGWILD) {
       std::vector<double> h(c->p64.n_doubles);
       CK(cudaMemcpyAsync(h.data(), c->p64.base, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
       *w0 = h[0];
-      for (uint32_t i = 0; i < n; i++) w[i] = h[1 + i];
+      for (uint32_t i = 0; i < n; i++) w[i] = h[Params64::off_w + i];
       const double* hv = h.data() + c->p64.off_v;
       for (int f = 0; f < k; f++)
         for (uint32_t i = 0; i < n; i++) v[(size_t)f * n + i] = hv[(size_t)i * k + f];
@@ -454,9 +460,15 @@ int fmb200_sgd_epoch_async(fmb200_ctx* c, int slot) {
   NEED_CTX(c);
   if (need_slot(c, slot)) return 1;
   if (bind(c)) return 1;
-  const DataSlot& d = c->slots[slot];
-  if (c->mode == FMB200_MODE_INORDER) {
-    if (c->k > 256) return fail("num_factor > 256 is not supported in INORDER mode");
+  DataSlot& d = c->slots[slot];
+  if (c->mode == FMB200_MODE_ORDERED) {
+    if (c->k > 256) return fail("num_factor > 256 is not supported in the fp64 modes");
+    bool handled = false;
+    CK(launch_sgd_ordered(c, d, &handled));
+    // shapes the ring cannot hold run row-at-a-time: the same order, just slower
+    if (!handled) CK(launch_sgd_inorder(c, d));
+  } else if (c->mode == FMB200_MODE_INORDER) {
+    if (c->k > 256) return fail("num_factor > 256 is not supported in the fp64 modes");
     CK(launch_sgd_inorder(c, d));
   } else {
     if (c->kp > 128) return fail("num_factor > 128 is not supported in HOGWILD mode");
@@ -497,7 +509,7 @@ int fmb200_evaluate(fmb200_ctx* c, int slot, double* sum_sq_err, double* sum_abs
   if (d.n_rows > 0) {
     const int nb = metric_blocks(c, d);
     if (ensure_partials(c, nb)) return 1;
-    if (c->mode == FMB200_MODE_INORDER) {
+    if (c->mode != FMB200_MODE_HOGWILD) {
       CK(launch_predict64(c, d, 0, nullptr, c->d_partials, nb));
     } else {
       CK(launch_predict32(c, d, 0, nullptr, c->d_partials, nb));
@@ -537,7 +549,7 @@ int fmb200_predict(fmb200_ctx* c, int slot, int transform, double* out) {
     c->pred_cap = d.n_rows;
   }
   const int nb = metric_blocks(c, d);
-  if (c->mode == FMB200_MODE_INORDER) {
+  if (c->mode != FMB200_MODE_HOGWILD) {
     CK(launch_predict64(c, d, transform, c->d_pred, nullptr, nb));
   } else {
     CK(launch_predict32(c, d, transform, c->d_pred, nullptr, nb));
@@ -670,11 +682,26 @@ int fmb200_last_epoch_config(fmb200_ctx* c, int* lanes_per_row, int* slots, int*
   return 0;
 }
 
+int fmb200_ordered_index(fmb200_ctx* c, int slot, uint32_t* link, uint32_t* rowdep) {
+  NEED_CTX(c);
+  if (need_slot(c, slot)) return 1;
+  if (bind(c)) return 1;
+  DataSlot& d = c->slots[slot];
+  if (d.nnz >= 0xffffffffull) return fail("the ORDERED index needs nnz < 2^32-1");
+  CK(build_ordered_links(c, d));
+  if (link && d.nnz)
+    CK(cudaMemcpyAsync(link, d.link, d.nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (rowdep && d.n_rows)
+    CK(cudaMemcpyAsync(rowdep, d.rowdep, d.n_rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 int fmb200_set_tuning(fmb200_ctx* c, int ctas_per_sm, int rows_per_tile, int threads, int damp,
                       int variant) {
   NEED_CTX(c);
-  if (threads && (threads % 32 != 0 || threads < 32 || threads > 256))
-    return fail("threads must be a multiple of 32 in [32,256]");
+  if (threads && (threads % 32 != 0 || threads < 32 || threads > 1024))
+    return fail("threads must be a multiple of 32 in [32,1024]");
   if (rows_per_tile && (rows_per_tile < 32 || rows_per_tile > 512))
     return fail("rows_per_tile must be in [32,512]");
   c->tune_ctas_per_sm = ctas_per_sm;

@@ -73,6 +73,14 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
   return p;
 }
 
+// ---- cp.async (LDGSTS): 16-byte L2 -> shared copies, per-thread completion groups ---------
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// all but the most recent group of this thread have landed
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
 // ---- parameter traffic ------------------------------------------------------
 // Parameters are mutated concurrently by other SMs through L2 reductions, so
 // gathers must not be served from a (non-coherent) L1 line: ld.global.cg.

@@ -1,0 +1,215 @@
+// fm_ordered.cu -- launcher of the sequentially consistent epoch (fm_ordered.cuh) and the
+// index work it needs per uploaded data set: for every entry the distance to the previous
+// entry naming the same feature, for every row the distance to the nearest earlier row it
+// depends on.  Both are pure functions of col[] / row_ptr[] (bit-exact ordering work) and
+// are built once per upload, on the device, the first time an ORDERED epoch needs them.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "fm_ordered.cuh"
+#include "fmb200_internal.h"
+
+namespace fmb {
+
+namespace {
+
+__global__ void ord_iota_kernel(uint32_t* p, uint64_t n) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    p[i] = (uint32_t)i;
+}
+
+// row containing entry e: the last r with row_ptr[r] <= e (empty rows skipped by construction)
+__device__ __forceinline__ uint64_t row_of(const uint64_t* __restrict__ rp, uint64_t n_rows, uint64_t e) {
+  uint64_t lo = 0, hi = n_rows;  // invariant: rp[lo] <= e < rp[hi]
+  while (hi - lo > 1) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (rp[mid] <= e) lo = mid;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// `ids` / `ent`: the entries stably sorted by feature id, i.e. each feature's occurrences in
+// file order.  Neighbours with equal id are consecutive occurrences of one feature.
+__global__ void ord_link_kernel(const uint32_t* __restrict__ ids, const uint32_t* __restrict__ ent,
+                                uint64_t nnz, const uint64_t* __restrict__ rp, uint64_t n_rows,
+                                uint32_t* __restrict__ link, uint32_t* __restrict__ rowdep) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nnz;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t e = ent[i];
+    uint32_t L = ORD_NONE;
+    if (i > 0 && ids[i - 1] == ids[i]) {
+      const uint32_t pe = ent[i - 1];
+      L = e - pe;
+      const uint64_t r = row_of(rp, n_rows, e), pr = row_of(rp, n_rows, pe);
+      atomicMin(rowdep + r, (uint32_t)(r - pr));
+    }
+    link[e] = L;
+  }
+}
+
+template <int GL, int KF, int TASK>
+__global__ void __launch_bounds__(ORD_MAX_THREADS, 1) fm_sgd_ordered_kernel(const OrderedArgs a) {
+  extern __shared__ __align__(128) unsigned char ord_smem[];
+  ordered_epoch_body<GL, KF, TASK>(a, ord_smem);
+}
+
+using OrdFn = void (*)(const OrderedArgs);
+
+template <int TASK>
+OrdFn pick_kernel(int k) {
+  if (k <= 1) return fm_sgd_ordered_kernel<1, 1, TASK>;
+  if (k <= 2) return fm_sgd_ordered_kernel<2, 1, TASK>;
+  if (k <= 4) return fm_sgd_ordered_kernel<4, 1, TASK>;
+  if (k <= 8) return fm_sgd_ordered_kernel<8, 1, TASK>;
+  if (k <= 16) return fm_sgd_ordered_kernel<16, 1, TASK>;
+  if (k <= 32) return fm_sgd_ordered_kernel<32, 1, TASK>;
+  if (k <= 64) return fm_sgd_ordered_kernel<32, 2, TASK>;
+  if (k <= 128) return fm_sgd_ordered_kernel<32, 4, TASK>;
+  return fm_sgd_ordered_kernel<32, 8, TASK>;
+}
+
+int grid_for(const fmb200_ctx* c, uint64_t work) {
+  const uint64_t blocks = (work + 255) / 256;
+  const uint64_t cap = (uint64_t)c->sm_count * 8;
+  return (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+
+}  // namespace
+
+// Build link[] / rowdep[] of a data set on c->stream (no host sync).
+cudaError_t build_ordered_links(fmb200_ctx* c, DataSlot& d) {
+  if (d.links_ready) return cudaSuccess;
+  if (d.nnz >= 0xffffffffull) return cudaErrorInvalidValue;
+  cudaError_t e;
+  const uint64_t cap_e = d.cap_nnz + 16, cap_r = d.cap_rows + 520;
+  if (!d.link) {
+    if ((e = cudaMalloc(&d.link, cap_e * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&d.rowdep, cap_r * sizeof(uint32_t))) != cudaSuccess) return e;
+  }
+  if ((e = cudaMemsetAsync(d.link, 0xff, cap_e * sizeof(uint32_t), c->stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(d.rowdep, 0xff, cap_r * sizeof(uint32_t), c->stream)) != cudaSuccess) return e;
+  if (d.nnz > 0) {
+    uint32_t *ids = nullptr, *ent_in = nullptr, *ent = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) < (uint64_t)c->n) bits++;
+    e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d.col, ids, ent_in, ent, (uint64_t)d.nnz, 0, bits,
+                                        c->stream);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaMalloc(&ids, d.nnz * sizeof(uint32_t))) == cudaSuccess &&
+        (e = cudaMalloc(&ent_in, d.nnz * sizeof(uint32_t))) == cudaSuccess &&
+        (e = cudaMalloc(&ent, d.nnz * sizeof(uint32_t))) == cudaSuccess &&
+        (e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16)) == cudaSuccess) {
+      ord_iota_kernel<<<grid_for(c, d.nnz), 256, 0, c->stream>>>(ent_in, d.nnz);
+      e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, d.col, ids, ent_in, ent, (uint64_t)d.nnz, 0, bits,
+                                          c->stream);
+      if (e == cudaSuccess) {
+        ord_link_kernel<<<grid_for(c, d.nnz), 256, 0, c->stream>>>(ids, ent, d.nnz, d.row_ptr, d.n_rows, d.link,
+                                                                  d.rowdep);
+        e = cudaGetLastError();
+        c->launches += 3;  // iota, link + the library's sort passes counted as one
+      }
+    }
+    // stream-ordered release would need a pool; this is a once-per-upload step
+    cudaError_t e2 = cudaStreamSynchronize(c->stream);
+    cudaFree(ids);
+    cudaFree(ent_in);
+    cudaFree(ent);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return e;
+    if (e2 != cudaSuccess) return e2;
+  }
+  d.links_ready = true;
+  return cudaSuccess;
+}
+
+// Pick the tile geometry; false if not even one row fits the ring (caller falls back to the
+// row-at-a-time kernel, which is also sequentially consistent).
+bool ordered_geometry(const fmb200_ctx* c, const DataSlot& d, int* TR_out, uint32_t* TE_out, int* kw_out,
+                      int* rs_out, size_t* smem_out) {
+  const int k = c->k;
+  const int kw = (k & 1) ? k + 1 : k;
+  const int rs = kw + 2;
+  const size_t limit = (size_t)c->max_smem_optin;
+  for (int TR = 256; TR >= 1; TR >>= 1) {
+    uint64_t span;
+    if (TR >= 32) {
+      int idx = 0;
+      while ((32 << idx) < TR) idx++;
+      span = d.tile_span[idx];
+    } else {
+      span = (uint64_t)TR * d.max_row_nnz + 6;
+      if (span > d.tile_span[0]) span = d.tile_span[0];
+    }
+    const uint64_t TE64 = ((span + 3) & ~3ull) + 4;
+    if (TE64 > (1u << 20)) continue;
+    const uint32_t TE = (uint32_t)TE64;
+    const size_t need = ord_smem_bytes(TR, TE, rs);
+    if (need <= limit) {
+      *TR_out = TR;
+      *TE_out = TE;
+      *kw_out = kw;
+      *rs_out = rs;
+      *smem_out = need;
+      return true;
+    }
+  }
+  return false;
+}
+
+cudaError_t launch_sgd_ordered(fmb200_ctx* c, DataSlot& d, bool* handled) {
+  *handled = false;
+  if (d.n_rows == 0) {
+    *handled = true;
+    return cudaSuccess;
+  }
+  if (d.nnz >= 0xffffffffull) return cudaSuccess;  // 32-bit entry distances: not eligible
+  int TR = 0, kw = 0, rs = 0;
+  uint32_t TE = 0;
+  size_t smem = 0;
+  if (!ordered_geometry(c, d, &TR, &TE, &kw, &rs, &smem)) return cudaSuccess;
+  cudaError_t e = build_ordered_links(c, d);
+  if (e != cudaSuccess) return e;
+
+  OrderedArgs a;
+  a.row_ptr = d.row_ptr;
+  a.col = d.col;
+  a.val = d.val;
+  a.target = d.target;
+  a.link = d.link;
+  a.rowdep = d.rowdep;
+  a.n_rows = d.n_rows;
+  a.n_tiles = (uint32_t)((d.n_rows + TR - 1) / TR);
+  a.tile_rows = TR;
+  a.tile_cap = TE;
+  a.w0 = c->p64.w0();
+  a.w = c->p64.w();
+  a.v = c->p64.v();
+  a.k = c->k;
+  a.kw = kw;
+  a.rs = rs;
+  a.use_w0 = c->k0;
+  a.use_w = c->k1;
+  a.lr = c->hp.lr;
+  a.reg0 = c->hp.reg0;
+  a.regw = c->hp.regw;
+  a.regv = c->hp.regv;
+  a.min_target = c->hp.min_target;
+  a.max_target = c->hp.max_target;
+  a.csr_bytes = ord_csr_bytes(TR, TE);
+  a.rec_bytes = TE * (uint32_t)rs * 8u;
+
+  int threads = c->tune_threads ? c->tune_threads : 512;
+  OrdFn fn = c->hp.task == FMB200_TASK_REGRESSION ? pick_kernel<0>(c->k) : pick_kernel<1>(c->k);
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  fn<<<1, threads, smem, c->stream>>>(a);
+  c->launches++;
+  c->last_cfg = EpochConfig{c->k <= 32 ? (c->k <= 1 ? 1 : (1 << (32 - __builtin_clz((unsigned)c->k - 1)))) : 32,
+                            ORD_SMAX, TR, 1, threads, (int)smem, 0};
+  *handled = true;
+  return cudaGetLastError();
+}
+
+}  // namespace fmb

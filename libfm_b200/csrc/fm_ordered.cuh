@@ -1,0 +1,447 @@
+// fm_ordered.cuh -- FMB200_MODE_ORDERED: the sequentially CONSISTENT epoch.
+//
+// Reference semantics (src/libfm/src/fm_learn_sgd_element.h:56-67): example t reads every
+// parameter as examples 0..t-1 left it.  This kernel keeps exactly that read/write ORDER
+// for w0, w and V and changes only the association of three floating-point sums, so its
+// result is deterministic and differs from the reference by rounding only (fp64 state;
+// ~1e-13 relative on the parameters, far inside the 1e-5 RMSE gate of BASELINE.json).  It
+// is NOT bit-exact: that is FMB200_MODE_INORDER (fm_inorder.cu).
+//
+// What makes the reference's loop serial, and how each part is handled here:
+//   (1) w / V rows: example t depends on the LAST earlier example that names one of its
+//       features.  Every upload precomputes, per entry, the distance to that previous
+//       entry (`link`) and, per row, the distance to the nearest earlier row sharing a
+//       feature (`rowdep`) -- pure index work (fm_ordered.cu).  Consecutive rows with no
+//       dependency among them form a RUN (found on the fly from rowdep with two ballots):
+//       their gathers, scores and fm_SGD write-backs (fm_sgd.h:38-50) run in parallel.
+//   (2) the bias: w0 is read and rewritten by every example (fm_model.h:107-109,
+//       fm_sgd.h:34-37), but only through  p_t = w0_t + R_t,  R_t = sum_i w_i x_i +
+//       1/2 sum_f (sum_f^2 - sumsq_f)  independent of w0.  For regression the step
+//       w0' = w0 - lr((clamp(w0+R_t) - y_t) + reg0 w0) is piecewise AFFINE in w0: each
+//       warp solves the whole run with one affine prefix scan (Kogge-Stone over shuffles,
+//       2 examples per lane), guessing every example's clamp state (inside / at min / at
+//       max) from the run's initial w0 and re-scanning while any guess is contradicted --
+//       a consistent assignment is the sequential answer (induction over t), and at least
+//       one more prefix element is final per pass.  Classification (logistic multiplier)
+//       walks the chain serially from shared memory.
+//   (3) memory latency: one CTA owns the epoch (there is ONE chain).  Rows are cut into
+//       TILES; while tile T is processed the CSR of tile T+2 arrives by TMA bulk copies
+//       (cp.async.bulk + mbarrier) and the w / V records of tile T+1 arrive by cp.async
+//       (L2 -> shared, 16 B) into a 3-deep ring of record buffers.  A record fetched that
+//       early is stale if its feature is written by tile T or T+1 itself; exactly those
+//       entries (known from `link`) skip the fetch and read the record FORWARDED in shared
+//       memory: every write-back also lands in the writer's own ring slot.
+//
+// Thread mapping: GL lanes per example (GL = power of two covering k, at most 32; each
+// lane owns KF factors), 32/GL examples per warp, at most ORD_SMAX examples per run.
+//
+// This header is also compiled for the host (tests/simt/: FMB_SIMT_HOST) and run thread
+// for thread against the sequential oracle.
+#pragma once
+#include <stdint.h>
+#ifndef FMB_SIMT_HOST
+#include "fm_device.cuh"
+#endif
+
+namespace fmb {
+
+constexpr uint32_t ORD_NONE = 0xffffffffu;
+constexpr int ORD_SMAX = 64;   // examples per run: 2 per lane in the bias scan
+constexpr int ORD_NBUF = 3;    // ring depth (CSR stages and record buffers)
+constexpr int ORD_HDR_BYTES = 64 + ORD_SMAX * 8;  // [0,24) mbarriers | [64, 64+512) sR
+constexpr int ORD_MAX_THREADS = 1024;
+
+struct OrderedArgs {
+  const uint64_t* row_ptr;
+  const uint32_t* col;
+  const float* val;
+  const float* target;
+  const uint32_t* link;    // [nnz]: e - (previous entry with the same feature), ORD_NONE if none
+  const uint32_t* rowdep;  // [n_rows]: r - (nearest earlier row sharing a feature); 0 = the row
+                           // names a feature twice; ORD_NONE if none
+  uint64_t n_rows;
+  uint32_t n_tiles;
+  int tile_rows;      // TR
+  uint32_t tile_cap;  // TE: entries staged per tile incl. alignment slack (multiple of 4)
+  double* w0;
+  double* w;  // 16-byte aligned
+  double* v;  // 16-byte aligned, attribute-major [n][k]
+  int k;
+  int kw;  // doubles copied per V row: k (k even) or k+1 (k odd: 16-byte window around the row)
+  int rs;  // record stride in doubles = kw + 2 (the aligned pair holding w[id])
+  int use_w0, use_w;
+  double lr, reg0, regw, regv, min_target, max_target;
+  uint32_t csr_bytes;  // one CSR stage
+  uint32_t rec_bytes;  // one record buffer = tile_cap * rs * 8
+};
+
+// ---- shared-memory layout (host and device agree through these) -------------------------
+__host__ __device__ inline uint32_t ord_rp_bytes(int TR) { return (uint32_t)(TR + 2) * 8u; }
+__host__ __device__ inline uint32_t ord_row_bytes(int TR) { return ((uint32_t)(TR + 4) * 4u + 15u) & ~15u; }
+__host__ __device__ inline uint32_t ord_csr_bytes(int TR, uint32_t TE) {
+  return ord_rp_bytes(TR) + 2u * ord_row_bytes(TR) + 4u * TE * 4u;
+}
+__host__ __device__ inline size_t ord_smem_bytes(int TR, uint32_t TE, int rs) {
+  return (size_t)ORD_HDR_BYTES + (size_t)ORD_NBUF * ord_csr_bytes(TR, TE) +
+         (size_t)ORD_NBUF * TE * (size_t)rs * 8u;
+}
+
+struct OrdStage {  // views into one CSR stage
+  const uint64_t* rp;     // rp[i] = row_ptr[r0 + i]
+  const float* tg;        // tg[i] = target[r0 + i]
+  const uint32_t* rd;     // rd[i] = rowdep[r0 + i]
+  const uint32_t* col;    // index j = e - (E0 & ~3)
+  const float* val;
+  const uint32_t* link;
+  uint32_t* src;          // byte offset (from the smem base) of the record each entry reads
+};
+
+__device__ __forceinline__ OrdStage ord_stage(const OrderedArgs& a, unsigned char* smem, uint32_t tile) {
+  unsigned char* b = smem + ORD_HDR_BYTES + (size_t)(tile % ORD_NBUF) * a.csr_bytes;
+  const uint64_t r0 = (uint64_t)tile * a.tile_rows;
+  const uint32_t rpb = ord_rp_bytes(a.tile_rows), rwb = ord_row_bytes(a.tile_rows);
+  OrdStage s;
+  s.rp = reinterpret_cast<const uint64_t*>(b) + (r0 & 1);
+  s.tg = reinterpret_cast<const float*>(b + rpb) + (r0 & 3);
+  s.rd = reinterpret_cast<const uint32_t*>(b + rpb + rwb) + (r0 & 3);
+  unsigned char* e = b + rpb + 2 * rwb;
+  s.col = reinterpret_cast<const uint32_t*>(e);
+  s.val = reinterpret_cast<const float*>(e + (size_t)a.tile_cap * 4);
+  s.link = reinterpret_cast<const uint32_t*>(e + (size_t)a.tile_cap * 8);
+  s.src = reinterpret_cast<uint32_t*>(e + (size_t)a.tile_cap * 12);
+  return s;
+}
+
+__device__ __forceinline__ uint32_t ord_rec_base(const OrderedArgs& a, uint32_t tile) {
+  return (uint32_t)ORD_HDR_BYTES + (uint32_t)ORD_NBUF * a.csr_bytes + (tile % ORD_NBUF) * a.rec_bytes;
+}
+
+// TMA producer (one thread): stage the CSR of `tile`, whose entry range [nb, ne) is known.
+__device__ __forceinline__ void ord_issue_csr(const OrderedArgs& a, unsigned char* smem, uint64_t* bars,
+                                              uint32_t tile, uint64_t nb, uint64_t ne, uint64_t policy) {
+  unsigned char* b = smem + ORD_HDR_BYTES + (size_t)(tile % ORD_NBUF) * a.csr_bytes;
+  const uint64_t r0 = (uint64_t)tile * a.tile_rows;
+  const uint32_t rpb = ord_rp_bytes(a.tile_rows), rwb = ord_row_bytes(a.tile_rows);
+  const uint64_t ab = nb & ~3ull, ae = (ne + 3ull) & ~3ull;
+  const uint32_t eb = (uint32_t)(ae - ab) * 4u;
+  uint64_t* bar = bars + (tile % ORD_NBUF);
+  mbar_arrive_expect_tx(bar, rpb + 2u * rwb + 3u * eb);
+  bulk_g2s_hint(b, a.row_ptr + (r0 & ~1ull), rpb, bar, policy);
+  bulk_g2s_hint(b + rpb, a.target + (r0 & ~3ull), rwb, bar, policy);
+  bulk_g2s_hint(b + rpb + rwb, a.rowdep + (r0 & ~3ull), rwb, bar, policy);
+  if (eb) {
+    unsigned char* e = b + rpb + 2 * rwb;
+    bulk_g2s_hint(e, a.col + ab, eb, bar, policy);
+    bulk_g2s_hint(e + (size_t)a.tile_cap * 4, a.val + ab, eb, bar, policy);
+    bulk_g2s_hint(e + (size_t)a.tile_cap * 8, a.link + ab, eb, bar, policy);
+  }
+}
+
+// Decide, for every entry of tile `tile`, where its record will be read from, and start the
+// fetch of the records that come from HBM/L2.  Runs while tile-1 is being processed, i.e.
+// after the barrier that closed tile-2: anything tile-2 or earlier wrote is visible to the
+// fetch; a feature last written by tile-1 or by this tile is forwarded from the writer's
+// ring slot instead (the fetched copy would be stale).
+__device__ __forceinline__ void ord_prep(const OrderedArgs& a, unsigned char* smem, uint32_t tile, int tid,
+                                         int nthreads) {
+  const OrdStage s = ord_stage(a, smem, tile);
+  const uint64_t r0 = (uint64_t)tile * a.tile_rows;
+  const uint32_t nrows = (uint32_t)min((uint64_t)a.tile_rows, a.n_rows - r0);
+  const uint64_t E0 = s.rp[0], E1 = s.rp[nrows];
+  const uint64_t ab = E0 & ~3ull;
+  const uint32_t j0 = (uint32_t)(E0 - ab), j1 = (uint32_t)(E1 - ab);
+  uint64_t E0p = E0, abp = ab;  // first entry of the previous tile (forwarding window)
+  if (tile > 0) {
+    const OrdStage sp = ord_stage(a, smem, tile - 1);
+    E0p = sp.rp[0];
+    abp = E0p & ~3ull;
+  }
+  const uint32_t rec = ord_rec_base(a, tile), recp = ord_rec_base(a, tile + ORD_NBUF - 1);
+  const uint32_t recb = (uint32_t)a.rs * 8u;
+  const int k = a.k, kw = a.kw;
+  for (uint32_t j = j0 + tid; j < j1; j += nthreads) {
+    const uint32_t L = s.link[j];
+    const uint64_t e = ab + j;
+    uint32_t src = rec + j * recb;
+    if (L != ORD_NONE && (uint64_t)L <= e - E0p) {  // previous writer is inside the window
+      if (L <= j - j0) src = rec + (j - L) * recb;                          // this tile
+      else src = recp + (uint32_t)((e - L) - abp) * recb;                   // the previous tile
+    } else {
+      const uint32_t id = s.col[j];
+      const uint32_t vo = (k & 1) ? (id & 1u) : 0u;
+      const double* gv = a.v + (size_t)id * k - vo;
+      unsigned char* dst = smem + src;
+      for (int c = 0; c < kw; c += 2) cp_async_16(dst + c * 8, gv + c);
+      if (a.use_w) cp_async_16(dst + kw * 8, a.w + (id & ~1u));
+    }
+    s.src[j] = src;
+  }
+}
+
+__device__ __forceinline__ double ord_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double ord_shfl_up(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double ord_shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+// clamp state of a score: 0 inside, 1 at min_target, 2 at max_target.  Same selection as
+// fmin(max, p) then fmax(min, .) (fm_learn_sgd_element.h:60-61): NaN or too large -> max,
+// then anything below min -> min.
+__device__ __forceinline__ int ord_state(double p, double lo, double hi, bool inverted) {
+  const bool h = !(p <= hi);
+  if (h) return inverted ? 1 : 2;
+  return (p < lo) ? 1 : 0;
+}
+
+// first row (tile-relative) at which the run starting at t0 must stop
+__device__ __forceinline__ int ord_detect(const OrdStage& s, int t0, int nrows, int smax, int lane) {
+  bool c0, c1;
+  {
+    const int t = lane, r = t0 + t;
+    c0 = (t >= smax) || (r >= nrows);
+    if (!c0 && t > 0) c0 = s.rd[r] <= (uint32_t)t;
+    if (t == 0 && !c0 && s.rd[r] == 0u) c0 = false;
+  }
+  {
+    const int t = 32 + lane, r = t0 + t;
+    c1 = (t >= smax) || (r >= nrows);
+    if (!c1) c1 = s.rd[r] <= (uint32_t)t;
+  }
+  const unsigned m0 = __ballot_sync(0xffffffffu, c0), m1 = __ballot_sync(0xffffffffu, c1);
+  int P = m0 ? (__ffs(m0) - 1) : (m1 ? 32 + __ffs(m1) - 1 : 64);
+  if (P < 1) P = 1;  // lane 0 never stops its own run (t0 < nrows is the caller's invariant)
+  return P;
+}
+
+template <int GL, int KF, int TASK>
+__device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigned char* smem) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+  constexpr int EPW = 32 / GL;
+  const int gl = lane % GL;
+  const int grp = warp * EPW + lane / GL;  // example slot inside a run
+  const int smax = min(ORD_SMAX, (nthreads >> 5) * EPW);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  double* sR = reinterpret_cast<double*>(smem + 64);
+  const unsigned full = 0xffffffffu;
+
+  if (tid == 0) {
+    for (int i = 0; i < ORD_NBUF; i++) mbar_init(bars + i, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int k = a.k, kw = a.kw;
+  const bool k0 = a.use_w0 != 0, k1 = a.use_w != 0;
+  const double lr = a.lr, reg0 = a.reg0, regw = a.regw, regv = a.regv;
+  const double lo = a.min_target, hi = a.max_target;
+  const bool inverted = hi < lo;
+  const double a_mid = 1.0 - lr * (1.0 + reg0), a_out = 1.0 - lr * reg0;
+  const uint32_t recb = (uint32_t)a.rs * 8u;
+  double w0 = k0 ? *a.w0 : 0.0;
+  const uint32_t NT = a.n_tiles;
+  const int TR = a.tile_rows;
+
+  // producer state (thread 0): entry range of the next tile to stage, fetched a tile ahead
+  uint64_t policy = 0, nb = 0, ne = 0;
+  if (tid == 0) {
+    policy = policy_evict_first();
+    for (uint32_t t = 0; t < 2 && t < NT; t++) {
+      const uint64_t r0 = (uint64_t)t * TR, r1 = min(r0 + TR, a.n_rows);
+      ord_issue_csr(a, smem, bars, t, a.row_ptr[r0], a.row_ptr[r1], policy);
+    }
+    if (2 < NT) {
+      const uint64_t r0 = 2ull * TR, r1 = min(r0 + TR, a.n_rows);
+      nb = a.row_ptr[r0];
+      ne = a.row_ptr[r1];
+    }
+  }
+  mbar_wait(bars + 0, 0);
+  ord_prep(a, smem, 0, tid, nthreads);
+  cp_async_commit();
+
+  for (uint32_t T = 0; T < NT; T++) {
+    if (tid == 0 && T + 2 < NT) {  // stage (T+2)%3 held tile T-1: closed by the last barrier
+      ord_issue_csr(a, smem, bars, T + 2, nb, ne, policy);
+      if (T + 3 < NT) {
+        const uint64_t r0 = (uint64_t)(T + 3) * TR, r1 = min(r0 + TR, a.n_rows);
+        nb = a.row_ptr[r0];
+        ne = a.row_ptr[r1];
+      }
+    }
+    if (T + 1 < NT) {
+      mbar_wait(bars + (T + 1) % ORD_NBUF, ((T + 1) / ORD_NBUF) & 1);
+      ord_prep(a, smem, T + 1, tid, nthreads);
+    }
+    cp_async_commit();
+    cp_async_wait_1();  // this thread's fetches for tile T have landed
+    __syncthreads();    // ... and everyone's; src[] of tile T is complete
+
+    const OrdStage s = ord_stage(a, smem, T);
+    const uint64_t r0 = (uint64_t)T * TR;
+    const int nrows = (int)min((uint64_t)TR, a.n_rows - r0);
+    const uint64_t ab = s.rp[0] & ~3ull;
+    const uint32_t rec = ord_rec_base(a, T);
+
+    int t0 = 0;
+    int P = ord_detect(s, 0, nrows, smax, lane);
+    while (t0 < nrows) {
+      // ---- scores of the run's examples: fm_model.h:105-127 with R_t = p_t - w0 ----------
+      const bool act = grp < P;
+      const int r = t0 + grp;
+      uint32_t jb = 0, je = 0;
+      bool rowdup = false;
+      double sum[KF];
+#pragma unroll
+      for (int q = 0; q < KF; q++) sum[q] = 0.0;
+      double Rloc = 0.0;
+      if (act) {
+        jb = (uint32_t)(s.rp[r] - ab);
+        je = (uint32_t)(s.rp[r + 1] - ab);
+        rowdup = s.rd[r] == 0u;
+        double ssq[KF];
+#pragma unroll
+        for (int q = 0; q < KF; q++) ssq[q] = 0.0;
+        for (uint32_t j = jb; j < je; j++) {
+          uint32_t jj = j;
+          if (rowdup)  // a feature named twice: both entries score with the value before the row
+            while (s.link[jj] != ORD_NONE && s.link[jj] <= jj - jb) jj -= s.link[jj];
+          const unsigned char* rp_ = smem + s.src[jj];
+          const uint32_t id = s.col[j];
+          const double x = (double)s.val[j];
+          const uint32_t vo = (k & 1) ? (id & 1u) : 0u;
+          const double* vr = reinterpret_cast<const double*>(rp_) + vo;
+#pragma unroll
+          for (int q = 0; q < KF; q++) {
+            const int f = gl + q * GL;
+            if (f < k) {
+              const double d = vr[f] * x;
+              sum[q] += d;
+              ssq[q] += d * d;
+            }
+          }
+          if (k1 && (int)((j - jb) % GL) == gl)
+            Rloc += reinterpret_cast<const double*>(rp_)[kw + (id & 1u)] * x;
+        }
+#pragma unroll
+        for (int q = 0; q < KF; q++)
+          if (gl + q * GL < k) Rloc += 0.5 * (sum[q] * sum[q] - ssq[q]);
+      }
+#pragma unroll
+      for (int o = GL / 2; o > 0; o >>= 1) Rloc += ord_shfl_xor(Rloc, o);
+
+      const int t0n = t0 + P;
+      double mult = 0.0;
+      if (k0) {
+        if (act && gl == 0) sR[grp] = Rloc;
+        __syncthreads();
+        if (TASK == 0) {
+          // ---- bias: affine prefix scan over the run, every warp redundantly ---------------
+          const int ta = 2 * lane, tb = ta + 1;
+          const bool va = ta < P, vb = tb < P;
+          const double Ra = va ? sR[ta] : 0.0, Rb = vb ? sR[tb] : 0.0;
+          const double ya = va ? (double)s.tg[t0 + ta] : 0.0, yb = vb ? (double)s.tg[t0 + tb] : 0.0;
+          int sa = ord_state(w0 + Ra, lo, hi, inverted), sb = ord_state(w0 + Rb, lo, hi, inverted);
+          double w0a = w0, w0b = w0, A = 1.0, B = 0.0;
+          for (int it = 0; it <= 2 * ORD_SMAX; it++) {
+            const double aa = va ? (sa == 0 ? a_mid : a_out) : 1.0;
+            const double ba = va ? -lr * ((sa == 0 ? Ra : (sa == 1 ? lo : hi)) - ya) : 0.0;
+            const double ab_ = vb ? (sb == 0 ? a_mid : a_out) : 1.0;
+            const double bb = vb ? -lr * ((sb == 0 ? Rb : (sb == 1 ? lo : hi)) - yb) : 0.0;
+            A = ab_ * aa;  // w0 -> ab_*(aa*w0 + ba) + bb
+            B = ab_ * ba + bb;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const double Ap = ord_shfl_up(A, o), Bp = ord_shfl_up(B, o);
+              if (lane >= o) {
+                B = A * Bp + B;
+                A = A * Ap;
+              }
+            }
+            double Ae = ord_shfl_up(A, 1), Be = ord_shfl_up(B, 1);
+            if (lane == 0) {
+              Ae = 1.0;
+              Be = 0.0;
+            }
+            w0a = Ae * w0 + Be;
+            w0b = aa * w0a + ba;
+            const int na = ord_state(w0a + Ra, lo, hi, inverted);
+            const int nb_ = ord_state(w0b + Rb, lo, hi, inverted);
+            const bool bad = (va && na != sa) || (vb && nb_ != sb);
+            sa = na;
+            sb = nb_;
+            if (!__any_sync(full, bad)) break;
+          }
+          // fm_learn_sgd_element.h:58-62: mult = -(y - clamp(p))
+          const double ma = (sa == 0 ? w0a + Ra : (sa == 1 ? lo : hi)) - ya;
+          const double mb = (sb == 0 ? w0b + Rb : (sb == 1 ? lo : hi)) - yb;
+          w0 = ord_shfl(A, 31) * w0 + ord_shfl(B, 31);
+          const double m0 = ord_shfl(ma, (grp >> 1) & 31), m1 = ord_shfl(mb, (grp >> 1) & 31);
+          mult = (grp & 1) ? m1 : m0;
+        } else {
+          // ---- classification: the chain walked serially (fm_learn_sgd_element.h:63-64) ----
+          for (int t = 0; t < P; t++) {
+            const double y = (double)s.tg[t0 + t];
+            const double p = w0 + sR[t];
+            const double m = -y * (1.0 - 1.0 / (1.0 + exp(-y * p)));
+            if (t == grp) mult = m;
+            w0 -= lr * (m + reg0 * w0);
+          }
+        }
+      } else if (act) {
+        const double y = (double)s.tg[r];
+        if (TASK == 0) {
+          const int st = ord_state(Rloc, lo, hi, inverted);
+          mult = (st == 0 ? Rloc : (st == 1 ? lo : hi)) - y;
+        } else {
+          mult = -y * (1.0 - 1.0 / (1.0 + exp(-y * Rloc)));
+        }
+      }
+      const int Pn = (t0n < nrows) ? ord_detect(s, t0n, nrows, smax, lane) : 1;
+
+      // ---- fm_SGD (fm_sgd.h:38-50) for the lane's example: own ring slot + global ----------
+      if (act) {
+        for (uint32_t j = jb; j < je; j++) {
+          uint32_t jj = j;
+          bool dupj = false;
+          if (rowdup) {
+            dupj = s.link[j] != ORD_NONE && s.link[j] <= j - jb;
+            if (!dupj)
+              while (s.link[jj] != ORD_NONE && s.link[jj] <= jj - jb) jj -= s.link[jj];
+          }
+          // a repeated feature continues from the row's previous write (fm_sgd.h:46 reads v again)
+          const uint32_t so = dupj ? rec + (j - s.link[j]) * recb : s.src[jj];
+          const unsigned char* rp_ = smem + so;
+          unsigned char* own = smem + rec + j * recb;
+          const uint32_t id = s.col[j];
+          const double x = (double)s.val[j];
+          const uint32_t vo = (k & 1) ? (id & 1u) : 0u;
+          const double* vr = reinterpret_cast<const double*>(rp_) + vo;
+          double* vown = reinterpret_cast<double*>(own) + vo;
+          double* gv = a.v + (size_t)id * k;
+#pragma unroll
+          for (int q = 0; q < KF; q++) {
+            const int f = gl + q * GL;
+            if (f < k) {
+              double c = vr[f];
+              const double grad = sum[q] * x - c * x * x;
+              c -= lr * (mult * grad + regv * c);
+              vown[f] = c;
+              gv[f] = c;
+            }
+          }
+          const bool mine = rowdup ? (gl == 0) : ((int)((j - jb) % GL) == gl);
+          if (k1 && mine) {
+            double c = reinterpret_cast<const double*>(rp_)[kw + (id & 1u)];
+            c -= lr * (mult * x + regw * c);
+            reinterpret_cast<double*>(own)[kw + (id & 1u)] = c;
+            a.w[id] = c;
+          }
+        }
+      }
+      __syncthreads();  // the run's ring slots are final before the next run reads them
+      t0 = t0n;
+      P = Pn;
+    }
+  }
+  if (tid == 0 && k0) *a.w0 = w0;
+}
+
+}  // namespace fmb

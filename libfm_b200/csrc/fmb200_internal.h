@@ -29,6 +29,11 @@ struct DataSlot {
   // worst-case 4-element-aligned nnz span of any tile of 2^(5+i) rows
   // (i = 0..4 -> 32, 64, 128, 256, 512 rows); sizes the smem staging buffers
   uint32_t tile_span[5] = {0, 0, 0, 0, 0};
+  // ORDERED mode (fm_ordered.cu): per-entry distance to the previous entry of the same
+  // feature, per-row distance to the nearest earlier row sharing a feature; built lazily
+  uint32_t* link = nullptr;
+  uint32_t* rowdep = nullptr;
+  bool links_ready = false;
 };
 
 // Packed fp32 state: [w0, 0, 0, 0 | w[n*ws] padded to a multiple of 4 | V[n][kp]].
@@ -46,13 +51,15 @@ struct Params32 {
   __host__ __device__ float* v() const { return base + off_v; }
 };
 
-// fp64 state: [w0 | w[n] | V[n][k]] attribute-major, unpadded
+// fp64 state: [w0, pad | w[n] (+pad to even) | V[n][k] | 2 pad] attribute-major; w and V start
+// on 16-byte boundaries (the ORDERED epoch fetches them with 16-byte cp.async)
 struct Params64 {
   double* base = nullptr;
   uint64_t n_doubles = 0;
   uint64_t off_v = 0;
+  static constexpr uint64_t off_w = 2;
   __host__ __device__ double* w0() const { return base; }
-  __host__ __device__ double* w() const { return base + 1; }
+  __host__ __device__ double* w() const { return base + off_w; }
   __host__ __device__ double* v() const { return base + off_v; }
 };
 
@@ -115,6 +122,10 @@ cudaError_t launch_sgd_inorder(fmb200_ctx* c, const DataSlot& d);
 // partials (3 doubles per block: sq, abs, correct) may be null.
 cudaError_t launch_predict64(fmb200_ctx* c, const DataSlot& d, int transform, double* out_pred,
                              double* partials, int n_blocks);
+// fm_ordered.cu: sequentially consistent fp64 epoch (runs of independent rows in parallel, bias by
+// affine scan).  *handled = false: shape not eligible, nothing launched (caller uses launch_sgd_inorder)
+cudaError_t launch_sgd_ordered(fmb200_ctx* c, DataSlot& d, bool* handled);
+cudaError_t build_ordered_links(fmb200_ctx* c, DataSlot& d);
 // fm_hogwild.cu: throughput epoch
 cudaError_t launch_sgd_hogwild(fmb200_ctx* c, const DataSlot& d);
 // fm_predict.cu: fp32 scores / metrics with sub-warp row groups

@@ -23,6 +23,7 @@ TASK_REGRESSION = 0  # fm_learn.h:47
 TASK_CLASSIFICATION = 1  # fm_learn.h:48
 MODE_INORDER = 0
 MODE_HOGWILD = 1
+MODE_ORDERED = 2  # sequentially consistent, fp64, parallel over conflict-free runs (fm_ordered.cuh)
 
 
 class FmError(RuntimeError):
@@ -261,14 +262,26 @@ class FmLearnSgdElement:
         self._check(self.lib.fmb200_upload_data(
             self._ctx, slot, data.num_cases, data.num_values, _p(data.row_ptr, C.c_uint64),
             _p(data.col, C.c_uint32), _p(data.val, C.c_float), _p(data.target, C.c_float)))
-        self._slots[id(data)] = slot
+        # the Data object is kept alive with its slot: id() values are reused after garbage
+        # collection, and a recycled id must never map to a stale upload
+        for key in [k for k, (s, _) in self._slots.items() if s == slot]:
+            del self._slots[key]
+        self._slots[id(data)] = (slot, data)
+
+    def release(self, data: Data) -> None:
+        """Free the device copy of `data` and its slot."""
+        ent = self._slots.pop(id(data), None)
+        if ent is not None:
+            self._check(self.lib.fmb200_free_data(self._ctx, ent[0]))
 
     def _slot_of(self, data: Data) -> int:
         if id(data) not in self._slots:
-            used = set(self._slots.values())
-            slot = next(s for s in range(8) if s not in used)
-            self.upload(data, slot)
-        return self._slots[id(data)]
+            used = {s for s, _ in self._slots.values()}
+            free = [s for s in range(8) if s not in used]
+            if not free:
+                raise FmError("all 8 data slots are in use: release() one first")
+            self.upload(data, free[0])
+        return self._slots[id(data)][0]
 
     # -- the reference's learner surface -----------------------------------
     def sgd_epoch(self, train: Data) -> float:
@@ -322,6 +335,14 @@ class FmLearnSgdElement:
         n = C.c_uint64()
         self._check(self.lib.fmb200_kernel_launches(self._ctx, C.byref(n)))
         return n.value
+
+    def ordered_index(self, data: Data):
+        """(link, rowdep) of fm_ordered.cu for `data` (tests)."""
+        link = np.empty(max(data.num_values, 1), dtype=np.uint32)
+        rowdep = np.empty(max(data.num_cases, 1), dtype=np.uint32)
+        self._check(self.lib.fmb200_ordered_index(self._ctx, self._slot_of(data), _p(link, C.c_uint32),
+                                                  _p(rowdep, C.c_uint32)))
+        return link[:data.num_values], rowdep[:data.num_cases]
 
     def epoch_config(self) -> dict:
         v = [C.c_int() for _ in range(7)]

@@ -109,20 +109,21 @@ bool run_case(const Case& c, int epochs) {
   const uint32_t n = c.n_feat;
   const int k = c.k;
   Rng r(99);
-  // oracle state: factor-major V [k][n]; device state: [w0 | w[n] | V[n][k]]
+  // oracle state: factor-major V [k][n]; device state: Params64 [w0, pad | w[n] (even) | V[n][k]]
   double w0 = 0.05;
   std::vector<double> w(n), v((size_t)k * n);
   for (auto& x : w) x = r.gauss() * 0.1;
   for (auto& x : v) x = r.gauss() * 0.1;
-  std::vector<double> dev(1 + (size_t)n + (size_t)n * k);
+  const size_t OW = fmb::Params64::off_w, OV = OW + (((size_t)n + 1) & ~(size_t)1);
+  std::vector<double> dev(OV + (size_t)n * k + 2);
   dev[0] = w0;
-  for (uint32_t i = 0; i < n; i++) dev[1 + i] = w[i];
+  for (uint32_t i = 0; i < n; i++) dev[OW + i] = w[i];
   for (int f = 0; f < k; f++)
-    for (uint32_t i = 0; i < n; i++) dev[1 + n + (size_t)i * k + f] = v[(size_t)f * n + i];
+    for (uint32_t i = 0; i < n; i++) dev[OV + (size_t)i * k + f] = v[(size_t)f * n + i];
   fmb::Params64 p;
   p.base = dev.data();
   p.n_doubles = dev.size();
-  p.off_v = 1 + (uint64_t)n;
+  p.off_v = OV;
   fmb::HParams hp;
   hp.task = c.task;
   hp.lr = 0.02;
@@ -144,10 +145,10 @@ bool run_case(const Case& c, int epochs) {
   if (c.k0 && memcmp(&dev[0], &w0, 8) != 0) bad++;
   if (!c.k0 && dev[0] != 0.05) bad++;  // no bias: untouched
   for (uint32_t i = 0; i < n; i++)
-    if (memcmp(&dev[1 + i], &w[i], 8) != 0) bad++;
+    if (memcmp(&dev[OW + i], &w[i], 8) != 0) bad++;
   for (int f = 0; f < k; f++)
     for (uint32_t i = 0; i < n; i++)
-      if (memcmp(&dev[1 + n + (size_t)i * k + f], &v[(size_t)f * n + i], 8) != 0) bad++;
+      if (memcmp(&dev[OV + (size_t)i * k + f], &v[(size_t)f * n + i], 8) != 0) bad++;
   printf("%-16s rows=%llu n=%u k=%d  %s (%llu differing values)\n", c.name, (unsigned long long)c.n_rows, n, k,
          bad ? "MISMATCH" : "bit-identical", (unsigned long long)bad);
   return bad == 0;
