@@ -13,9 +13,15 @@ and the 1/N scale).  Weak scaling: every rank owns a full C2-sized row shard.
 value  : examples/s with inputs resident in HBM, CUDA events on the library's own
          stream, L2 flushed (256 MiB write) before every timed step, max over ranks.
 e2e    : examples/s through the C ABI with HOST (pinned) buffers: every step uploads
-         the CSR (fmb200_upload_data_async, two device slots so the copy of the next
-         step overlaps this step's epoch), runs the epoch and reads the model back
-         (fmb200_get_params); wall clock over the timed steps.
+         the data set (fmb200_upload_onehot_async: ids + targets, 12 B/row for this one-hot
+         shape; two device slots so the copy of the next step overlaps this step's epoch),
+         runs the epoch and reads the model back (fmb200_get_params); wall clock.
+parity : RMSE trajectory of the timed mode against the sequential oracle on a planted-signal
+         C2-shaped set from the same initial model (N == 1).
+tolerance_mode : the same workload in FMB200_MODE_ORDERED (sequentially consistent, fp64, inside
+         the 1e-5 RMSE gate): examples/s device-timed and end to end, and its parity numbers.
+extra  : BASELINE configs C3 (k=64, 39 nnz/row, 1M features, 10M rows) and C2 with Zipf(1) ids,
+         each with its own roofline object (N == 1; --no-extras skips them).
 """
 from __future__ import annotations
 
@@ -165,6 +171,125 @@ class _DevBuf:
 
 
 # --------------------------------------------------------------------------
+# parity of a mode against the sequential oracle (planted-signal C2 shape)
+# --------------------------------------------------------------------------
+def parity_run(mode, device, epochs=5, tuning=None):
+    """RMSE per epoch (train, held-out) of `mode` and of the oracle from the same initial model."""
+    import numpy as np
+    from libfm_b200 import FmLearnSgdElement, FmModel, synth
+    from oracle import Port
+    tr = synth.movielens_1m_shaped(seed=7, planted_k=4)
+    te = synth.two_field(100_000, 6040, 3706, seed=8, planted_k=4)
+    n = tr.num_feature
+    v0 = np.random.default_rng(42).standard_normal((K_FACTORS, n)) * 0.1
+    port = Port(n, K_FACTORS)
+    port.set_params(0.0, np.zeros(n), v0)
+    fm = FmModel(n, K_FACTORS)
+    fm.v = v0.copy()
+    l = FmLearnSgdElement(fm, device=device, mode=mode)
+    l.task, l.learn_rate = 0, LEARN_RATE
+    l.min_target, l.max_target = tr.min_target, tr.max_target
+    l.push_hparams()
+    if tuning:
+        l.set_tuning(*tuning)
+    gpu, ref = [], []
+    for _ in range(epochs):
+        l.sgd_epoch(tr)
+        port.sgd_epoch(tr, 0, LEARN_RATE, tr.min_target, tr.max_target)
+        gpu.append([l.evaluate(tr), l.evaluate(te)])
+        ref.append([port.metric(tr, 0, tr.min_target, tr.max_target),
+                    port.metric(te, 0, tr.min_target, tr.max_target)])
+    l.close()
+    gap = max(max(abs(g[0] - r[0]), abs(g[1] - r[1])) for g, r in zip(gpu, ref))
+    return {"data": "C2-shaped, planted rank-4 signal + noise, 1000209 train / 100000 held-out rows",
+            "epochs": epochs, "rmse_gpu": gpu, "rmse_ref": ref, "max_abs_gap": gap,
+            "oracle": "oracle/fm_oracle.c (pinned bit-exact to the reference)", "tolerance_north_star": 1e-5}
+
+
+def timed_epochs(lrn, data, steps, warmup, flush, stream, torch):
+    """CUDA-event time per epoch on the library's stream, L2 flushed before every step."""
+    lib, ctx = lrn.lib, lrn._ctx
+    slot = lrn._slot_of(data)
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            flush.zero_()
+            if lib.fmb200_sgd_epoch_async(ctx, slot) != 0:
+                raise RuntimeError(lib.fmb200_last_error().decode())
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            flush.zero_()
+            a.record(stream)
+            if lib.fmb200_sgd_epoch_async(ctx, slot) != 0:
+                raise RuntimeError(lib.fmb200_last_error().decode())
+            b.record(stream)
+        torch.cuda.synchronize()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    return sum(ms) / len(ms)
+
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def static_traffic(key, rows):
+    """ncu dram__bytes_read+write per launch from the committed capture (NOT a per-run measurement;
+    scaled by the row count when the captured launch covered fewer rows)."""
+    tp = os.path.join(ROOT, "profiles", "epoch_dram_bytes.json")
+    try:
+        ent = json.load(open(tp))[key]
+        scale = rows / ent["rows_per_launch"]
+        src = "static: " + ent["source"]
+        if abs(scale - 1.0) > 1e-9:
+            src += "; scaled x%.3g to this launch's rows" % scale
+        return ent["dram_bytes_per_launch"] * scale, src
+    except Exception:
+        return None, None
+
+
+def kernel_name(cfg, mode):
+    if mode == "ordered":
+        return "fm_sgd_ordered_kernel<GL=%d> (1 CTA x %d threads)" % (cfg["lanes_per_row"], cfg["block"])
+    if cfg["lanes_per_row"] == 1:
+        return "fm_sgd_rowlane_kernel<GP=%d,Z=%d,DAMP=%d> (grid %d x %d)" % (
+            2 if K_FACTORS > 4 else 1, cfg["slots"], cfg["damp"], cfg["grid"], cfg["block"])
+    return "fm_sgd_hogwild_kernel<G=%d,S=%d,DAMP=%d> (grid %d x %d)" % (
+        cfg["lanes_per_row"], cfg["slots"], cfg["damp"], cfg["grid"], cfg["block"])
+
+
+def extra_config(name, data, k, task, device, steps, warmup, flush, stream, torch, traffic_key):
+    """One more BASELINE config, device-timed, with its own roofline object."""
+    from libfm_b200 import FmLearnSgdElement, FmModel, MODE_HOGWILD
+    fm = FmModel(data.num_feature, k)
+    fm.init_stdev = 0.1
+    fm.init_numpy(42)
+    l = FmLearnSgdElement(fm, device=device, mode=MODE_HOGWILD)
+    l.task, l.learn_rate = task, LEARN_RATE
+    l.min_target, l.max_target = data.min_target, data.max_target
+    l.push_hparams()
+    l.upload(data, 0)
+    launches0 = l.kernel_launches()
+    ms = timed_epochs(l, data, steps, warmup, flush, stream, torch)
+    launches = l.kernel_launches() - launches0
+    cfg = l.epoch_config()
+    l.close()
+    peak, peak_src = hbm_peak()
+    z = data.num_values / data.num_cases
+    bpe = 2 * k * z * 4
+    achieved = data.num_cases * bpe / (ms * 1e-3) / 1e9
+    traffic, tsrc = static_traffic(traffic_key, data.num_cases)
+    return {"workload": name, "rows": data.num_cases, "k": k, "nnz_per_row": z, "value": data.num_cases / (ms * 1e-3),
+            "unit": UNIT, "ms_per_step": ms, "steps": steps, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src,
+                         "algorithmic_bytes_per_example": bpe, "kernel": kernel_name(cfg, "hogwild")},
+            "kernel_geometry": cfg}
+
+
+# --------------------------------------------------------------------------
 # the GPU arm
 # --------------------------------------------------------------------------
 def run_gpu_arm(args):
@@ -272,7 +397,6 @@ def run_gpu_arm(args):
             b.record(stream)
         torch.cuda.synchronize()
         sampler.sample()
-        sampler.stop_flag = True
         wall = time.perf_counter() - wall0
         barrier()
     launches = lrn.kernel_launches() - launches0
@@ -287,16 +411,17 @@ def run_gpu_arm(args):
 
     # ---- end to end through the C ABI, host buffers ------------------------
     from libfm_b200.model import pinned_copy
-    rp, col, val, tgt = [pinned_copy(a) for a in (data.row_ptr, data.col, data.val, data.target)]
+    ids_h, tgt_h = pinned_copy(data.col), pinned_copy(data.target)
     w0 = C.c_double()
     w_out = np.empty(n, dtype=np.float64)
     v_out = np.empty((K_FACTORS, n), dtype=np.float64)
     P = lambda a, t: a.ctypes.data_as(C.POINTER(t))  # noqa: E731
     n_e2e = max(3, min(args.steps, 20))
+    nnz_per_row = data.num_values // rows
 
     def upload_async(slot):
-        rc = lib.fmb200_upload_data_async(ctx, slot, rows, int(rp[-1]), P(rp, C.c_uint64), P(col, C.c_uint32),
-                                          P(val, C.c_float), P(tgt, C.c_float))
+        # one-hot shape: ids + targets cross PCIe, offsets / values are materialised on the device
+        rc = lib.fmb200_upload_onehot_async(ctx, slot, rows, nnz_per_row, P(ids_h, C.c_uint32), P(tgt_h, C.c_float))
         if rc != 0:
             raise RuntimeError(lib.fmb200_last_error().decode())
 
@@ -305,13 +430,12 @@ def run_gpu_arm(args):
     # pays one full upload, one epoch (+ exchange) and one read-back of the model.
     cur_slot = [2, 3]
 
-    def e2e_step():
+    def e2e_step(exchange=True):
         upload_async(cur_slot[1])                 # next step's inputs: host -> device
-        global_slot = cur_slot[0]
-        rc = lib.fmb200_sgd_epoch_async(ctx, global_slot)   # waits for this slot's upload
-        if rc == 0 and collective == "p2p":
+        rc = lib.fmb200_sgd_epoch_async(ctx, cur_slot[0])   # waits for this slot's upload
+        if exchange and rc == 0 and collective == "p2p":
             rc = lib.fmb200_allreduce_mean(ctx)
-        elif rc == 0 and collective == "nccl":
+        elif exchange and rc == 0 and collective == "nccl":
             with torch.cuda.stream(stream):
                 dist.all_reduce(params)
             rc = lib.fmb200_scale_params(ctx, 1.0 / world)
@@ -321,52 +445,91 @@ def run_gpu_arm(args):
             raise RuntimeError(lib.fmb200_last_error().decode())
         cur_slot.reverse()
 
-    upload_async(cur_slot[0])
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(n_e2e):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    barrier()
-    e2e_value = world * rows / float(e2e_s.item())
-    h2d = int(rp.nbytes + col.nbytes + val.nbytes + tgt.nbytes)
-    d2h = int(n_floats * 4)
+    def e2e_measure(exchange=True):
+        upload_async(cur_slot[0])
+        for _ in range(2):
+            e2e_step(exchange)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step(exchange)
+        torch.cuda.synchronize()
+        t = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device="cuda")
+        if world > 1 and exchange:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(t.item())
 
+    e2e_value = world * rows / e2e_measure()
+    h2d = int(ids_h.nbytes + tgt_h.nbytes)
+    d2h = int(n_floats * 4)
     cfg = lrn.epoch_config()
+    launches_total = lrn.kernel_launches()
+
+    # ---- the tolerance mode: the same workload, sequentially consistent (N == 1) -------------
+    tol = None
+    if world == 1 and not args.no_tolerance_mode:
+        from libfm_b200 import MODE_ORDERED
+        lrn.set_mode(MODE_ORDERED)
+        l0 = lrn.kernel_launches()
+        o_steps = max(3, min(args.steps, 10))
+        o_ms = timed_epochs(lrn, data, o_steps, 2, flush, stream, torch)
+        o_launches = lrn.kernel_launches() - l0
+        o_cfg = lrn.epoch_config()
+        o_e2e = rows / e2e_measure(exchange=False)
+        peak, _ = hbm_peak()
+        o_ach = rows * (2 * K_FACTORS * 2 * 4) / (o_ms * 1e-3) / 1e9
+        tol = {"mode": "ordered (FMB200_MODE_ORDERED: the reference's read/write order on w0/w/V; conflict-free "
+                       "runs of rows in parallel, bias chain by affine prefix scan; fp64 state)",
+               "dtype": "f64", "value": rows / (o_ms * 1e-3), "unit": UNIT, "ms_per_step": o_ms, "steps": o_steps,
+               "e2e": {"value": o_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": int((2 + n + n * K_FACTORS) * 8), "steps": n_e2e},
+               "gpu_launches": int(o_launches), "kernel": kernel_name(o_cfg, "ordered"), "kernel_geometry": o_cfg,
+               "roofline": {"bound": "latency (one dependency chain: one CTA on one SM)", "achieved": o_ach,
+                            "peak": peak, "unit": "GB/s", "frac": o_ach / peak,
+                            "note": "the sequential semantics leave one chain; HBM is not what bounds this mode"}}
+        if not args.no_parity:
+            tol["parity"] = parity_run(MODE_ORDERED, local_rank)
+    sampler.sample()
+    sampler.stop_flag = True
     lrn.close()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (fm_sgd_hogwild_kernel) -------------
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    # ---- roofline of the dominant kernel (the epoch kernel of the timed mode) ----------------
+    peak, peak_src = hbm_peak()
     bytes_per_example = 2 * K_FACTORS * 2 * 4  # 2*k*nnz*4
-    if world == 1:
-        kernel_ms = ms_per_step  # the step is exactly one launch of the epoch kernel
-    else:
-        kernel_ms = ms_per_step  # epoch kernel + all-reduce + scale; the kernel dominates
+    kernel_ms = ms_per_step  # N == 1: the step is exactly one launch; N > 1: + the peer exchange kernel
     achieved = rows * bytes_per_example / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "c2_epoch_dram_bytes.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    traffic, traffic_src = static_traffic("c2", rows)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_example": bytes_per_example,
-                "kernel": "fm_sgd_hogwild_kernel<G=%d,S=%d>" % (cfg["lanes_per_row"], cfg["slots"])}
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src, "algorithmic_bytes_per_example": bytes_per_example,
+                "kernel": kernel_name(cfg, "hogwild")}
+
+    parity = None
+    extra = {}
+    if world == 1:
+        if not args.no_parity:
+            parity = parity_run(MODE_HOGWILD, local_rank)
+            parity["mode"] = "hogwild (the timed mode): statistical parity only, NOT inside the 1e-5 gate; " \
+                             "see tolerance_mode for the path that is"
+        if not args.no_extras:
+            try:
+                dz = synth.movielens_1m_shaped(seed=7, zipf=1.0)
+                extra["c2_zipf"] = extra_config("C2 with Zipf(1) user/item ids (hot-feature stress)", dz, K_FACTORS, 0,
+                                                local_rank, 10, 3, flush, stream, torch, "c2_zipf")
+                del dz
+                d3 = synth.multi_field(args.c3_rows, 39, 1_000_000, 11)
+                d3.binarize_targets()
+                extra["c3"] = extra_config("C3: SGD k=64, Criteo-shaped CSR (1M features, 39 nnz/row, %d rows), "
+                                           "-task c, Hogwild" % args.c3_rows, d3, 64, 1, local_rank, 5, 3, flush,
+                                           stream, torch, "c3")
+                del d3
+            except Exception as exc:  # an extra must never cost the headline line
+                extra["error"] = repr(exc)
 
     # ---- CPU baseline on this box's host cores (N == 1 only) ------------------
     cpu = None
@@ -386,10 +549,14 @@ def run_gpu_arm(args):
                        kernel_geometry=cfg),
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": n_e2e},
+                "steps": n_e2e, "upload": "fmb200_upload_onehot_async (ids + targets; one-hot rows)"},
         "gpu_launches": int(launches),
+        "gpu_launches_whole_run": int(launches_total),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "parity": parity,
+        "tolerance_mode": tol,
+        "extra": extra,
         "timed_region_wall_s": wall,
     }
     print(json.dumps(line), flush=True)
@@ -405,6 +572,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-tolerance-mode", action="store_true")
+    ap.add_argument("--c3-rows", type=int, default=10_000_000)
     ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"])
     args = ap.parse_args()
     if args.impl == "reference":

@@ -81,9 +81,20 @@ int fmb200_upload_data_async(fmb200_ctx* ctx, int slot, uint64_t n_rows, uint64_
                              const float* target);
 /* Same, straight from the reference's AoS layout (util/fmatrix.h:34-42):
  * `rows` points at n_rows sparse_row{sparse_entry* data; uint size;} records (16 B
- * each on LP64), each entry {uint id; float value} (8 B). */
+ * each on LP64), each entry {uint id; float value} (8 B).  When the rows lie back to back in one
+ * block -- as Data::load allocates them (Data.h:238,260) -- the row array and the block are
+ * copied as they are and converted on the device (offset scan + AoS->SoA split); rows scattered
+ * over the heap are gathered on the host first. */
 int fmb200_upload_data_aos(fmb200_ctx* ctx, int slot, uint64_t n_rows, const void* rows,
                            const float* target);
+/* One-hot rows of a fixed width (every value 1.0, e.g. (user, item) pairs -- what Data::load
+ * produces for `y u:1 i:1` files): only ids[n_rows * nnz_per_row] and the targets cross PCIe
+ * (4*z + 4 bytes per row instead of 12*z + 12); row offsets and values are materialised on the
+ * device.  The _async form behaves like fmb200_upload_data_async. */
+int fmb200_upload_onehot(fmb200_ctx* ctx, int slot, uint64_t n_rows, uint32_t nnz_per_row,
+                         const uint32_t* ids, const float* target);
+int fmb200_upload_onehot_async(fmb200_ctx* ctx, int slot, uint64_t n_rows, uint32_t nnz_per_row,
+                               const uint32_t* ids, const float* target);
 int fmb200_free_data(fmb200_ctx* ctx, int slot);
 
 /* Page-locked host memory for the arrays handed to fmb200_upload_data: uploads from it
@@ -139,6 +150,10 @@ int fmb200_allreduce_mean(fmb200_ctx* ctx);
 int fmb200_peer_barrier(fmb200_ctx* ctx);
 
 /* Introspection for tests / bench */
+/* the device CSR of a slot, copied back (any pointer may be NULL): lets the tests check the
+ * layout conversions of the upload paths bit for bit */
+int fmb200_download_data(fmb200_ctx* ctx, int slot, uint64_t* n_rows, uint64_t* nnz, uint64_t* row_ptr,
+                         uint32_t* col, float* val, float* target);
 int fmb200_kernel_launches(fmb200_ctx* ctx, uint64_t* count); /* kernels launched so far */
 int fmb200_last_epoch_config(fmb200_ctx* ctx, int* lanes_per_row, int* slots, int* rows_per_tile,
                              int* grid, int* block, int* smem_bytes, int* damp);

@@ -29,6 +29,8 @@ SYMBOLS = {
     "fmb200_upload_data": (C.c_int, [_ctx, C.c_int, C.c_uint64, C.c_uint64, _u64p, _u32p, _f32p, _f32p]),
     "fmb200_upload_data_async": (C.c_int, [_ctx, C.c_int, C.c_uint64, C.c_uint64, _u64p, _u32p, _f32p, _f32p]),
     "fmb200_upload_data_aos": (C.c_int, [_ctx, C.c_int, C.c_uint64, C.c_void_p, _f32p]),
+    "fmb200_upload_onehot": (C.c_int, [_ctx, C.c_int, C.c_uint64, C.c_uint32, _u32p, _f32p]),
+    "fmb200_upload_onehot_async": (C.c_int, [_ctx, C.c_int, C.c_uint64, C.c_uint32, _u32p, _f32p]),
     "fmb200_free_data": (C.c_int, [_ctx, C.c_int]),
     "fmb200_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
     "fmb200_host_free": (C.c_int, [C.c_void_p]),
@@ -47,6 +49,7 @@ SYMBOLS = {
     "fmb200_peer_attach_local": (C.c_int, [_ctx, C.c_int, C.c_int, C.POINTER(_ctx)]),
     "fmb200_allreduce_mean": (C.c_int, [_ctx]),
     "fmb200_peer_barrier": (C.c_int, [_ctx]),
+    "fmb200_download_data": (C.c_int, [_ctx, C.c_int, _u64p, _u64p, _u64p, _u32p, _f32p, _f32p]),
     "fmb200_kernel_launches": (C.c_int, [_ctx, _u64p]),
     "fmb200_last_epoch_config": (C.c_int, [_ctx] + [_intp] * 7),
     "fmb200_set_tuning": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -35,6 +35,7 @@ CU_SOURCES = {
     "fm_predict.cu": [],
     "fm_inorder.cu": ["--fmad=false"],
     "fm_ordered.cu": [],
+    "fm_upload.cu": [],
 }
 CU_HEADERS = ["fm_device.cuh", "fm_rowgroup.cuh", "fm_hogwild_common.cuh", "fmb200_internal.h",
               "fm_inorder_wavefront.cuh", "fm_ordered.cuh"]

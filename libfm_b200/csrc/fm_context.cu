@@ -73,10 +73,9 @@ void free_slot(DataSlot& s) {
 constexpr uint64_t kRowSlack = 512 + 8;
 constexpr uint64_t kEntrySlack = 16;
 
-// Enqueue the copies + the device-side inspection of one data set on `st` and leave
-// the results in the slot's pinned flag mirror; upload_finish() collects them.
-int upload_enqueue(fmb200_ctx* c, int slot, uint64_t n_rows, uint64_t nnz, const uint64_t* row_ptr,
-                   const uint32_t* col, const float* val, const float* target, cudaStream_t st) {
+// Make `slot` ready to receive a data set of (n_rows, nnz): drain an earlier asynchronous
+// upload, (re)allocate, reset the bookkeeping.  Enqueues only the memsets of fresh buffers.
+int upload_begin(fmb200_ctx* c, int slot, uint64_t n_rows, uint64_t nnz, cudaStream_t st) {
   DataSlot& s = c->slots[slot];
   if (s.pending) {  // an earlier asynchronous upload into this slot: drain it first
     CK(cudaEventSynchronize(s.ready));
@@ -105,18 +104,20 @@ int upload_enqueue(fmb200_ctx* c, int slot, uint64_t n_rows, uint64_t nnz, const
   s.links_ready = false;
   s.n_rows = n_rows;
   s.nnz = nnz;
-  CK(cudaMemcpyAsync(s.row_ptr, row_ptr, (n_rows + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(s.target, target, n_rows * sizeof(float), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(s.col, col, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(s.val, val, nnz * sizeof(float), cudaMemcpyHostToDevice, st));
-  // Inspection runs on the device: offsets monotone and consistent, longest row, tile
-  // spans, largest column id (the reference asserts id < num_attribute per access,
-  // fm_model.h:112), and the per-feature occurrence counts used by the HOGWILD damping.
+  return 0;
+}
+
+// Inspection runs on the device: offsets monotone and consistent, longest row, tile
+// spans, largest column id (the reference asserts id < num_attribute per access,
+// fm_model.h:112), and the per-feature occurrence counts used by the HOGWILD damping.
+// Leaves the results in the slot's pinned flag mirror; upload_finish() collects them.
+int upload_inspect(fmb200_ctx* c, int slot, cudaStream_t st) {
+  DataSlot& s = c->slots[slot];
   cudaStream_t saved = c->stream;
   c->stream = st;  // the launch helpers enqueue on c->stream
   cudaError_t e1 = cudaMemsetAsync(s.d_flag, 0, 16 * sizeof(unsigned int), st);
-  cudaError_t e2 = launch_csr_inspect(c, s.row_ptr, n_rows, nnz, s.d_flag);
-  cudaError_t e3 = launch_feature_counts(c, s.col, nnz, s.feat_cnt, s.d_flag + 8, s.d_flag + 9);
+  cudaError_t e2 = launch_csr_inspect(c, s.row_ptr, s.n_rows, s.nnz, s.d_flag);
+  cudaError_t e3 = launch_feature_counts(c, s.col, s.nnz, s.feat_cnt, s.d_flag + 8, s.d_flag + 9);
   c->stream = saved;
   CK(e1);
   CK(e2);
@@ -126,6 +127,43 @@ int upload_enqueue(fmb200_ctx* c, int slot, uint64_t n_rows, uint64_t nnz, const
   s.pending = true;
   return 0;
 }
+
+// Enqueue the copies + the device-side inspection of one SoA data set on `st`.
+int upload_enqueue(fmb200_ctx* c, int slot, uint64_t n_rows, uint64_t nnz, const uint64_t* row_ptr,
+                   const uint32_t* col, const float* val, const float* target, cudaStream_t st) {
+  if (upload_begin(c, slot, n_rows, nnz, st)) return 1;
+  DataSlot& s = c->slots[slot];
+  CK(cudaMemcpyAsync(s.row_ptr, row_ptr, (n_rows + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s.target, target, n_rows * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s.col, col, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s.val, val, nnz * sizeof(float), cudaMemcpyHostToDevice, st));
+  return upload_inspect(c, slot, st);
+}
+
+// One-hot rows of fixed width z: ids [n_rows*z] and targets cross PCIe; row offsets and the
+// all-ones values are written by a kernel (fm_upload.cu).
+int upload_onehot_enqueue(fmb200_ctx* c, int slot, uint64_t n_rows, uint32_t z, const uint32_t* ids,
+                          const float* target, cudaStream_t st) {
+  const uint64_t nnz = n_rows * z;
+  if (upload_begin(c, slot, n_rows, nnz, st)) return 1;
+  DataSlot& s = c->slots[slot];
+  CK(cudaMemcpyAsync(s.target, target, n_rows * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s.col, ids, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  cudaStream_t saved = c->stream;
+  c->stream = st;
+  cudaError_t e = launch_onehot_fill(c, n_rows, z, s.row_ptr, s.val);
+  c->stream = saved;
+  CK(e);
+  return upload_inspect(c, slot, st);
+}
+
+// RAII for the temporaries of the AoS upload
+struct DevTmp {
+  void* p = nullptr;
+  ~DevTmp() {
+    if (p) cudaFree(p);
+  }
+};
 
 // The one host sync of an upload: wait for the slot's event and read the verdict.
 int upload_finish(fmb200_ctx* c, int slot) {
@@ -335,24 +373,21 @@ int fmb200_upload_data_async(fmb200_ctx* c, int slot, uint64_t n_rows, uint64_t 
   return upload_enqueue(c, slot, n_rows, nnz, row_ptr, col, val, target, c->copy_stream);
 }
 
-int fmb200_upload_data_aos(fmb200_ctx* c, int slot, uint64_t n_rows, const void* rows,
-                           const float* target) {
-  NEED_CTX(c);
-  if (slot < 0 || slot >= FMB200_MAX_SLOTS) return fail("slot %d out of range", slot);
-  if (n_rows && (!rows || !target)) return fail("null data pointer");
-  if (bind(c)) return 1;
+// reference layout, util/fmatrix.h:34-42
+struct AosEntry {
+  uint32_t id;
+  float value;
+};
+struct AosRow {
+  const AosEntry* data;
+  uint32_t size;
+};
+static_assert(sizeof(AosRow) == 16 && sizeof(AosEntry) == 8, "LP64 layout of sparse_row/sparse_entry");
+
+// rows scattered over the heap: gather them on the host (slow path)
+static int upload_aos_host_gather(fmb200_ctx* c, int slot, uint64_t n_rows, const AosRow* r,
+                                  const float* target) {
   return guarded([&]() -> int {
-    // reference layout, util/fmatrix.h:34-42
-    struct Entry {
-      uint32_t id;
-      float value;
-    };
-    struct Row {
-      const Entry* data;
-      uint32_t size;
-    };
-    static_assert(sizeof(Row) == 16 && sizeof(Entry) == 8, "LP64 layout of sparse_row/sparse_entry");
-    const Row* r = static_cast<const Row*>(rows);
     std::vector<uint64_t> rp(n_rows + 1);
     rp[0] = 0;
     for (uint64_t i = 0; i < n_rows; i++) rp[i + 1] = rp[i] + r[i].size;
@@ -360,7 +395,7 @@ int fmb200_upload_data_aos(fmb200_ctx* c, int slot, uint64_t n_rows, const void*
     std::vector<uint32_t> col(nnz ? nnz : 1);
     std::vector<float> val(nnz ? nnz : 1);
     for (uint64_t i = 0; i < n_rows; i++) {
-      const Entry* e = r[i].data;
+      const AosEntry* e = r[i].data;
       uint64_t o = rp[i];
       for (uint32_t j = 0; j < r[i].size; j++) {
         col[o + j] = e[j].id;
@@ -369,6 +404,80 @@ int fmb200_upload_data_aos(fmb200_ctx* c, int slot, uint64_t n_rows, const void*
     }
     return upload_common(c, slot, n_rows, nnz, rp.data(), col.data(), val.data(), target);
   });
+}
+
+int fmb200_upload_data_aos(fmb200_ctx* c, int slot, uint64_t n_rows, const void* rows,
+                           const float* target) {
+  NEED_CTX(c);
+  if (slot < 0 || slot >= FMB200_MAX_SLOTS) return fail("slot %d out of range", slot);
+  if (n_rows && (!rows || !target)) return fail("null data pointer");
+  if (n_rows > 0xffffffffull) return fail("row count exceeds the reference's uint range");
+  if (bind(c)) return 1;
+  const AosRow* r = static_cast<const AosRow*>(rows);
+  // The reference keeps all entries in ONE block (Data.h:238,260).  The row array crosses PCIe
+  // as it is; the device scans the sizes into row offsets and checks that every row pointer is
+  // where a contiguous block puts it.  Only then is the block itself read (8 B per entry, one
+  // copy) and split into ids / values on the device.
+  uint64_t first = 0;
+  while (first < n_rows && r[first].size == 0) first++;
+  if (first == n_rows) {  // no entries at all
+    std::vector<uint64_t> rp;
+    try {
+      rp.assign(n_rows + 1, 0);
+    } catch (const std::bad_alloc&) {
+      return fail("out of host memory");
+    }
+    uint32_t dc = 0;
+    float dv = 0.f;
+    return upload_common(c, slot, n_rows, 0, rp.data(), &dc, &dv, target);
+  }
+  const unsigned long long base = (unsigned long long)(uintptr_t)r[first].data;
+  cudaStream_t st = c->stream;
+  DevTmp d_rows, d_rp, d_scr, d_ent;
+  unsigned int* flag = c->d_flag;
+  CK(cudaMalloc(&d_rows.p, n_rows * sizeof(AosRow)));
+  CK(cudaMalloc(&d_rp.p, (n_rows + 1) * sizeof(uint64_t)));
+  CK(cudaMalloc(&d_scr.p, (aos_scan_tiles(n_rows) + 1) * sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(flag, 0, 16 * sizeof(unsigned int), st));
+  CK(cudaMemcpyAsync(d_rows.p, r, n_rows * sizeof(AosRow), cudaMemcpyHostToDevice, st));
+  CK(launch_aos_to_csr(c, d_rows.p, nullptr, n_rows, 0, base, static_cast<unsigned long long*>(d_scr.p),
+                       static_cast<uint64_t*>(d_rp.p), nullptr, nullptr, flag));
+  uint64_t nnz = 0;
+  CK(cudaMemcpyAsync(c->h_flag, flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&nnz, static_cast<uint64_t*>(d_rp.p) + n_rows, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (c->h_flag[0] & 1u) return upload_aos_host_gather(c, slot, n_rows, r, target);
+  if (upload_begin(c, slot, n_rows, nnz, st)) return 1;
+  DataSlot& s = c->slots[slot];
+  CK(cudaMalloc(&d_ent.p, (nnz ? nnz : 1) * sizeof(AosEntry)));
+  CK(cudaMemcpyAsync(d_ent.p, r[first].data, nnz * sizeof(AosEntry), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s.row_ptr, d_rp.p, (n_rows + 1) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(s.target, target, n_rows * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(launch_aos_split(c, d_ent.p, nnz, s.col, s.val));
+  if (upload_inspect(c, slot, st)) return 1;
+  return upload_finish(c, slot);  // syncs: the temporaries may be released
+}
+
+int fmb200_upload_onehot(fmb200_ctx* c, int slot, uint64_t n_rows, uint32_t nnz_per_row,
+                         const uint32_t* ids, const float* target) {
+  NEED_CTX(c);
+  if (slot < 0 || slot >= FMB200_MAX_SLOTS) return fail("slot %d out of range", slot);
+  if (n_rows && (!target || (nnz_per_row && !ids))) return fail("null data pointer");
+  if (n_rows > 0xffffffffull) return fail("row count exceeds the reference's uint range");
+  if (bind(c)) return 1;
+  if (upload_onehot_enqueue(c, slot, n_rows, nnz_per_row, ids, target, c->stream)) return 1;
+  return upload_finish(c, slot);
+}
+
+int fmb200_upload_onehot_async(fmb200_ctx* c, int slot, uint64_t n_rows, uint32_t nnz_per_row,
+                               const uint32_t* ids, const float* target) {
+  NEED_CTX(c);
+  if (slot < 0 || slot >= FMB200_MAX_SLOTS) return fail("slot %d out of range", slot);
+  if (n_rows && (!target || (nnz_per_row && !ids))) return fail("null data pointer");
+  if (n_rows > 0xffffffffull) return fail("row count exceeds the reference's uint range");
+  if (bind(c)) return 1;
+  if (c->copy_stream == nullptr) CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  return upload_onehot_enqueue(c, slot, n_rows, nnz_per_row, ids, target, c->copy_stream);
 }
 
 int fmb200_host_alloc(void** out, uint64_t bytes) {
@@ -679,6 +788,22 @@ int fmb200_last_epoch_config(fmb200_ctx* c, int* lanes_per_row, int* slots, int*
   if (block) *block = c->last_cfg.block;
   if (smem_bytes) *smem_bytes = c->last_cfg.smem;
   if (damp) *damp = c->last_cfg.damp;
+  return 0;
+}
+
+int fmb200_download_data(fmb200_ctx* c, int slot, uint64_t* n_rows, uint64_t* nnz, uint64_t* row_ptr,
+                         uint32_t* col, float* val, float* target) {
+  NEED_CTX(c);
+  if (need_slot(c, slot)) return 1;
+  if (bind(c)) return 1;
+  const DataSlot& d = c->slots[slot];
+  if (n_rows) *n_rows = d.n_rows;
+  if (nnz) *nnz = d.nnz;
+  if (row_ptr) CK(cudaMemcpyAsync(row_ptr, d.row_ptr, (d.n_rows + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+  if (col && d.nnz) CK(cudaMemcpyAsync(col, d.col, d.nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (val && d.nnz) CK(cudaMemcpyAsync(val, d.val, d.nnz * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (target && d.n_rows) CK(cudaMemcpyAsync(target, d.target, d.n_rows * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

@@ -145,6 +145,14 @@ cudaError_t launch_csr_inspect(fmb200_ctx* c, const uint64_t* rp, uint64_t n_row
 cudaError_t launch_feature_counts(fmb200_ctx* c, const uint32_t* col, uint64_t nnz, float* cnt,
                                   unsigned int* out_max_id, unsigned int* out_max);
 
+// fm_upload.cu: the reference's AoS containers -> SoA CSR on the device; one-hot materialisation
+cudaError_t launch_aos_to_csr(fmb200_ctx* c, const void* d_rows, const void* d_entries, uint64_t n_rows,
+                              uint64_t nnz, unsigned long long host_base_ptr, unsigned long long* scratch,
+                              uint64_t* row_ptr, uint32_t* col, float* val, unsigned int* flag);
+cudaError_t launch_aos_split(fmb200_ctx* c, const void* d_entries, uint64_t nnz, uint32_t* col, float* val);
+uint64_t aos_scan_tiles(uint64_t n_rows);
+cudaError_t launch_onehot_fill(fmb200_ctx* c, uint64_t n_rows, uint32_t z, uint64_t* row_ptr, float* val);
+
 // pick the sub-warp geometry for a data set: G lanes per V row (power of two
 // covering kp/4 float4 chunks), S entry slots per row group
 void pick_geometry(int kp, uint64_t n_rows, uint64_t nnz, int* G, int* S);

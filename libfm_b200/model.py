@@ -268,6 +268,43 @@ class FmLearnSgdElement:
             del self._slots[key]
         self._slots[id(data)] = (slot, data)
 
+    def upload_onehot(self, data: Data, slot: int) -> None:
+        """fmb200_upload_onehot: ids + targets only (rows of a fixed width, every value 1)."""
+        z = data.num_values // max(data.num_cases, 1)
+        if data.num_values != z * data.num_cases or not np.all(data.val == 1.0) or \
+                not np.array_equal(data.row_ptr, np.arange(data.num_cases + 1, dtype=np.uint64) * np.uint64(z)):
+            raise FmError("upload_onehot needs fixed-width rows with every value 1")
+        self._check(self.lib.fmb200_upload_onehot(self._ctx, slot, data.num_cases, z,
+                                                  _p(data.col, C.c_uint32), _p(data.target, C.c_float)))
+        for key in [k for k, (s, _) in self._slots.items() if s == slot]:
+            del self._slots[key]
+        self._slots[id(data)] = (slot, data)
+
+    def upload_aos(self, data: Data, slot: int, contiguous: bool = True) -> None:
+        """fmb200_upload_data_aos from a host image of the reference's containers
+        (sparse_row[] pointing into sparse_entry[]; util/fmatrix.h:34-42)."""
+        ent = np.empty(max(data.num_values, 1), dtype=[("id", np.uint32), ("value", np.float32)])
+        ent["id"][:data.num_values] = data.col
+        ent["value"][:data.num_values] = data.val
+        rows = np.zeros(max(data.num_cases, 1), dtype=[("data", np.uint64), ("size", np.uint32), ("pad", np.uint32)])
+        sizes = np.diff(data.row_ptr.astype(np.int64)).astype(np.uint32)
+        keep = [ent]
+        if contiguous:
+            rows["data"][:data.num_cases] = ent.ctypes.data + 8 * data.row_ptr[:-1]
+        else:  # every row in its own allocation, as a loader without the block would do
+            for r in range(data.num_cases):
+                a, b = int(data.row_ptr[r]), int(data.row_ptr[r + 1])
+                part = ent[a:b].copy()
+                keep.append(part)
+                rows["data"][r] = part.ctypes.data
+        rows["size"][:data.num_cases] = sizes
+        self._check(self.lib.fmb200_upload_data_aos(self._ctx, slot, data.num_cases,
+                                                    rows.ctypes.data_as(C.c_void_p), _p(data.target, C.c_float)))
+        del keep
+        for key in [k for k, (s, _) in self._slots.items() if s == slot]:
+            del self._slots[key]
+        self._slots[id(data)] = (slot, data)
+
     def release(self, data: Data) -> None:
         """Free the device copy of `data` and its slot."""
         ent = self._slots.pop(id(data), None)
@@ -335,6 +372,18 @@ class FmLearnSgdElement:
         n = C.c_uint64()
         self._check(self.lib.fmb200_kernel_launches(self._ctx, C.byref(n)))
         return n.value
+
+    def download(self, slot: int) -> Data:
+        """The device CSR of a slot, copied back (tests of the upload paths)."""
+        nr, nz = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.fmb200_download_data(self._ctx, slot, C.byref(nr), C.byref(nz), None, None, None, None))
+        rp = np.zeros(nr.value + 1, dtype=np.uint64)
+        col = np.zeros(max(nz.value, 1), dtype=np.uint32)
+        val = np.zeros(max(nz.value, 1), dtype=np.float32)
+        tg = np.zeros(max(nr.value, 1), dtype=np.float32)
+        self._check(self.lib.fmb200_download_data(self._ctx, slot, None, None, _p(rp, C.c_uint64),
+                                                  _p(col, C.c_uint32), _p(val, C.c_float), _p(tg, C.c_float)))
+        return Data(rp, col[:nz.value], val[:nz.value], tg[:nr.value], 0)
 
     def ordered_index(self, data: Data):
         """(link, rowdep) of fm_ordered.cu for `data` (tests)."""
