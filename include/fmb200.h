@@ -146,6 +146,13 @@ int fmb200_peer_export(fmb200_ctx* ctx, void* handle /* FMB200_IPC_HANDLE_BYTES 
 int fmb200_peer_attach_ipc(fmb200_ctx* ctx, int world, int rank, const void* handles /* world x 64 B */);
 int fmb200_peer_attach_local(fmb200_ctx* ctx, int world, int rank, fmb200_ctx* const* contexts);
 int fmb200_allreduce_mean(fmb200_ctx* ctx);
+/* Same exchange, but instead of the plain mean the replicas' epoch steps are combined as
+ * theta = theta0 + gamma_i * sum_g (theta_g - theta0), gamma_i = (1-(1-s_i)^G)/(G s_i) with s_i the
+ * relative size of one shard-epoch's step on parameter i (from the per-feature counts every upload
+ * builds): parameters a shard-epoch already converges (the bias, hot features) are averaged, barely
+ * touched ones are summed.  8 shards then follow the single-stream trajectory instead of advancing
+ * 1/8 epoch per epoch.  Call after every epoch, like fmb200_allreduce_mean. */
+int fmb200_allreduce_meanfield(fmb200_ctx* ctx);
 /* stream-ordered barrier across the attached peers (no data); used to align ranks */
 int fmb200_peer_barrier(fmb200_ctx* ctx);
 

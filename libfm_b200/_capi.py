@@ -48,6 +48,7 @@ SYMBOLS = {
     "fmb200_peer_attach_ipc": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_void_p]),
     "fmb200_peer_attach_local": (C.c_int, [_ctx, C.c_int, C.c_int, C.POINTER(_ctx)]),
     "fmb200_allreduce_mean": (C.c_int, [_ctx]),
+    "fmb200_allreduce_meanfield": (C.c_int, [_ctx]),
     "fmb200_peer_barrier": (C.c_int, [_ctx]),
     "fmb200_download_data": (C.c_int, [_ctx, C.c_int, _u64p, _u64p, _u64p, _u32p, _f32p, _f32p]),
     "fmb200_kernel_launches": (C.c_int, [_ctx, _u64p]),

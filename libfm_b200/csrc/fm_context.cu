@@ -241,8 +241,10 @@ static int create_resources(fmb200_ctx* c, int device, const cudaDeviceProp& pro
   c->p64.off_v = Params64::off_w + (((uint64_t)n_attr + 1) & ~1ull);
   c->p64.n_doubles = c->p64.off_v + (uint64_t)n_attr * num_factor + 2;
   c->comm_buf_bytes = (c->p32.n_floats * sizeof(float) + 255) & ~(size_t)255;
-  CK(cudaMalloc(&c->comm_base, c->comm_hdr + 2 * c->comm_buf_bytes));
-  CK(cudaMemsetAsync(c->comm_base, 0, c->comm_hdr + 2 * c->comm_buf_bytes, c->stream));
+  c->comm_cnt_floats = ((size_t)n_attr + 63) & ~(size_t)63;
+  const size_t comm_total = c->comm_hdr + 3 * c->comm_buf_bytes + (c->comm_cnt_floats + 1024) * sizeof(float);
+  CK(cudaMalloc(&c->comm_base, comm_total));
+  CK(cudaMemsetAsync(c->comm_base, 0, comm_total, c->stream));
   c->p32.base = reinterpret_cast<float*>(c->comm_base + c->comm_hdr);
   c->peer_base[0] = c->comm_base;
   CK(cudaMalloc(&c->p64.base, c->p64.n_doubles * sizeof(double)));
@@ -347,6 +349,7 @@ int fmb200_set_mode(fmb200_ctx* c, int mode) {
   }
   CK(cudaStreamSynchronize(c->stream));
   c->mode = mode;
+  c->peer_base_valid = false;
   return 0;
 }
 
@@ -526,6 +529,7 @@ int fmb200_set_params(fmb200_ctx* c, double w0, const double* w, const double* v
     CK(cudaMemcpyAsync(c->p64.base, h64.data(), h64.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->p32.base, h32.data(), h32.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    c->peer_base_valid = false;
     return 0;
   });
 }
@@ -581,6 +585,7 @@ int fmb200_sgd_epoch_async(fmb200_ctx* c, int slot) {
     CK(launch_sgd_inorder(c, d));
   } else {
     if (c->kp > 128) return fail("num_factor > 128 is not supported in HOGWILD mode");
+    CK(peer_before_epoch(c, d));  // multi-GPU: theta0 + shard counts for the mean-field combine
     CK(launch_sgd_hogwild(c, d));
   }
   return 0;
@@ -681,6 +686,7 @@ int fmb200_scale_params(fmb200_ctx* c, double factor) {
   if (c->mode != FMB200_MODE_HOGWILD) return fail("scale_params applies to the HOGWILD state");
   if (bind(c)) return 1;
   CK(launch_scale_p32(c, (float)factor));
+  c->peer_base_valid = false;
   return 0;
 }
 
@@ -755,6 +761,16 @@ int fmb200_allreduce_mean(fmb200_ctx* c) {
   if (c->peer_world <= 1) return 0;
   if (bind(c)) return 1;
   CK(launch_peer_mean(c));
+  return 0;
+}
+
+int fmb200_allreduce_meanfield(fmb200_ctx* c) {
+  NEED_CTX(c);
+  if (c->mode != FMB200_MODE_HOGWILD) return fail("the peer exchange applies to the HOGWILD state");
+  if (c->peer_world <= 1) return 0;
+  if (!c->peer_base_valid) return fail("no epoch has run since the state was last set: nothing to combine");
+  if (bind(c)) return 1;
+  CK(launch_peer_meanfield(c));
   return 0;
 }
 

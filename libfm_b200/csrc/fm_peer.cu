@@ -70,6 +70,160 @@ __global__ void __launch_bounds__(256) fm_peer_mean_kernel(const PeerArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Mean-field combine.  Averaging G replicas that each saw N/G rows advances the model by
+// about one G-th of an epoch (scripts/study_shard_combine.py: test RMSE after epoch 1 at
+// G = 8 is 0.86 against 0.67 for one sequential stream).  The exchange therefore forms
+//     theta = theta0 + gamma_i * sum_g (theta_g - theta0)
+// per parameter, with gamma_i the factor that makes G summed shard-steps of relative size
+// s_i equal to G such steps taken one after the other on a quadratic,
+//     gamma_i = (1 - (1 - s_i)^G) / (G s_i),   1 - s_i = exp(-u_i),   u_i = lr (h_i + reg) c_i,
+// c_i = the feature's mean occurrence count per shard, h_i = 1 for w0 / w, the mean squared
+// factor-row norm of theta0 for V -- the closed form the HOGWILD kernels use inside one GPU
+// (fm_hogwild_common.cuh: gamma_scale), applied across GPUs.  A parameter its shard-epoch has
+// already converged (the bias, hot features: s -> 1) is averaged, one that was barely touched
+// (s -> 0) is summed.
+//
+// Same one-shot structure as fm_peer_mean_kernel.  Additional state behind the two state
+// buffers of the comm block: `base` = theta0 (rewritten here with the new theta), `cnt` = this
+// rank's per-feature counts (peers read them), `part` = per-block partial sums of |V|^2 of the
+// theta this kernel writes (fixed-order reduction: every rank derives the SAME h for the next
+// exchange, so the replicas stay bit-identical).
+struct MeanFieldArgs {
+  PeerArgs p;
+  float4* base_local;              // theta0 in, theta out
+  const float* cnt[FMB200_MAX_PEERS];
+  const float* part_in;            // [n_part] partial sums of |V|^2 of theta0
+  float* part_out;                 // [gridDim.x]
+  int n_part;
+  uint64_t off_w, off_v;           // in floats
+  int ws, kp;
+  uint32_t n;
+  float lr, regw, regv, reg0;
+};
+
+__device__ __forceinline__ float mf_gamma(float u, float G) {
+  // (1 - exp(-G u)) / (G (1 - exp(-u))); -> 1 as u -> 0, -> 1/G as u -> inf
+  if (!(u > 1e-6f)) return 1.f;
+  const float a = -expm1f(-G * u), b = -expm1f(-u);
+  return a / (G * b);
+}
+
+__global__ void __launch_bounds__(256) fm_peer_meanfield_kernel(const MeanFieldArgs a) {
+  const PeerArgs& p = a.p;
+  __shared__ float s_red[256];
+  if (blockIdx.x == 0 && threadIdx.x < p.world) st_release_sys(p.flags[threadIdx.x] + p.rank, p.seq);
+  if (threadIdx.x < p.world) {
+    const unsigned int* mine = p.flags[p.rank] + threadIdx.x;
+    while ((int)(ld_acquire_sys(mine) - p.seq) < 0) {
+    }
+  }
+  __syncthreads();
+  const float G = (float)p.world;
+  // h_V: mean squared factor-row norm of theta0, from the partials of the previous exchange
+  // (fixed order: identical in every block of every rank)
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < a.n_part; i += 256) acc += a.part_in[i];
+  s_red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const float hv = a.n ? s_red[0] / (float)a.n : 0.f;
+  __syncthreads();
+  // rows per shard (header words [64, 64+world)), averaged
+  float rows = 0.f;
+  for (int q = 0; q < p.world; q++) rows += (float)__ldcv(p.flags[q] + 64 + q);
+  rows /= G;
+  const float g0 = mf_gamma(a.lr * (1.f + a.reg0) * rows, G);
+
+  float sq = 0.f;  // |V|^2 of what this thread writes
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < p.n_vec;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const float4 b4 = a.base_local[i];
+    float b[4] = {b4.x, b4.y, b4.z, b4.w};
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int q = 0; q < p.world; q++) {
+      const float4 v = __ldcv(p.cur[q] + i);
+      d[0] += v.x - b[0];
+      d[1] += v.y - b[1];
+      d[2] += v.z - b[2];
+      d[3] += v.w - b[3];
+    }
+    const uint64_t e0 = i * 4;
+    float g[4];
+    if (e0 < a.off_w) {
+      g[0] = g0;
+      g[1] = g[2] = g[3] = 0.f;
+    } else if (e0 < a.off_v) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint64_t rel = e0 + j - a.off_w;
+        const uint64_t f = rel / a.ws;
+        g[j] = 0.f;
+        if (rel % a.ws == 0 && f < a.n) {
+          float c = 0.f;
+          for (int q = 0; q < p.world; q++) c += __ldcv(a.cnt[q] + f);
+          g[j] = mf_gamma(a.lr * (1.f + a.regw) * (c / G), G);
+        }
+      }
+    } else {
+      const uint64_t f = (e0 - a.off_v) / a.kp;  // kp is a multiple of 4: one row per float4
+      float gv = 0.f;
+      if (f < a.n) {
+        float c = 0.f;
+        for (int q = 0; q < p.world; q++) c += __ldcv(a.cnt[q] + f);
+        gv = mf_gamma(a.lr * (hv + a.regv) * (c / G), G);
+      }
+      g[0] = g[1] = g[2] = g[3] = gv;
+    }
+    float4 o;
+    o.x = b[0] + g[0] * d[0];
+    o.y = b[1] + g[1] * d[1];
+    o.z = b[2] + g[2] * d[2];
+    o.w = b[3] + g[3] * d[3];
+    if (e0 >= a.off_v) sq += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+    p.next_local[i] = o;
+    a.base_local[i] = o;
+  }
+  s_red[threadIdx.x] = sq;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) a.part_out[blockIdx.x] = s_red[0];
+}
+
+// theta0 := the current state, its |V|^2 partials, this rank's counts and row count into the
+// comm block (before the FIRST epoch after an attach / set_params)
+__global__ void __launch_bounds__(256) fm_peer_capture_kernel(const float4* cur, float4* base, uint64_t n_vec,
+                                                              uint64_t off_v4, float* part_out) {
+  __shared__ float s_red[256];
+  float sq = 0.f;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_vec;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const float4 v = cur[i];
+    base[i] = v;
+    if (i >= off_v4) sq += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  s_red[threadIdx.x] = sq;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part_out[blockIdx.x] = s_red[0];
+}
+
+__global__ void fm_peer_counts_kernel(const float* __restrict__ src, float* __restrict__ dst, uint32_t n,
+                                      unsigned int* rows_word, unsigned int rows) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *rows_word = rows;
+}
+
 // Cross-GPU barrier on the stream (no data): same signal / wait through the peers' flag
 // blocks, on its own flag row and sequence so it never interferes with the averaging.
 __global__ void fm_peer_barrier_kernel(const PeerArgs a) {
@@ -92,6 +246,75 @@ cudaError_t launch_peer_barrier(fmb200_ctx* c) {
   return cudaGetLastError();
 }
 
+static int peer_grid(const fmb200_ctx* c, uint64_t n_vec) {
+  return (int)std::max<uint64_t>(1, std::min<uint64_t>((n_vec + 255) / 256, (uint64_t)c->sm_count * 2));
+}
+
+// called in front of a HOGWILD epoch when peers are attached: theta0 and the shard's counts
+cudaError_t peer_before_epoch(fmb200_ctx* c, const DataSlot& d) {
+  if (c->peer_world <= 1) return cudaSuccess;
+  const uint64_t n_vec = (c->p32.n_floats + 3) / 4;
+  unsigned char* extra = c->comm_base + c->comm_hdr + 2 * c->comm_buf_bytes;
+  float4* base = reinterpret_cast<float4*>(extra);
+  float* cnt = reinterpret_cast<float*>(extra + c->comm_buf_bytes);
+  float* part = cnt + c->comm_cnt_floats;
+  if (!c->peer_base_valid) {
+    const int grid = peer_grid(c, n_vec);
+    fm_peer_capture_kernel<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(c->p32.base), base, n_vec,
+                                                        c->p32.off_v / 4, part + (size_t)c->peer_part_cur * 512);
+    c->peer_n_part = grid;
+    c->peer_base_valid = true;
+    c->launches++;
+  }
+  if (c->n > 0 && d.feat_cnt != nullptr) {
+    const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>((c->n + 255) / 256, 64));
+    fm_peer_counts_kernel<<<grid, 256, 0, c->stream>>>(d.feat_cnt, cnt, c->n,
+                                                       reinterpret_cast<unsigned int*>(c->comm_base) + 64 + c->peer_rank,
+                                                       (unsigned int)d.n_rows);
+    c->launches++;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_peer_meanfield(fmb200_ctx* c) {
+  MeanFieldArgs a;
+  const int cur = c->peer_cur;
+  const size_t extra = c->comm_hdr + 2 * c->comm_buf_bytes;
+  for (int q = 0; q < c->peer_world; q++) {
+    a.p.flags[q] = reinterpret_cast<unsigned int*>(c->peer_base[q]);
+    a.p.cur[q] = reinterpret_cast<const float4*>(c->peer_base[q] + c->comm_hdr + (size_t)cur * c->comm_buf_bytes);
+    a.cnt[q] = reinterpret_cast<const float*>(c->peer_base[q] + extra + c->comm_buf_bytes);
+  }
+  a.p.next_local = reinterpret_cast<float4*>(c->comm_base + c->comm_hdr + (size_t)(cur ^ 1) * c->comm_buf_bytes);
+  a.p.world = c->peer_world;
+  a.p.rank = c->peer_rank;
+  a.p.seq = ++c->peer_seq;
+  a.p.n_vec = (c->p32.n_floats + 3) / 4;
+  a.p.inv_world = 1.f / (float)c->peer_world;
+  a.base_local = reinterpret_cast<float4*>(c->comm_base + extra);
+  float* part = reinterpret_cast<float*>(c->comm_base + extra + c->comm_buf_bytes) + c->comm_cnt_floats;
+  a.part_in = part + (size_t)c->peer_part_cur * 512;
+  a.part_out = part + (size_t)(c->peer_part_cur ^ 1) * 512;
+  a.n_part = c->peer_n_part;
+  a.off_w = c->p32.off_w;
+  a.off_v = c->p32.off_v;
+  a.ws = c->p32.ws;
+  a.kp = c->kp;
+  a.n = c->n;
+  a.lr = (float)c->hp.lr;
+  a.reg0 = (float)c->hp.reg0;
+  a.regw = (float)c->hp.regw;
+  a.regv = (float)c->hp.regv;
+  const int grid = peer_grid(c, a.p.n_vec);
+  fm_peer_meanfield_kernel<<<grid, 256, 0, c->stream>>>(a);
+  c->launches++;
+  c->peer_n_part = grid;
+  c->peer_part_cur ^= 1;
+  c->peer_cur = cur ^ 1;
+  c->p32.base = reinterpret_cast<float*>(c->comm_base + c->comm_hdr + (size_t)c->peer_cur * c->comm_buf_bytes);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_peer_mean(fmb200_ctx* c) {
   PeerArgs a;
   const int cur = c->peer_cur;
@@ -110,6 +333,7 @@ cudaError_t launch_peer_mean(fmb200_ctx* c) {
   c->launches++;
   c->peer_cur = cur ^ 1;
   c->p32.base = reinterpret_cast<float*>(c->comm_base + c->comm_hdr + (size_t)c->peer_cur * c->comm_buf_bytes);
+  c->peer_base_valid = false;  // theta0 of the mean-field combine no longer matches
   return cudaGetLastError();
 }
 

@@ -106,6 +106,10 @@ struct fmb200_ctx {
   // peer-memory parameter averaging (fm_peer.cu).  comm block = [flags | buf0 | buf1]
   unsigned char* comm_base = nullptr;
   size_t comm_hdr = 1024, comm_buf_bytes = 0;
+  // behind the two state buffers: theta0 (comm_buf_bytes) | counts (comm_cnt_floats) | |V|^2 partials (2 x 512)
+  size_t comm_cnt_floats = 0;
+  bool peer_base_valid = false;  // theta0 holds the state the running epoch started from
+  int peer_part_cur = 0, peer_n_part = 0;
   unsigned char* peer_base[FMB200_MAX_PEERS] = {nullptr};
   bool peer_ipc[FMB200_MAX_PEERS] = {false};
   int peer_world = 1, peer_rank = 0, peer_cur = 0;
@@ -138,6 +142,9 @@ cudaError_t launch_scale_p32(fmb200_ctx* c, float factor);
 // fm_peer.cu: one-shot all-reduce (mean) of the packed fp32 state over peer memory
 cudaError_t launch_peer_mean(fmb200_ctx* c);
 cudaError_t launch_peer_barrier(fmb200_ctx* c);
+// mean-field combine theta = theta0 + gamma_i * sum_g (theta_g - theta0) (see fm_peer.cu)
+cudaError_t launch_peer_meanfield(fmb200_ctx* c);
+cudaError_t peer_before_epoch(fmb200_ctx* c, const DataSlot& d);
 // device-side structural check of row offsets (see fm_predict.cu)
 cudaError_t launch_csr_inspect(fmb200_ctx* c, const uint64_t* rp, uint64_t n_rows, uint64_t nnz,
                                unsigned int* out8);

@@ -399,3 +399,85 @@ def test_launch_geometry_matrix(k, maxnnz, built_lib):
         np.testing.assert_allclose(l.fm.w, p.w, atol=tol, err_msg=str((ctas, rows, threads, variant)))
         np.testing.assert_allclose(l.fm.v, p.v, atol=tol, err_msg=str((ctas, rows, threads, variant)))
         l.close()
+
+
+def _mf_gamma(u, G):
+    u = np.asarray(u, dtype=np.float64)
+    out = np.ones_like(u)
+    m = u > 1e-6
+    out[m] = -np.expm1(-G * u[m]) / (G * -np.expm1(-u[m]))
+    return out
+
+
+def test_peer_meanfield_two_contexts(built_lib):
+    """fm_peer.cu mean-field combine: theta = theta0 + gamma_i * sum_g (theta_g - theta0).  Two replicas
+    (two contexts, one device) train one epoch on their own shard from a common theta0, then combine:
+    both end bit-identical, equal to a numpy restatement of the rule, and -- over a few epochs -- closer
+    to the single-stream oracle than plain averaging is."""
+    import ctypes as C
+    full = synth.two_field(120_000, 1500, 1000, seed=5, planted_k=4)
+    te = synth.two_field(20_000, 1500, 1000, seed=6, planted_k=4)
+    n, k, lr, G = full.num_feature, 8, 0.01, 2
+    half = full.num_cases // 2
+    shards = [full.rows(0, half), full.rows(half, full.num_cases)]
+    cfg = _cfg(n, k, lr=lr, mn=full.min_target, mx=full.max_target)
+    init = (0.0, np.zeros(n), _rand_init(n, k, 7)[2])
+
+    def pair():
+        ls = [make_learner(cfg, init, mode=MODE_HOGWILD) for _ in range(G)]
+        arr = (C.c_void_p * G)(*[l._ctx for l in ls])
+        for rank, l in enumerate(ls):
+            assert l.lib.fmb200_peer_attach_local(l._ctx, G, rank, arr) == 0, l.lib.fmb200_last_error()
+        return ls
+
+    def exchange(ls, fn):
+        for l in ls:
+            assert getattr(l.lib, fn)(l._ctx) == 0, l.lib.fmb200_last_error()
+        for l in ls:
+            assert l.lib.fmb200_sync(l._ctx) == 0
+
+    # --- one exchange against the numpy restatement ---
+    ls = pair()
+    for l, d in zip(ls, shards):
+        l.sgd_epoch(d)
+        l.pull_params()
+    th = [(np.float32(l.fm.w0), l.fm.w.astype(np.float32), l.fm.v.astype(np.float32)) for l in ls]
+    w0_0, w_0, v_0 = np.float32(init[0]), init[1].astype(np.float32), init[2].astype(np.float32)
+    cnt = np.mean([np.bincount(d.col, minlength=n) for d in shards], axis=0)
+    rows = np.mean([d.num_cases for d in shards])
+    hv = float(np.sum(v_0.astype(np.float64) ** 2) / n)
+    g0 = _mf_gamma(np.array([lr * rows]), G)[0]
+    gw, gv = _mf_gamma(lr * cnt, G), _mf_gamma(lr * hv * cnt, G)
+    want_w0 = w0_0 + g0 * sum(t[0] - w0_0 for t in th)
+    want_w = w_0 + gw * sum(t[1] - w_0 for t in th)
+    want_v = v_0 + gv[None, :] * sum(t[2] - v_0 for t in th)
+    exchange(ls, "fmb200_allreduce_meanfield")
+    for l in ls:
+        l.pull_params()
+    a, b = ls
+    assert a.fm.w0 == b.fm.w0 and np.array_equal(a.fm.w, b.fm.w) and np.array_equal(a.fm.v, b.fm.v)
+    assert abs(a.fm.w0 - want_w0) < 1e-5
+    np.testing.assert_allclose(a.fm.w, want_w, atol=2e-6)
+    np.testing.assert_allclose(a.fm.v, want_v, atol=2e-6)
+    for l in ls:
+        l.close()
+
+    # --- trajectories: single stream (oracle) vs mean-field vs plain averaging, 3 epochs ---
+    p = _port(cfg, init)
+    rmse = {}
+    for name, fn in (("meanfield", "fmb200_allreduce_meanfield"), ("average", "fmb200_allreduce_mean")):
+        ls = pair()
+        for _ in range(3):
+            for l, d in zip(ls, shards):
+                l.sgd_epoch(d)
+            exchange(ls, fn)
+        rmse[name] = ls[0].evaluate(te)
+        for l in ls:
+            l.close()
+    for _ in range(3):
+        p.sgd_epoch(full, 0, lr, cfg["min_target"], cfg["max_target"])
+    seq = p.metric(te, 0, cfg["min_target"], cfg["max_target"])
+    print("\n[peer combine, 2 shards, 3 epochs] held-out RMSE: sequential %.4f  meanfield %.4f  average %.4f" %
+          (seq, rmse["meanfield"], rmse["average"]))
+    assert abs(rmse["meanfield"] - seq) < abs(rmse["average"] - seq)
+    assert abs(rmse["meanfield"] - seq) < 0.02
