@@ -351,10 +351,13 @@ def run_gpu_arm(args):
         if collective == "nccl":
             params = torch.as_tensor(_DevBuf(ptr, n_floats), device=torch.device("cuda", local_rank))
 
+    # the combine rule of the peer exchange: mean-field weighted delta sum (default) or plain mean
+    peer_exchange = lib.fmb200_allreduce_meanfield if args.exchange == "meanfield" else lib.fmb200_allreduce_mean
+
     def step():
         rc = lib.fmb200_sgd_epoch_async(ctx, 0)
         if rc == 0 and collective == "p2p":
-            rc = lib.fmb200_allreduce_mean(ctx)
+            rc = peer_exchange(ctx)
         elif rc == 0 and collective == "nccl":
             dist.all_reduce(params)  # sum over ranks on the library's stream
             rc = lib.fmb200_scale_params(ctx, 1.0 / world)
@@ -434,7 +437,7 @@ def run_gpu_arm(args):
         upload_async(cur_slot[1])                 # next step's inputs: host -> device
         rc = lib.fmb200_sgd_epoch_async(ctx, cur_slot[0])   # waits for this slot's upload
         if exchange and rc == 0 and collective == "p2p":
-            rc = lib.fmb200_allreduce_mean(ctx)
+            rc = peer_exchange(ctx)
         elif exchange and rc == 0 and collective == "nccl":
             with torch.cuda.stream(stream):
                 dist.all_reduce(params)
@@ -545,7 +548,8 @@ def run_gpu_arm(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict(WORKLOAD, parallelism="row-sharded dp%d, per-epoch all-reduce of w0|w|V (%s)" % (
-            world, {"p2p": "one-shot kernel over NVLink peer memory", "nccl": "NCCL", "none": "single GPU"}[collective]),
+            world, {"p2p": "one-shot %s kernel over NVLink peer memory" % args.exchange, "nccl": "NCCL mean",
+                    "none": "single GPU"}[collective]),
                        kernel_geometry=cfg),
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -577,6 +581,7 @@ def main():
     ap.add_argument("--no-tolerance-mode", action="store_true")
     ap.add_argument("--c3-rows", type=int, default=10_000_000)
     ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"])
+    ap.add_argument("--exchange", default="meanfield", choices=["meanfield", "mean"])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -128,6 +128,14 @@ int fmb200_evaluate(fmb200_ctx* ctx, int slot, double* sum_sq_err, double* sum_a
  * returns the raw score of fm_model::predict (fm_model.h:105-127). */
 int fmb200_predict(fmb200_ctx* ctx, int slot, int transform, double* out);
 
+/* Replaces: fm_learn_mcmc::predict_data_and_write_to_eterms (fm_learn_mcmc.h:148-378, data sets
+ * without relations) -- the full re-prediction of a data set the MCMC / ALS learner runs on train
+ * and test once per iteration (fm_learn_mcmc_simultaneous.h:69,122).  e_out[c] receives the e-term
+ * of case c, accumulated in the learner's own order (feature-major through the transposed data),
+ * bit-identical to the reference; the caller subtracts the targets and keeps the Gibbs draws.
+ * Uses the fp64 state (INORDER / ORDERED mode): fmb200_set_params after every draw_all(). */
+int fmb200_mcmc_eterms(fmb200_ctx* ctx, int slot, double* e_out);
+
 /* Multi-GPU plumbing (row sharding + one all-reduce of w0|w|V per epoch; the
  * reference has no equivalent).  The HOGWILD state is one packed fp32 device
  * buffer [w0, pad x3 | w (strided) | V[n][kp]]; the caller all-reduces it

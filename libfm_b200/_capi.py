@@ -41,6 +41,7 @@ SYMBOLS = {
     "fmb200_sync": (C.c_int, [_ctx]),
     "fmb200_evaluate": (C.c_int, [_ctx, C.c_int, _f64p, _f64p, _u64p]),
     "fmb200_predict": (C.c_int, [_ctx, C.c_int, C.c_int, _f64p]),
+    "fmb200_mcmc_eterms": (C.c_int, [_ctx, C.c_int, _f64p]),
     "fmb200_params_device": (C.c_int, [_ctx, C.POINTER(C.c_void_p), _u64p]),
     "fmb200_scale_params": (C.c_int, [_ctx, C.c_double]),
     "fmb200_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),

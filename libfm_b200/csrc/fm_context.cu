@@ -673,6 +673,28 @@ int fmb200_predict(fmb200_ctx* c, int slot, int transform, double* out) {
   return 0;
 }
 
+int fmb200_mcmc_eterms(fmb200_ctx* c, int slot, double* e_out) {
+  NEED_CTX(c);
+  if (need_slot(c, slot)) return 1;
+  if (bind(c)) return 1;
+  if (c->mode == FMB200_MODE_HOGWILD)
+    return fail("e-terms are computed from the fp64 state: set INORDER or ORDERED mode first");
+  const DataSlot& d = c->slots[slot];
+  if (d.n_rows == 0) return 0;
+  if (!e_out) return fail("null output pointer");
+  if (c->pred_cap < d.n_rows) {
+    if (c->d_pred) cudaFree(c->d_pred);
+    c->d_pred = nullptr;
+    c->pred_cap = 0;
+    CK(cudaMalloc(&c->d_pred, d.n_rows * sizeof(double)));
+    c->pred_cap = d.n_rows;
+  }
+  CK(launch_mcmc_eterms(c, d, c->d_pred));
+  CK(cudaMemcpyAsync(e_out, c->d_pred, d.n_rows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 int fmb200_params_device(fmb200_ctx* c, void** device_ptr, uint64_t* n_floats) {
   NEED_CTX(c);
   if (c->mode != FMB200_MODE_HOGWILD) return fail("packed fp32 state is live only in HOGWILD mode");

@@ -249,6 +249,113 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// MCMC / ALS e-term pass (reference libfm/src/fm_learn_mcmc.h:148-378, no relations): the
+// learner re-predicts every case once per iteration through the TRANSPOSED copy of the data, so
+// each case accumulates its terms in ascending feature id (ties in row order) and in a different
+// association than fm_model::predict:
+//   e = sum_f 0.5 q_f^2 ;  q = sum_f sum_i -0.5 v_if^2 x_i^2  (+ sum_i w_i x_i) ;  e = (e + q) + w0
+// One thread per case, every operation in that order (this TU is compiled with --fmad=false):
+// bit-identical e-terms.  Rows whose ids are not ascending are visited through a per-thread
+// order array (rows of <= ET_LOCAL entries) or by repeated selection (longer rows).
+constexpr int ET_LOCAL = 64;
+
+struct RowOrder {
+  const uint32_t* c;
+  uint32_t size;
+  bool sorted;
+  unsigned short ord[ET_LOCAL];
+  __device__ __forceinline__ void init(const uint32_t* col, uint32_t n) {
+    c = col;
+    size = n;
+    sorted = true;
+    for (uint32_t i = 1; i < n; i++)
+      if (col[i] < col[i - 1]) sorted = false;
+    if (!sorted && n <= (uint32_t)ET_LOCAL) {  // stable insertion sort by id
+      for (uint32_t i = 0; i < n; i++) ord[i] = (unsigned short)i;
+      for (uint32_t i = 1; i < n; i++) {
+        const unsigned short o = ord[i];
+        uint32_t j = i;
+        while (j > 0 && col[ord[j - 1]] > col[o]) {
+          ord[j] = ord[j - 1];
+          j--;
+        }
+        ord[j] = o;
+      }
+    }
+  }
+  // position of the i-th entry in (id, position) order; `prev` = position of the (i-1)-th
+  __device__ __forceinline__ uint32_t at(uint32_t i, uint32_t prev) const {
+    if (sorted) return i;
+    if (size <= (uint32_t)ET_LOCAL) return ord[i];
+    // selection: the smallest (id, position) greater than (c[prev], prev)
+    uint32_t best = 0xffffffffu;
+    for (uint32_t j = 0; j < size; j++) {
+      const bool after = (i == 0) || c[j] > c[prev] || (c[j] == c[prev] && j > prev);
+      if (!after) continue;
+      if (best == 0xffffffffu || c[j] < c[best]) best = j;
+    }
+    return best;
+  }
+};
+
+__global__ void __launch_bounds__(128)
+    fm_eterm64_kernel(Params64 p, int k, int use_w0, int use_w, uint64_t n_rows,
+                      const uint64_t* __restrict__ row_ptr, const uint32_t* __restrict__ col,
+                      const float* __restrict__ val, double* __restrict__ e_out) {
+  const double* w = p.w();
+  const double* v = p.v();
+  const double w0 = *p.w0();
+  for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n_rows;
+       r += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t beg = row_ptr[r];
+    const uint32_t size = (uint32_t)(row_ptr[r + 1] - beg);
+    const uint32_t* c = col + beg;
+    const float* x = val + beg;
+    RowOrder o;
+    o.init(c, size);
+    double e = 0.0, q = 0.0;
+    for (int f = 0; f < k; f++) {  // fm_learn_mcmc.h:172-252
+      q = 0.0;
+      uint32_t pos = 0;
+      for (uint32_t i = 0; i < size; i++) {
+        pos = o.at(i, pos);
+        q += v[(size_t)c[pos] * k + f] * (double)x[pos];
+      }
+      e += 0.5 * q * q;
+    }
+    q = 0.0;
+    for (int f = 0; f < k; f++) {  // :255-306
+      uint32_t pos = 0;
+      for (uint32_t i = 0; i < size; i++) {
+        pos = o.at(i, pos);
+        const double vif = v[(size_t)c[pos] * k + f];
+        const float xi = x[pos];
+        q -= 0.5 * vif * vif * xi * xi;  // (((0.5*v)*v)*x)*x, x promoted to double per factor
+      }
+    }
+    if (use_w) {  // :309-346
+      uint32_t pos = 0;
+      for (uint32_t i = 0; i < size; i++) {
+        pos = o.at(i, pos);
+        q += w[c[pos]] * (double)x[pos];
+      }
+    }
+    e = e + q;  // :350-362
+    if (use_w0) e += w0;
+    e_out[r] = e;
+  }
+}
+
+cudaError_t launch_mcmc_eterms(fmb200_ctx* c, const DataSlot& d, double* e_out) {
+  if (d.n_rows == 0) return cudaSuccess;
+  const uint64_t blocks = (d.n_rows + 127) / 128;
+  const int grid = (int)(blocks < (uint64_t)c->sm_count * 16 ? blocks : (uint64_t)c->sm_count * 16);
+  fm_eterm64_kernel<<<grid, 128, 0, c->stream>>>(c->p64, c->k, c->k0, c->k1, d.n_rows, d.row_ptr, d.col, d.val,
+                                                 e_out);
+  c->launches++;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_sgd_inorder(fmb200_ctx* c, const DataSlot& d) {
   if (c->k > 32 * KF_MAX) return cudaErrorInvalidValue;
   // Opt-in (fmb200_set_tuning variant 4) until it has been measured on the device.

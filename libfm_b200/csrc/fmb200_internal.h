@@ -130,6 +130,8 @@ cudaError_t launch_predict64(fmb200_ctx* c, const DataSlot& d, int transform, do
 // affine scan).  *handled = false: shape not eligible, nothing launched (caller uses launch_sgd_inorder)
 cudaError_t launch_sgd_ordered(fmb200_ctx* c, DataSlot& d, bool* handled);
 cudaError_t build_ordered_links(fmb200_ctx* c, DataSlot& d);
+// fm_inorder.cu: the MCMC / ALS e-term pass (fm_learn_mcmc.h:148-378), bit-identical accumulation
+cudaError_t launch_mcmc_eterms(fmb200_ctx* c, const DataSlot& d, double* e_out);
 // fm_hogwild.cu: throughput epoch
 cudaError_t launch_sgd_hogwild(fmb200_ctx* c, const DataSlot& d);
 // fm_predict.cu: fp32 scores / metrics with sub-warp row groups

@@ -344,6 +344,12 @@ class FmLearnSgdElement:
                                             _p(out, C.c_double)))
         return out
 
+    def mcmc_eterms(self, data: Data) -> np.ndarray:
+        """fm_learn_mcmc::predict_data_and_write_to_eterms (fm_learn_mcmc.h:148-378) for one data set."""
+        out = np.empty(data.num_cases, dtype=np.float64)
+        self._check(self.lib.fmb200_mcmc_eterms(self._ctx, self._slot_of(data), _p(out, C.c_double)))
+        return out
+
     def learn(self, train: Data, test: Data, log=None):
         """fm_learn_sgd_element::learn (fm_learn_sgd_element.h:48-78)."""
         self.push_hparams()

@@ -96,6 +96,15 @@ class Port:
                              _p(data.col, C.c_uint32), _p(data.val, C.c_float), _p(out, C.c_double))
         return out
 
+    def mcmc_eterms(self, data):
+        """fm_learn_mcmc::predict_data_and_write_to_eterms (fm_learn_mcmc.h:148-378), one data set."""
+        out = np.empty(data.num_cases, dtype=np.float64)
+        self.lib.fmo_mcmc_eterms(C.c_uint32(self.n), self.k, self.k0, self.k1, self.w0,
+                                 _p(self.w, C.c_double), _p(self.v, C.c_double),
+                                 C.c_uint64(data.num_cases), _p(data.row_ptr, C.c_uint64),
+                                 _p(data.col, C.c_uint32), _p(data.val, C.c_float), _p(out, C.c_double))
+        return out
+
     def predict_row(self, col, val):
         col = np.ascontiguousarray(col, dtype=np.uint32)
         val = np.ascontiguousarray(val, dtype=np.float32)
@@ -183,6 +192,14 @@ class Ref:
         out = np.empty(d.num_cases)
         rc = self.lib().ref_predict(self.h, self.data(d), task, C.c_double(min_target),
                                     C.c_double(max_target), _p(out, C.c_double))
+        if rc != 0:
+            raise RuntimeError(self.lib().ref_last_error().decode())
+        return out
+
+    def mcmc_eterms(self, d):
+        """the reference's own e-term pass (through its transposed copy of the data)"""
+        out = np.empty(d.num_cases)
+        rc = self.lib().ref_mcmc_eterms(self.h, self.data(d), _p(out, C.c_double))
         if rc != 0:
             raise RuntimeError(self.lib().ref_last_error().decode())
         return out

@@ -201,3 +201,62 @@ void fmo_v_to_device_layout(uint32_t n, int k, int kp, const double* v, float* o
   for (uint32_t i = 0; i < n; i++)
     for (int f = 0; f < kp; f++) out[(size_t)i * kp + f] = f < k ? (float)v[(size_t)f * n + i] : 0.f;
 }
+
+/* ---- MCMC / ALS e-term pass: libfm/src/fm_learn_mcmc.h:148-378 (no relations) -------------
+ * The learner re-predicts every case once per iteration THROUGH THE TRANSPOSED COPY of the data
+ * (Data::create_data_t, Data.h:292-337: feature i lists its cases in ascending case order, and a
+ * case's own entries in their row order).  Seen from one case c, the terms therefore arrive in
+ * ascending feature id, ties in row order -- not in the row's stored order:
+ *   (1) :172-252  for f: q = sum_i v_if x_i ; e += 0.5 q q
+ *   (2) :255-306  for f: for i: q -= 0.5 v_if v_if x_i x_i          (one running q over all f)
+ *   (3) :309-346  for i: q += w_i x_i                               (if k1)
+ *       :350-362  e = e + q ; if k0: e += w0
+ * `order` (scratch, max_row_nnz entries) receives the row's entries sorted by (id, position). */
+static void sort_row(uint32_t size, const uint32_t* col, uint32_t* order) {
+  for (uint32_t i = 0; i < size; i++) order[i] = i;
+  for (uint32_t i = 1; i < size; i++) { /* stable insertion sort by id */
+    uint32_t o = order[i];
+    uint32_t j = i;
+    while (j > 0 && col[order[j - 1]] > col[o]) {
+      order[j] = order[j - 1];
+      j--;
+    }
+    order[j] = o;
+  }
+}
+
+void fmo_mcmc_eterms(uint32_t n, int k, int k0, int k1, double w0, const double* w, const double* v,
+                     uint64_t n_rows, const uint64_t* row_ptr, const uint32_t* col, const float* val,
+                     double* e_out) {
+  uint32_t max_size = 1;
+  for (uint64_t r = 0; r < n_rows; r++) {
+    uint64_t s = row_ptr[r + 1] - row_ptr[r];
+    if (s > max_size) max_size = (uint32_t)s;
+  }
+  uint32_t* order = (uint32_t*)malloc(sizeof(uint32_t) * max_size);
+  for (uint64_t r = 0; r < n_rows; r++) {
+    const uint32_t size = (uint32_t)(row_ptr[r + 1] - row_ptr[r]);
+    const uint32_t* c = col + row_ptr[r];
+    const float* x = val + row_ptr[r];
+    sort_row(size, c, order);
+    double e = 0.0, q = 0.0;
+    for (int f = 0; f < k; f++) {
+      q = 0.0;
+      for (uint32_t i = 0; i < size; i++) q += v[(size_t)f * n + c[order[i]]] * x[order[i]];
+      e += 0.5 * q * q;
+    }
+    q = 0.0;
+    for (int f = 0; f < k; f++)
+      for (uint32_t i = 0; i < size; i++) {
+        const double vif = v[(size_t)f * n + c[order[i]]];
+        const float xi = x[order[i]];
+        q -= 0.5 * vif * vif * xi * xi;
+      }
+    if (k1)
+      for (uint32_t i = 0; i < size; i++) q += w[c[order[i]]] * x[order[i]];
+    e = e + q;
+    if (k0) e += w0;
+    e_out[r] = e;
+  }
+  free(order);
+}

@@ -17,6 +17,8 @@
 //   fm_learn_sgd::predict                    libfm/src/fm_learn_sgd.h:76-90
 //   Data::load                               libfm/src/Data.h:113-290
 //   fm_model::saveModel / loadModel          fm_core/fm_model.h:132-190
+//   fm_learn_mcmc::predict_data_and_write_to_eterms  libfm/src/fm_learn_mcmc.h:148-378
+//   Data::create_data_t                      libfm/src/Data.h:292-337
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
@@ -35,6 +37,7 @@
 #include "libfm/src/fm_learn.h"
 #include "libfm/src/fm_learn_sgd.h"
 #include "libfm/src/fm_learn_sgd_element.h"
+#include "libfm/src/fm_learn_mcmc_simultaneous.h"
 
 namespace {
 
@@ -88,11 +91,47 @@ void setup_learner(fm_learn_sgd_element& l, RefFm* m, int task, double lr, int n
   if (log != NULL) log->init();
 }
 
+// Data::create_data_t is protected: reached through a derived view of the same object
+struct DataProbe : public Data {
+  DataProbe() : Data(0, true, false) {}
+  void make_t() { create_data_t(); }
+};
+
+// the e-term pass is a protected member: a derived probe exposes it (nothing is modified)
+struct McmcProbe : public fm_learn_mcmc_simultaneous {
+  void eterms(DVector<Data*>& d, DVector<e_q_term*>& c) { predict_data_and_write_to_eterms(d, c); }
+};
+
 }  // namespace
 
 extern "C" {
 
 const char* ref_last_error() { return g_err; }
+
+// fm_learn_mcmc::predict_data_and_write_to_eterms on one data set (no relations): e_out[c] is the
+// e-term = the model's score of case c, accumulated feature-major through the transposed copy
+// exactly as the MCMC/ALS learner does once per iteration (fm_learn_mcmc_simultaneous.h:69,122).
+int ref_mcmc_eterms(void* fm_h, void* data_h, double* e_out) {
+  RefFm* m = (RefFm*)fm_h;
+  RefData* r = (RefData*)data_h;
+  return guarded([&]() {
+    CoutMute mute;
+    if (r->d->data_t == NULL) static_cast<DataProbe*>(r->d)->make_t();
+    McmcProbe l;
+    l.fm = &m->fm;
+    l.meta = m->meta;
+    l.task = 0;
+    l.log = NULL;
+    DVector<Data*> main_data(1);
+    DVector<e_q_term*> main_cache(1);
+    e_q_term* cache = new e_q_term[r->d->num_cases > 0 ? r->d->num_cases : 1];
+    main_data(0) = r->d;
+    main_cache(0) = cache;
+    l.eterms(main_data, main_cache);
+    for (uint c = 0; c < r->d->num_cases; c++) e_out[c] = cache[c].e;
+    delete[] cache;
+  });
+}
 
 // srand(seed) then fm_model::init(): the exact draw order of libfm.cpp:115-116,245-257
 void* ref_fm_create(uint32_t n_attr, int k, int k0, int k1, double init_mean, double init_stdev,

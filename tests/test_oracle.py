@@ -154,3 +154,36 @@ def test_wavefront_schedule_refuses_ineligible_shapes():
     assert p.sgd_epoch_wavefront(tr, 0, 0.01, 1.0, 5.0) == 0
     q = Port(100, 16)
     assert q.sgd_epoch_wavefront(synth.two_field(100, 50, 50, seed=1), 0, 0.01, 1.0, 5.0) == 0
+
+
+@pytest.mark.parametrize("case", ["ragged_unsorted_dups", "two_field", "no_linear", "k0_only"])
+def test_mcmc_eterm_port_is_bit_identical_to_reference(case):
+    """oracle/fm_oracle.c::fmo_mcmc_eterms against the reference's own e-term pass
+    (fm_learn_mcmc::predict_data_and_write_to_eterms, run through its transposed copy of the data)."""
+    from oracle import Ref, have_ref
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    k, k0, k1 = 6, 1, 1
+    if case == "ragged_unsorted_dups":
+        d = synth.ragged(4000, 300, 11, seed=31)   # unsorted ids, repeated ids inside rows, empty rows
+    elif case == "two_field":
+        d = synth.two_field(6000, 400, 300, seed=32)
+        k = 16
+    elif case == "no_linear":
+        d = synth.ragged(2000, 200, 6, seed=33)
+        k1 = 0
+    else:
+        d = synth.ragged(2000, 200, 6, seed=34)
+        k = 0
+    n = d.num_feature
+    ref = Ref(n, k, k0, k1, seed=42, init_stdev=0.1)
+    _, _, v = ref.get_params()
+    r = np.random.default_rng(5)
+    w0, w = 0.25, r.standard_normal(n) * 0.1
+    ref.set_params(w0, w, v)
+    p = Port(n, k, k0, k1)
+    p.set_params(w0, w, v)
+    got, want = p.mcmc_eterms(d), ref.mcmc_eterms(d)
+    assert np.array_equal(got, want)
+    # same quantity as fm_model::predict, different association: equal to rounding only
+    assert np.max(np.abs(got - p.predict(d, 0, 0, 0, transform=False))) < 1e-12
