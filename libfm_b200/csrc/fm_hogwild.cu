@@ -143,6 +143,10 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, (R * U <= 4 ? 3 : (R > 20 ? 1 
     const uint64_t row0 = tile * (uint64_t)TR;
     const int rows_here = (int)min((uint64_t)TR, a.n_rows - row0);
     const uint64_t ab = rp[0] & ~3ull;
+    if (a.global_entries) {  // rows longer than the ring can stage: entries straight from global
+      ids = a.col + ab;
+      xs = a.val + ab;
+    }
 
     float msum = 0.f, hsum = 0.f;
     float w0 = 0.f;
@@ -378,6 +382,7 @@ static HogwildArgs make_args(fmb200_ctx* c, const DataSlot& d, uint64_t n_tiles,
   a.w0_conc = 1.f;
   a.hot_thr = 3.0e38f;
   a.sched = c->d_sched;
+  a.global_entries = 0;
   return a;
 }
 
@@ -465,16 +470,22 @@ cudaError_t launch_sgd_hogwild(fmb200_ctx* c, const DataSlot& d) {
     tr_idx = 0;
     while (tr_idx < 4 && (32 << (tr_idx + 1)) <= c->tune_rows_per_tile) tr_idx++;
   }
-  auto stage_bytes_for = [&](int idx) {
-    const int TR = 32 << idx;
-    const uint32_t cap = (d.tile_span[idx] + 3u) & ~3u;
-    return (uint32_t)((TR + 2) * 8 + TR * 4 + 2 * cap * 4 + 15) & ~15u;
+  auto stage_bytes_for = [&](int idx) -> uint64_t {
+    const uint64_t TR = 32ull << idx;
+    const uint64_t cap = ((uint64_t)d.tile_span[idx] + 3u) & ~3ull;
+    return ((TR + 2) * 8 + TR * 4 + 2 * cap * 4 + 15) & ~15ull;
   };
-  while (tr_idx > 0 && HW_HDR_BYTES + HW_NSTAGE * (int)stage_bytes_for(tr_idx) > budget) tr_idx--;
+  while (tr_idx > 0 && (uint64_t)HW_HDR_BYTES + HW_NSTAGE * stage_bytes_for(tr_idx) > (uint64_t)budget) tr_idx--;
+  // Not even 32 rows fit (rows of hundreds of entries: text / dense libsvm data): stage only the
+  // row offsets and targets and let the lanes read ids / values from global memory.  The
+  // reference trains on any row length; so does this path, at a lower rate.
+  const bool global_entries =
+      (uint64_t)HW_HDR_BYTES + (uint64_t)HW_NSTAGE * stage_bytes_for(tr_idx) > (uint64_t)c->max_smem_optin;
+  if (global_entries) tr_idx = 1;
   const int TR = 32 << tr_idx;
-  const uint32_t sbytes = stage_bytes_for(tr_idx);
+  const uint32_t sbytes =
+      global_entries ? (uint32_t)((TR + 2) * 8 + TR * 4 + 15) & ~15u : (uint32_t)stage_bytes_for(tr_idx);
   const int smem = HW_HDR_BYTES + HW_NSTAGE * (int)sbytes;
-  if (smem > c->max_smem_optin) return cudaErrorInvalidConfiguration;  // one row longer than smem
 
   // hot-feature damping is compiled in only when the hottest feature's expected
   // concurrency makes q = c*lr*(1+reg) non-negligible for this launch geometry
@@ -496,7 +507,8 @@ cudaError_t launch_sgd_hogwild(fmb200_ctx* c, const DataSlot& d) {
   const uint64_t n_tiles = (d.n_rows + TR - 1) / TR;
   const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)c->sm_count * per_sm);
 
-  HogwildArgs a = make_args(c, d, n_tiles, TR, (d.tile_span[tr_idx] + 3u) & ~3u, sbytes);
+  HogwildArgs a = make_args(c, d, n_tiles, TR, global_entries ? 0u : (d.tile_span[tr_idx] + 3u) & ~3u, sbytes);
+  a.global_entries = global_entries ? 1 : 0;
   a.conc_scale = (float)(std::min<double>((double)d.n_rows, (double)grid * rows_per_cta_step) /
                          (double)d.n_rows);
   a.w0_conc = (float)std::min<double>((double)d.n_rows, (double)grid * TR);

@@ -34,6 +34,8 @@ struct HogwildArgs {
   float w0_conc;          // rows in flight w.r.t. the bias (tile granularity)
   float hot_thr;          // COMBINE: occurrence count from which a feature is parked in the CTA's hot table
   unsigned int* sched;    // [0] next unclaimed tile, [1] CTAs that ran dry (both 0 between launches)
+  int global_entries;     // rows too long for the staging ring: ids / values are read from global
+                          // memory, only row offsets and targets are staged (tile_cap == 0)
 };
 
 __device__ __forceinline__ unsigned char* stage_base(unsigned char* smem, const HogwildArgs& a,
@@ -49,7 +51,7 @@ __device__ __forceinline__ void issue_tile(const HogwildArgs& a, unsigned char* 
   const uint64_t r0 = (uint64_t)tile * TR;
   const uint64_t ab = nb & ~3ull;
   const uint64_t ae = (ne + 3ull) & ~3ull;
-  const uint32_t ebytes = (uint32_t)(ae - ab) * 4u;
+  const uint32_t ebytes = a.global_entries ? 0u : (uint32_t)(ae - ab) * 4u;
   const uint32_t rp_bytes = (uint32_t)(TR + 2) * 8u;
   const uint32_t y_bytes = (uint32_t)TR * 4u;
   unsigned char* sb = stage_base(smem, a, stage);

@@ -481,3 +481,37 @@ def test_peer_meanfield_two_contexts(built_lib):
           (seq, rmse["meanfield"], rmse["average"]))
     assert abs(rmse["meanfield"] - seq) < abs(rmse["average"] - seq)
     assert abs(rmse["meanfield"] - seq) < 0.02
+
+
+def test_hogwild_rows_longer_than_the_staging_ring(built_lib):
+    """any 32-row window with more than ~9.6k non-zeros used to fail the launch
+    ('invalid configuration').  Such rows (dense libsvm / text data) now train with their ids and
+    values read from global memory; a one-row epoch still equals one reference step."""
+    r = np.random.default_rng(3)
+    n, k, per_row = 4000, 8, 1200           # 32 rows x 1200 entries = 38k entries >> the ring
+    rows = 96
+    col = np.concatenate([np.sort(r.choice(n, size=per_row, replace=False)) for _ in range(rows)]).astype(np.uint32)
+    d = Data(np.arange(rows + 1, dtype=np.uint64) * np.uint64(per_row), col,
+             (r.standard_normal(rows * per_row) * 0.05).astype(np.float32),
+             r.integers(1, 6, size=rows).astype(np.float32), n)
+    cfg = _cfg(n, k, lr=0.001, mn=1.0, mx=5.0)
+    init = _rand_init(n, k, 4)
+    l = make_learner(cfg, init, mode=MODE_HOGWILD)
+    got = l.predict(d, transform=False)
+    want = _port(cfg, init).predict(d, 0, 0, 0, transform=False)
+    assert np.max(np.abs(got - want)) < 5e-4
+    before = l.evaluate(d)
+    for _ in range(3):
+        l.sgd_epoch(d)
+    assert l.evaluate(d) < before
+    # one row, one epoch == one fm_SGD step of the reference (fp32 rounding)
+    one = d.rows(5, 6)
+    m = make_learner(cfg, init, mode=MODE_HOGWILD)
+    p = _port(cfg, init)
+    m.sgd_epoch(one)
+    p.sgd_epoch(one, 0, cfg["lr"], 1.0, 5.0)
+    m.pull_params()
+    np.testing.assert_allclose(m.fm.v, p.v, atol=2e-6)
+    np.testing.assert_allclose(m.fm.w, p.w, atol=2e-6)
+    l.close()
+    m.close()
