@@ -623,23 +623,49 @@ int fmb200_evaluate(fmb200_ctx* c, int slot, double* sum_sq_err, double* sum_abs
   if (d.n_rows > 0) {
     const int nb = metric_blocks(c, d);
     if (ensure_partials(c, nb)) return 1;
-    if (c->mode != FMB200_MODE_HOGWILD) {
-      CK(launch_predict64(c, d, 0, nullptr, c->d_partials, nb));
+    if (c->mode != FMB200_MODE_HOGWILD && c->hp.task == FMB200_TASK_REGRESSION) {
+      // fp64 modes: the reference sums err*err and |err| left to right over the rows
+      // (fm_learn.h:136-146); a tree reduction may differ in the last ulps and flip a printed
+      // digit.  The kernel writes the per-row error, the host adds them in row order.
+      if (c->pred_cap < d.n_rows) {
+        if (c->d_pred) cudaFree(c->d_pred);
+        c->d_pred = nullptr;
+        c->pred_cap = 0;
+        CK(cudaMalloc(&c->d_pred, d.n_rows * sizeof(double)));
+        c->pred_cap = d.n_rows;
+      }
+      CK(launch_predict64(c, d, 2, c->d_pred, nullptr, nb));
+      std::vector<double> err;
+      try {
+        err.resize(d.n_rows);
+      } catch (const std::bad_alloc&) {
+        return fail("out of host memory");
+      }
+      CK(cudaMemcpyAsync(err.data(), c->d_pred, d.n_rows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      for (uint64_t i = 0; i < d.n_rows; i++) {
+        sq += err[i] * err[i];
+        ab += std::abs(err[i]);
+      }
     } else {
-      CK(launch_predict32(c, d, 0, nullptr, c->d_partials, nb));
-    }
-    std::vector<double> h;
-    try {
-      h.resize(3 * (size_t)nb);
-    } catch (const std::bad_alloc&) {
-      return fail("out of host memory");
-    }
-    CK(cudaMemcpyAsync(h.data(), c->d_partials, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    for (int b = 0; b < nb; b++) {  // fixed order: deterministic result
-      sq += h[3 * b + 0];
-      ab += h[3 * b + 1];
-      ok += h[3 * b + 2];
+      if (c->mode != FMB200_MODE_HOGWILD) {
+        CK(launch_predict64(c, d, 0, nullptr, c->d_partials, nb));
+      } else {
+        CK(launch_predict32(c, d, 0, nullptr, c->d_partials, nb));
+      }
+      std::vector<double> h;
+      try {
+        h.resize(3 * (size_t)nb);
+      } catch (const std::bad_alloc&) {
+        return fail("out of host memory");
+      }
+      CK(cudaMemcpyAsync(h.data(), c->d_partials, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      for (int b = 0; b < nb; b++) {  // fixed order: deterministic result
+        sq += h[3 * b + 0];
+        ab += h[3 * b + 1];
+        ok += h[3 * b + 2];
+      }
     }
   }
   if (sum_sq_err) *sum_sq_err = sq;

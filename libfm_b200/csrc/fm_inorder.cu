@@ -219,11 +219,12 @@ __global__ void __launch_bounds__(256)
       double err = pc - y;
       sq += err * err;
       ab += fabs(err);
-      if (transform) pr = pc;
+      if (transform == 1) pr = pc;
+      if (transform == 2) pr = err;  // evaluate in row order on the host (fm_learn.h:139)
     } else {
       // fm_learn.h:118-120
       if (((pr >= 0) && (y >= 0)) || ((pr < 0) && (y < 0))) ok += 1;
-      if (transform) pr = 1.0 / (1.0 + exp(-pr));  // fm_learn_sgd.h:84
+      if (transform == 1) pr = 1.0 / (1.0 + exp(-pr));  // fm_learn_sgd.h:84
     }
     if (out_pred != nullptr && lane == 0) out_pred[r] = pr;
   }

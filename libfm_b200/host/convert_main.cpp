@@ -61,6 +61,8 @@ int main(int argc, char** argv) {
     std::cerr << e << std::endl;  // the reference prints the bare message (convert.cpp:200-202)
   } catch (char const*& e) {
     std::cerr << e << std::endl;
+  } catch (const std::exception& e) {  // e.g. bad_alloc on a corrupt size field
+    std::cerr << std::endl << "ERROR: " << e.what() << std::endl;
   }
   return 1;
 }

@@ -7,7 +7,8 @@
 // error instead of silently doing something else.
 //
 // New, optional flags (old command lines are unaffected):
-//   -mode hogwild|inorder   throughput (default) or sequential-equivalent fp64
+//   -mode hogwild|ordered|inorder   throughput (default); sequentially consistent fp64 (parallel over
+//                           conflict-free runs, within rounding of the reference); bit-exact fp64
 //   -gpus N                 row-shard the training set over N GPUs (hogwild)
 //   -device D               first CUDA ordinal
 #include <algorithm>
@@ -59,7 +60,7 @@ int main(int argc, char** argv) {
     const std::string p_save = cmd.add("save_model", "filename for writing the FM model");
     const std::string p_load = cmd.add("load_model", "filename for reading the FM model");
     // additions
-    const std::string p_mode = cmd.add("mode", "GPU execution mode: hogwild (throughput, default) or inorder (sequential-equivalent fp64)");
+    const std::string p_mode = cmd.add("mode", "GPU execution mode: hogwild (throughput, default), ordered (the reference's update order, fp64, parallel over independent rows) or inorder (bit-exact fp64, one row at a time)");
     const std::string p_gpus = cmd.add("gpus", "number of GPUs to shard the training rows over; default=1");
     const std::string p_dev = cmd.add("device", "first CUDA device ordinal; default=0");
 
@@ -136,6 +137,7 @@ int main(int argc, char** argv) {
     const std::string mode = cmd.str(p_mode, "hogwild");
     if (mode == "hogwild") fml.mode = FMB200_MODE_HOGWILD;
     else if (mode == "inorder") fml.mode = FMB200_MODE_INORDER;
+    else if (mode == "ordered") fml.mode = FMB200_MODE_ORDERED;
     else throw std::string("unknown -mode " + mode);
     fml.num_gpus = (int)cmd.integer(p_gpus, 1);
     fml.first_device = (int)cmd.integer(p_dev, 0);
@@ -227,6 +229,8 @@ int main(int argc, char** argv) {
     std::cerr << std::endl << "ERROR: " << e << std::endl;
   } catch (char const*& e) {
     std::cerr << std::endl << "ERROR: " << e << std::endl;
+  } catch (const std::exception& e) {  // e.g. bad_alloc on a corrupt size field
+    std::cerr << std::endl << "ERROR: " << e.what() << std::endl;
   }
   return 1;  // the reference falls off main with 0 here; a non-zero status is the one deliberate change
 }

@@ -226,6 +226,13 @@ struct SparseData {
       in.read(reinterpret_cast<char*>(&fh), sizeof(fh));
       if (!in || fh.id != 2 || fh.float_size != sizeof(float)) throw "could not read " + fx;
       if (fh.num_rows != target.size()) throw "row count of " + fx + " and " + fy + " differ";
+      {  // a truncated / corrupt header must not size the arrays: bound num_values by the file
+        in.seekg(0, std::ios::end);
+        const uint64_t fsize = (uint64_t)in.tellg();
+        in.seekg(sizeof(fh), std::ios::beg);
+        const uint64_t fixed = sizeof(fh) + 4ull * fh.num_rows;
+        if (!in || fsize < fixed || fh.num_values > (fsize - fixed) / 8) throw "could not read " + fx;
+      }
       col.resize(fh.num_values);
       val.resize(fh.num_values);
       row_ptr.assign(1, 0);
@@ -246,6 +253,7 @@ struct SparseData {
         pos += size;
         row_ptr.push_back(pos);
       }
+      if (pos != fh.num_values) throw "could not read " + fx;
       num_feature = (int)fh.num_cols;
     }
     for (float y : target) {  // Data.h:166-171
