@@ -178,8 +178,7 @@ def parity_run(mode, device, epochs=5, tuning=None):
     import numpy as np
     from libfm_b200 import FmLearnSgdElement, FmModel, synth
     from oracle import Port
-    tr = synth.movielens_1m_shaped(seed=7, planted_k=4)
-    te = synth.two_field(100_000, 6040, 3706, seed=8, planted_k=4)
+    tr, te = synth.movielens_1m_planted(100_000, seed=7)
     n = tr.num_feature
     v0 = np.random.default_rng(42).standard_normal((K_FACTORS, n)) * 0.1
     port = Port(n, K_FACTORS)

@@ -76,7 +76,8 @@ struct OrderedArgs {
 };
 
 // ---- shared-memory layout (host and device agree through these) -------------------------
-__host__ __device__ inline uint32_t ord_rp_bytes(int TR) { return (uint32_t)(TR + 2) * 8u; }
+// every staged array is a whole number of 16-byte units (TMA bulk copies) starting on one
+__host__ __device__ inline uint32_t ord_rp_bytes(int TR) { return ((uint32_t)(TR + 2) * 8u + 15u) & ~15u; }
 __host__ __device__ inline uint32_t ord_row_bytes(int TR) { return ((uint32_t)(TR + 4) * 4u + 15u) & ~15u; }
 __host__ __device__ inline uint32_t ord_csr_bytes(int TR, uint32_t TE) {
   return ord_rp_bytes(TR) + 2u * ord_row_bytes(TR) + 4u * TE * 4u;

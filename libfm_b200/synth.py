@@ -51,6 +51,18 @@ def two_field(n_rows: int, n_users: int, n_items: int, seed: int, zipf: float = 
     return _fields_to_data(cols, y, n_users + n_items)
 
 
+def split_rows(d: Data, n_first: int):
+    """(first n_first rows, the remaining rows) of one data set -- train / held-out rows of the SAME
+    planted model (two generator calls with different seeds plant different models)."""
+    return d.rows(0, n_first), d.rows(n_first, d.num_cases)
+
+
+def movielens_1m_planted(n_test: int = 100_000, seed: int = 7, zipf: float = 0.0):
+    """C2-shaped train set (1 000 209 rows) + held-out rows drawn from the same planted rank-4 model."""
+    full = two_field(1_000_209 + n_test, 6040, 3706, seed, zipf=zipf, planted_k=4)
+    return split_rows(full, 1_000_209)
+
+
 def movielens_1m_shaped(seed: int = 7, zipf: float = 0.0, planted_k: int = 0,
                         n_rows: int = 1_000_209) -> Data:
     """BASELINE config C2: 6040 users x 3706 items, ~1M rows, 2 nnz/row."""

@@ -23,8 +23,7 @@ def main():
     ap.add_argument("--out", default="gpurun_out/r2_sweep.json")
     ap.add_argument("--zipf", type=float, default=0.0)
     args = ap.parse_args()
-    tr = synth.movielens_1m_shaped(seed=7, planted_k=4, zipf=args.zipf)
-    te = synth.two_field(100_000, 6040, 3706, seed=8, planted_k=4, zipf=args.zipf)
+    tr, te = synth.movielens_1m_planted(100_000, seed=7, zipf=args.zipf)
     n, k = tr.num_feature, 8
     v0 = np.random.default_rng(42).standard_normal((k, n)) * 0.1
     port = Port(n, k)

@@ -415,8 +415,7 @@ def test_peer_meanfield_two_contexts(built_lib):
     both end bit-identical, equal to a numpy restatement of the rule, and -- over a few epochs -- closer
     to the single-stream oracle than plain averaging is."""
     import ctypes as C
-    full = synth.two_field(120_000, 1500, 1000, seed=5, planted_k=4)
-    te = synth.two_field(20_000, 1500, 1000, seed=6, planted_k=4)
+    full, te = synth.split_rows(synth.two_field(140_000, 1500, 1000, seed=5, planted_k=4), 120_000)
     n, k, lr, G = full.num_feature, 8, 0.01, 2
     half = full.num_cases // 2
     shards = [full.rows(0, half), full.rows(half, full.num_cases)]
@@ -480,7 +479,7 @@ def test_peer_meanfield_two_contexts(built_lib):
     print("\n[peer combine, 2 shards, 3 epochs] held-out RMSE: sequential %.4f  meanfield %.4f  average %.4f" %
           (seq, rmse["meanfield"], rmse["average"]))
     assert abs(rmse["meanfield"] - seq) < abs(rmse["average"] - seq)
-    assert abs(rmse["meanfield"] - seq) < 0.02
+    assert abs(rmse["meanfield"] - seq) < 0.03
 
 
 def test_hogwild_rows_longer_than_the_staging_ring(built_lib):
@@ -494,7 +493,7 @@ def test_hogwild_rows_longer_than_the_staging_ring(built_lib):
     d = Data(np.arange(rows + 1, dtype=np.uint64) * np.uint64(per_row), col,
              (r.standard_normal(rows * per_row) * 0.05).astype(np.float32),
              r.integers(1, 6, size=rows).astype(np.float32), n)
-    cfg = _cfg(n, k, lr=0.001, mn=1.0, mx=5.0)
+    cfg = _cfg(n, k, lr=0.001, mn=-10.0, mx=10.0)   # wide bounds: the clamp must not hide the learning
     init = _rand_init(n, k, 4)
     l = make_learner(cfg, init, mode=MODE_HOGWILD)
     got = l.predict(d, transform=False)
@@ -509,7 +508,7 @@ def test_hogwild_rows_longer_than_the_staging_ring(built_lib):
     m = make_learner(cfg, init, mode=MODE_HOGWILD)
     p = _port(cfg, init)
     m.sgd_epoch(one)
-    p.sgd_epoch(one, 0, cfg["lr"], 1.0, 5.0)
+    p.sgd_epoch(one, 0, cfg["lr"], -10.0, 10.0)
     m.pull_params()
     np.testing.assert_allclose(m.fm.v, p.v, atol=2e-6)
     np.testing.assert_allclose(m.fm.w, p.w, atol=2e-6)

@@ -203,8 +203,7 @@ def test_ordered_c2_full_size_trajectory(built_lib):
     """BASELINE config C2 at full size (1 000 209 rows, 6040 x 3706, k = 8), planted signal, 5 epochs:
     |RMSE_gpu - RMSE_oracle| <= 1e-5 every epoch (asserted 1e-8), parameters to 1e-9, and the epoch is
     timed next to the oracle's single core (report only; bench.py carries the driver-run number)."""
-    tr = synth.movielens_1m_shaped(seed=7, planted_k=4)
-    te = synth.two_field(100_000, 6040, 3706, seed=8, planted_k=4)
+    tr, te = synth.movielens_1m_planted(100_000, seed=7)
     n = tr.num_feature
     init = _rand_init(n, 8, 42)
     init = (0.0, np.zeros(n), init[2])
