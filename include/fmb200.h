@@ -136,6 +136,19 @@ int fmb200_predict(fmb200_ctx* ctx, int slot, int transform, double* out);
  * Uses the fp64 state (INORDER / ORDERED mode): fmb200_set_params after every draw_all(). */
 int fmb200_mcmc_eterms(fmb200_ctx* ctx, int slot, double* e_out);
 
+/* Replaces: fm_learn_sgd_element_adapt_reg (SGDA, fm_learn_sgd_element_adapt_reg.h).
+ *  _begin: init() + the prologue of learn() (:60-90, :281-292): stored gradients and the per-group
+ *          regularisation values start at 0, fm->w is zeroed; attr_group[n] = DataMetaInfo::attr_group
+ *          (NULL = one group).
+ *  _epoch: one pass of :295-311 -- a theta-step (:136-169) per training row, each followed, when
+ *          lambda_steps != 0 (the reference skips them in its first epoch, :301), by a lambda-step
+ *          (:201-248) on the next validation row, the cursor restarting per epoch and wrapping.
+ *          Sequential semantics, fp64, bit-identical to the reference (one warp: a parity path).
+ *  _get_reg: reg_w[n_groups], reg_v[n_groups][num_factor]. */
+int fmb200_sgda_begin(fmb200_ctx* ctx, uint32_t n_groups, const uint32_t* attr_group);
+int fmb200_sgda_epoch(fmb200_ctx* ctx, int train_slot, int val_slot, int lambda_steps, double* device_seconds);
+int fmb200_sgda_get_reg(fmb200_ctx* ctx, double* reg_w, double* reg_v);
+
 /* Multi-GPU plumbing (row sharding + one all-reduce of w0|w|V per epoch; the
  * reference has no equivalent).  The HOGWILD state is one packed fp32 device
  * buffer [w0, pad x3 | w (strided) | V[n][kp]]; the caller all-reduces it

@@ -41,6 +41,9 @@ SYMBOLS = {
     "fmb200_sync": (C.c_int, [_ctx]),
     "fmb200_evaluate": (C.c_int, [_ctx, C.c_int, _f64p, _f64p, _u64p]),
     "fmb200_predict": (C.c_int, [_ctx, C.c_int, C.c_int, _f64p]),
+    "fmb200_sgda_begin": (C.c_int, [_ctx, C.c_uint32, _u32p]),
+    "fmb200_sgda_epoch": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, _f64p]),
+    "fmb200_sgda_get_reg": (C.c_int, [_ctx, _f64p, _f64p]),
     "fmb200_mcmc_eterms": (C.c_int, [_ctx, C.c_int, _f64p]),
     "fmb200_params_device": (C.c_int, [_ctx, C.POINTER(C.c_void_p), _u64p]),
     "fmb200_scale_params": (C.c_int, [_ctx, C.c_double]),

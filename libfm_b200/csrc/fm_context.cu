@@ -304,6 +304,11 @@ void fmb200_destroy(fmb200_ctx* c) {
     if (c->peer_ipc[q] && c->peer_base[q]) cudaIpcCloseMemHandle(c->peer_base[q]);
   if (c->comm_base) cudaFree(c->comm_base);
   if (c->p64.base) cudaFree(c->p64.base);
+  if (c->sgda_grad_w) cudaFree(c->sgda_grad_w);
+  if (c->sgda_grad_v) cudaFree(c->sgda_grad_v);
+  if (c->sgda_reg_w) cudaFree(c->sgda_reg_w);
+  if (c->sgda_reg_v) cudaFree(c->sgda_reg_v);
+  if (c->sgda_group) cudaFree(c->sgda_group);
   if (c->d_partials) cudaFree(c->d_partials);
   if (c->d_pred) cudaFree(c->d_pred);
   if (c->d_sched) cudaFree(c->d_sched);
@@ -695,6 +700,72 @@ int fmb200_predict(fmb200_ctx* c, int slot, int transform, double* out) {
     CK(launch_predict32(c, d, transform, c->d_pred, nullptr, nb));
   }
   CK(cudaMemcpyAsync(out, c->d_pred, d.n_rows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int fmb200_sgda_begin(fmb200_ctx* c, uint32_t n_groups, const uint32_t* attr_group) {
+  NEED_CTX(c);
+  if (bind(c)) return 1;
+  if (c->mode == FMB200_MODE_HOGWILD) return fail("SGDA runs on the fp64 state: set INORDER or ORDERED mode first");
+  if (n_groups == 0 || n_groups > 1024) return fail("n_groups must be in [1,1024]");
+  if (n_groups > 1 && !attr_group) return fail("attr_group is required for more than one group");
+  if (attr_group)
+    for (uint32_t i = 0; i < c->n; i++)
+      if (attr_group[i] >= n_groups) return fail("attr_group[%u] = %u >= n_groups", i, attr_group[i]);
+  const size_t n1 = c->n ? c->n : 1, nk = (size_t)c->n * c->k ? (size_t)c->n * c->k : 1;
+  const size_t gk = (size_t)n_groups * (c->k ? c->k : 1);
+  if (!c->sgda_grad_w) {
+    CK(cudaMalloc(&c->sgda_grad_w, n1 * sizeof(double)));
+    CK(cudaMalloc(&c->sgda_grad_v, nk * sizeof(double)));
+    CK(cudaMalloc(&c->sgda_group, n1 * sizeof(uint32_t)));
+  }
+  if (c->sgda_groups != n_groups) {
+    if (c->sgda_reg_w) cudaFree(c->sgda_reg_w);
+    if (c->sgda_reg_v) cudaFree(c->sgda_reg_v);
+    c->sgda_reg_w = c->sgda_reg_v = nullptr;
+    CK(cudaMalloc(&c->sgda_reg_w, n_groups * sizeof(double)));
+    CK(cudaMalloc(&c->sgda_reg_v, gk * sizeof(double)));
+    c->sgda_groups = n_groups;
+  }
+  // init(): grad_w = grad_v = 0 (:73-74); learn(): w = 0, reg_w = reg_v = 0 (:283-291)
+  CK(cudaMemsetAsync(c->sgda_grad_w, 0, n1 * sizeof(double), c->stream));
+  CK(cudaMemsetAsync(c->sgda_grad_v, 0, nk * sizeof(double), c->stream));
+  CK(cudaMemsetAsync(c->sgda_reg_w, 0, n_groups * sizeof(double), c->stream));
+  CK(cudaMemsetAsync(c->sgda_reg_v, 0, gk * sizeof(double), c->stream));
+  CK(cudaMemsetAsync(c->p64.w(), 0, n1 * sizeof(double), c->stream));
+  if (attr_group) CK(cudaMemcpyAsync(c->sgda_group, attr_group, c->n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  else CK(cudaMemsetAsync(c->sgda_group, 0, n1 * sizeof(uint32_t), c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int fmb200_sgda_epoch(fmb200_ctx* c, int train_slot, int val_slot, int lambda_steps, double* device_seconds) {
+  NEED_CTX(c);
+  if (need_slot(c, train_slot) || need_slot(c, val_slot)) return 1;
+  if (bind(c)) return 1;
+  if (c->mode == FMB200_MODE_HOGWILD) return fail("SGDA runs on the fp64 state: set INORDER or ORDERED mode first");
+  if (c->sgda_groups == 0) return fail("call fmb200_sgda_begin first");
+  if (c->k > 256) return fail("num_factor > 256 is not supported in the fp64 modes");
+  CK(cudaEventRecord(c->ev0, c->stream));
+  CK(launch_sgda_epoch(c, c->slots[train_slot], c->slots[val_slot], lambda_steps));
+  CK(cudaEventRecord(c->ev1, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (device_seconds) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    *device_seconds = (double)ms * 1e-3;
+  }
+  return 0;
+}
+
+int fmb200_sgda_get_reg(fmb200_ctx* c, double* reg_w, double* reg_v) {
+  NEED_CTX(c);
+  if (bind(c)) return 1;
+  if (c->sgda_groups == 0) return fail("call fmb200_sgda_begin first");
+  if (reg_w) CK(cudaMemcpyAsync(reg_w, c->sgda_reg_w, c->sgda_groups * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (reg_v && c->k)
+    CK(cudaMemcpyAsync(reg_v, c->sgda_reg_v, (size_t)c->sgda_groups * c->k * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }

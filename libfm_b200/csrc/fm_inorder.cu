@@ -357,6 +357,247 @@ cudaError_t launch_mcmc_eterms(fmb200_ctx* c, const DataSlot& d, double* e_out) 
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------
+// SGDA: SGD with self-adaptive regularisation (reference
+// libfm/src/fm_learn_sgd_element_adapt_reg.h).  Every training row's theta-step (:136-169) is
+// followed by a lambda-step on the next validation row (:201-248) that moves the per-group
+// regularisation values; both touch state every later step reads (w0, reg_w, reg_v), so the
+// epoch is one chain like the plain in-order epoch and runs the same way: one warp, lane =
+// factor, every operation in the reference's order (--fmad=false): bit-identical parameters and
+// regularisation values.  Per-group accumulators of a lambda-step live in shared memory
+// ([group][factor], one column per lane: no two lanes share a word).
+struct SgdaArgs {
+  Params64 p;
+  double* grad_w;        // [n]
+  double* grad_v;        // [n][k] attribute-major
+  double* reg_w;         // [G]
+  double* reg_v;         // [G][k]
+  const uint32_t* group; // [n]
+  uint32_t n_groups;
+  int k, use_w0, use_w, lambda_steps;
+  HParams hp;
+  uint64_t n_rows, v_rows;
+  const uint64_t *row_ptr, *v_row_ptr;
+  const uint32_t *col, *v_col;
+  const float *val, *v_val, *target, *v_target;
+};
+
+template <int KF>
+__global__ void __launch_bounds__(32, 1) fm_sgda_epoch_kernel(const SgdaArgs a) {
+  extern __shared__ double sg_smem[];  // reg_w[G] | reg_v[G][k] | sum_f[G][k] | sum_f_dash_f[G][k] | lwg[G]
+  const int lane = threadIdx.x;
+  const int k = a.k;
+  const uint32_t G = a.n_groups;
+  double* s_reg_w = sg_smem;
+  double* s_reg_v = s_reg_w + G;
+  double* s_sum_f = s_reg_v + (size_t)G * k;
+  double* s_sdf = s_sum_f + (size_t)G * k;
+  double* s_lwg = s_sdf + (size_t)G * k;
+  for (uint32_t i = lane; i < G; i += 32) s_reg_w[i] = a.reg_w[i];
+  for (uint32_t i = lane; i < G * (uint32_t)k; i += 32) s_reg_v[i] = a.reg_v[i];
+  __syncwarp();
+  RowCtx m;
+  m.k = k;
+  m.k0 = a.use_w0 != 0;
+  m.k1 = a.use_w != 0;
+  m.w = a.p.w();
+  m.v = a.p.v();
+  double* w = a.p.w();
+  double* v = a.p.v();
+  double w0 = *a.p.w0();
+  const double lr = a.hp.lr;
+  const unsigned full = 0xffffffffu;
+  double sum[KF];
+  uint64_t vc = 0;
+  for (uint64_t r = 0; r < a.n_rows; r++) {
+    {  // ---- sgd_theta_step, :136-169 ----
+      const uint64_t beg = a.row_ptr[r];
+      const uint32_t size = (uint32_t)(a.row_ptr[r + 1] - beg);
+      const uint32_t* c = a.col + beg;
+      const float* x = a.val + beg;
+      const float target = a.target[r];
+      double p = predict_row_exact<KF>(m, w0, c, x, size, sum, lane);
+      double mult = 0;
+      if (a.hp.task == FMB200_TASK_REGRESSION) {
+        p = fmin(a.hp.max_target, p);
+        p = fmax(a.hp.min_target, p);
+        mult = 2 * (p - target);
+      } else {
+        mult = target * ((1.0 / (1.0 + exp(-target * p))) - 1.0);
+      }
+      if (m.k0) w0 -= lr * (mult + 2 * 0.0 * w0);  // reg_0 stays 0 (:60,79)
+      if (m.k1 && lane == 0) {
+        for (uint32_t i = 0; i < size; i++) {
+          const uint32_t id = c[i];
+          const uint32_t g = a.group[id];
+          double cur = w[id];
+          const double gw = mult * x[i];
+          a.grad_w[id] = gw;
+          cur -= lr * (gw + 2 * s_reg_w[g] * cur);
+          w[id] = cur;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < KF; j++) {
+        const int f = lane + 32 * j;
+        if (f < k) {
+          for (uint32_t i = 0; i < size; i++) {
+            const uint32_t id = c[i];
+            const uint32_t g = a.group[id];
+            double* vp = &v[(size_t)id * k + f];
+            double cur = *vp;
+            const double gv = mult * (x[i] * (sum[j] - cur * x[i]));
+            a.grad_v[(size_t)id * k + f] = gv;
+            cur -= lr * (gv + 2 * s_reg_v[(size_t)g * k + f] * cur);
+            *vp = cur;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (a.lambda_steps && a.v_rows > 0) {  // ---- sgd_lambda_step, :201-248 ----
+      if (vc == a.v_rows) vc = 0;  // :302-305
+      const uint64_t beg = a.v_row_ptr[vc];
+      const uint32_t size = (uint32_t)(a.v_row_ptr[vc + 1] - beg);
+      const uint32_t* c = a.v_col + beg;
+      const float* x = a.v_val + beg;
+      const float target = a.v_target[vc];
+      vc++;
+      // predict_scaled, :171-199
+      double p = 0.0;
+      if (lane == 0) {
+        if (m.k0) p += w0;
+        if (m.k1)
+          for (uint32_t i = 0; i < size; i++) {
+            const uint32_t id = c[i];
+            const double wv = w[id];
+            const double w_dash = wv - lr * (a.grad_w[id] + 2 * s_reg_w[a.group[id]] * wv);
+            p += w_dash * x[i];
+          }
+      }
+      p = __shfl_sync(full, p, 0);
+      double term[KF];
+#pragma unroll
+      for (int j = 0; j < KF; j++) {
+        const int f = lane + 32 * j;
+        double s = 0.0, ss = 0.0;
+        if (f < k)
+          for (uint32_t i = 0; i < size; i++) {
+            const uint32_t id = c[i];
+            const double vv = v[(size_t)id * k + f];
+            const double v_dash =
+                vv - lr * (a.grad_v[(size_t)id * k + f] + 2 * s_reg_v[(size_t)a.group[id] * k + f] * vv);
+            const double d = v_dash * x[i];
+            s += d;
+            ss += d * d;
+          }
+        term[j] = 0.5 * (s * s - ss);
+      }
+#pragma unroll
+      for (int j = 0; j < KF; j++) {
+        const int fbase = 32 * j;
+        if (fbase < k) {
+          const int cnt = min(32, k - fbase);
+          for (int l = 0; l < cnt; l++) p += __shfl_sync(full, term[j], l);
+        }
+      }
+      double grad_loss = 0;
+      if (a.hp.task == FMB200_TASK_REGRESSION) {
+        p = fmin(a.hp.max_target, p);
+        p = fmax(a.hp.min_target, p);
+        grad_loss = 2 * (p - target);
+      } else {
+        grad_loss = target * ((1.0 / (1.0 + exp(-target * p))) - 1.0);
+      }
+      if (m.k1) {  // :213-223: lane g owns group g, g+32, ...
+        for (uint32_t g = lane; g < G; g += 32) {
+          double acc = 0.0;
+          for (uint32_t i = 0; i < size; i++)
+            if (a.group[c[i]] == g) acc += x[i] * w[c[i]];
+          acc = -2 * lr * acc;
+          double rw = s_reg_w[g] - lr * grad_loss * acc;
+          s_reg_w[g] = (0.0 < rw) ? rw : 0.0;  // std::max(0.0, .)
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < KF; j++) {  // :224-247
+        const int f = lane + 32 * j;
+        if (f < k) {
+          double sum_f_dash = 0.0;
+          for (uint32_t g = 0; g < G; g++) {
+            s_sum_f[(size_t)g * k + f] = 0.0;
+            s_sdf[(size_t)g * k + f] = 0.0;
+          }
+          for (uint32_t i = 0; i < size; i++) {
+            const uint32_t id = c[i];
+            const uint32_t g = a.group[id];
+            const double vv = v[(size_t)id * k + f];
+            const double v_dash = vv - lr * (a.grad_v[(size_t)id * k + f] + 2 * s_reg_v[(size_t)g * k + f] * vv);
+            sum_f_dash += v_dash * x[i];
+            s_sum_f[(size_t)g * k + f] += vv * x[i];
+            s_sdf[(size_t)g * k + f] += v_dash * x[i] * vv * x[i];
+          }
+          for (uint32_t g = 0; g < G; g++) {
+            const double lvg = -2 * lr * (sum_f_dash * s_sum_f[(size_t)g * k + f] - s_sdf[(size_t)g * k + f]);
+            const double rv = s_reg_v[(size_t)g * k + f] - lr * grad_loss * lvg;
+            s_reg_v[(size_t)g * k + f] = (0.0 < rv) ? rv : 0.0;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  (void)s_lwg;
+  if (lane == 0 && m.k0) *a.p.w0() = w0;
+  for (uint32_t i = lane; i < G; i += 32) a.reg_w[i] = s_reg_w[i];
+  for (uint32_t i = lane; i < G * (uint32_t)k; i += 32) a.reg_v[i] = s_reg_v[i];
+}
+
+cudaError_t launch_sgda_epoch(fmb200_ctx* c, const DataSlot& tr, const DataSlot& va, int lambda_steps) {
+  if (c->k > 32 * KF_MAX) return cudaErrorInvalidValue;
+  SgdaArgs a;
+  a.p = c->p64;
+  a.grad_w = c->sgda_grad_w;
+  a.grad_v = c->sgda_grad_v;
+  a.reg_w = c->sgda_reg_w;
+  a.reg_v = c->sgda_reg_v;
+  a.group = c->sgda_group;
+  a.n_groups = c->sgda_groups;
+  a.k = c->k;
+  a.use_w0 = c->k0;
+  a.use_w = c->k1;
+  a.lambda_steps = lambda_steps;
+  a.hp = c->hp;
+  a.n_rows = tr.n_rows;
+  a.row_ptr = tr.row_ptr;
+  a.col = tr.col;
+  a.val = tr.val;
+  a.target = tr.target;
+  a.v_rows = va.n_rows;
+  a.v_row_ptr = va.row_ptr;
+  a.v_col = va.col;
+  a.v_val = va.val;
+  a.v_target = va.target;
+  const size_t smem = sizeof(double) * ((size_t)c->sgda_groups * (2 + 3 * (size_t)c->k));
+  if (smem > (size_t)c->max_smem_optin) return cudaErrorInvalidConfiguration;
+  const int kf = (c->k + 31) / 32;
+#define FMB_SGDA(KF)                                                                                  \
+  do {                                                                                                \
+    cudaError_t e_ = cudaFuncSetAttribute(fm_sgda_epoch_kernel<KF>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)smem);                                                 \
+    if (e_ != cudaSuccess) return e_;                                                                 \
+    fm_sgda_epoch_kernel<KF><<<1, 32, smem, c->stream>>>(a);                                          \
+  } while (0)
+  if (kf <= 1) FMB_SGDA(1);
+  else if (kf <= 2) FMB_SGDA(2);
+  else if (kf <= 4) FMB_SGDA(4);
+  else FMB_SGDA(8);
+#undef FMB_SGDA
+  c->launches++;
+  c->last_cfg = EpochConfig{32, 1, 1, 1, 32, (int)smem, 0};
+  return cudaGetLastError();
+}
+
 cudaError_t launch_sgd_inorder(fmb200_ctx* c, const DataSlot& d) {
   if (c->k > 32 * KF_MAX) return cudaErrorInvalidValue;
   // The wavefront schedule (k <= 8, rows of <= 4 entries) is the default for eligible shapes:

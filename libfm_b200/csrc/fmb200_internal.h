@@ -114,6 +114,10 @@ struct fmb200_ctx {
   bool peer_ipc[FMB200_MAX_PEERS] = {false};
   int peer_world = 1, peer_rank = 0, peer_cur = 0;
   unsigned int peer_seq = 0, peer_bar_seq = 0;
+  // SGDA state (fm_learn_sgd_element_adapt_reg.h): stored gradients, per-group regularisation
+  double *sgda_grad_w = nullptr, *sgda_grad_v = nullptr, *sgda_reg_w = nullptr, *sgda_reg_v = nullptr;
+  uint32_t* sgda_group = nullptr;
+  uint32_t sgda_groups = 0;
   int tune_damp = 0;  // 0 auto, 1 force on, -1 force off
   int tune_variant = 0;  // 0 auto, 1 row-group kernel, 2 row-lane kernel when eligible
 };
@@ -132,6 +136,8 @@ cudaError_t launch_sgd_ordered(fmb200_ctx* c, DataSlot& d, bool* handled);
 cudaError_t build_ordered_links(fmb200_ctx* c, DataSlot& d);
 // fm_inorder.cu: the MCMC / ALS e-term pass (fm_learn_mcmc.h:148-378), bit-identical accumulation
 cudaError_t launch_mcmc_eterms(fmb200_ctx* c, const DataSlot& d, double* e_out);
+// fm_inorder.cu: one SGDA epoch (theta-step per training row, lambda-step per validation row)
+cudaError_t launch_sgda_epoch(fmb200_ctx* c, const DataSlot& tr, const DataSlot& va, int lambda_steps);
 // fm_hogwild.cu: throughput epoch
 cudaError_t launch_sgd_hogwild(fmb200_ctx* c, const DataSlot& d);
 // fm_predict.cu: fp32 scores / metrics with sub-warp row groups

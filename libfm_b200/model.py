@@ -344,6 +344,28 @@ class FmLearnSgdElement:
                                             _p(out, C.c_double)))
         return out
 
+    # -- SGDA: fm_learn_sgd_element_adapt_reg ----------------------------------
+    def sgda_begin(self, attr_group=None) -> None:
+        if attr_group is None:
+            self._sgda_groups = 1
+            self._check(self.lib.fmb200_sgda_begin(self._ctx, 1, None))
+        else:
+            g = np.ascontiguousarray(attr_group, dtype=np.uint32)
+            self._sgda_groups = int(g.max()) + 1
+            self._check(self.lib.fmb200_sgda_begin(self._ctx, self._sgda_groups, _p(g, C.c_uint32)))
+
+    def sgda_epoch(self, train: Data, validation: Data, lambda_steps: bool) -> float:
+        sec = C.c_double()
+        self._check(self.lib.fmb200_sgda_epoch(self._ctx, self._slot_of(train), self._slot_of(validation),
+                                               int(lambda_steps), C.byref(sec)))
+        return sec.value
+
+    def sgda_reg(self):
+        reg_w = np.zeros(self._sgda_groups)
+        reg_v = np.zeros((self._sgda_groups, self.fm.num_factor))
+        self._check(self.lib.fmb200_sgda_get_reg(self._ctx, _p(reg_w, C.c_double), _p(reg_v, C.c_double)))
+        return reg_w, reg_v
+
     def mcmc_eterms(self, data: Data) -> np.ndarray:
         """fm_learn_mcmc::predict_data_and_write_to_eterms (fm_learn_mcmc.h:148-378) for one data set."""
         out = np.empty(data.num_cases, dtype=np.float64)

@@ -96,6 +96,24 @@ class Port:
                              _p(data.col, C.c_uint32), _p(data.val, C.c_float), _p(out, C.c_double))
         return out
 
+    def sgda_begin(self, group=None):
+        """state of fm_learn_sgd_element_adapt_reg (:60-90 init, :281-292 learn prologue)"""
+        self.group = np.zeros(self.n, dtype=np.uint32) if group is None else np.ascontiguousarray(group, dtype=np.uint32)
+        self.n_groups = int(self.group.max()) + 1 if self.n else 1
+        self.grad_w = np.zeros(self.n)
+        self.grad_v = np.zeros((self.k, self.n))
+        self.reg_w = np.zeros(self.n_groups)
+        self.reg_v = np.zeros((self.n_groups, max(self.k, 1)))[:, :self.k].copy()
+        self.w[:] = 0.0  # :283
+
+    def sgda_epoch(self, train, val, task, lr, min_target, max_target, lambda_steps):
+        self.lib.fmo_sgda_epoch(C.c_uint32(self.n), self.k, self.k0, self.k1, C.byref(self.w0),
+                                _p(self.w, C.c_double), _p(self.v, C.c_double), _p(self.grad_w, C.c_double),
+                                _p(self.grad_v, C.c_double), _p(self.reg_w, C.c_double), _p(self.reg_v, C.c_double),
+                                _p(self.group, C.c_uint32), C.c_uint32(self.n_groups), C.c_double(lr), task,
+                                C.c_double(min_target), C.c_double(max_target), int(lambda_steps),
+                                *_csr(train), *_csr(val))
+
     def mcmc_eterms(self, data):
         """fm_learn_mcmc::predict_data_and_write_to_eterms (fm_learn_mcmc.h:148-378), one data set."""
         out = np.empty(data.num_cases, dtype=np.float64)
@@ -195,6 +213,20 @@ class Ref:
         if rc != 0:
             raise RuntimeError(self.lib().ref_last_error().decode())
         return out
+
+    def sgda_learn(self, train, val, test, group, task, lr, num_iter, min_target, max_target):
+        """fm_learn_sgd_element_adapt_reg::learn; returns (reg_w, reg_v); parameters via get_params()"""
+        group = np.ascontiguousarray(group, dtype=np.uint32)
+        ng = int(group.max()) + 1
+        reg_w = np.zeros(ng)
+        reg_v = np.zeros((ng, self.k))
+        rc = self.lib().ref_sgda_learn(self.h, self.data(train), self.data(val), self.data(test),
+                                       _p(group, C.c_uint32), C.c_uint32(ng), task, C.c_double(lr), num_iter,
+                                       C.c_double(min_target), C.c_double(max_target), _p(reg_w, C.c_double),
+                                       _p(reg_v, C.c_double))
+        if rc != 0:
+            raise RuntimeError(self.lib().ref_last_error().decode())
+        return reg_w, reg_v
 
     def mcmc_eterms(self, d):
         """the reference's own e-term pass (through its transposed copy of the data)"""

@@ -37,6 +37,7 @@
 #include "libfm/src/fm_learn.h"
 #include "libfm/src/fm_learn_sgd.h"
 #include "libfm/src/fm_learn_sgd_element.h"
+#include "libfm/src/fm_learn_sgd_element_adapt_reg.h"
 #include "libfm/src/fm_learn_mcmc_simultaneous.h"
 
 namespace {
@@ -107,6 +108,41 @@ struct McmcProbe : public fm_learn_mcmc_simultaneous {
 extern "C" {
 
 const char* ref_last_error() { return g_err; }
+
+// fm_learn_sgd_element_adapt_reg::learn (SGDA) with the given attribute groups; returns the learned
+// regularisation values (reg_w [n_groups], reg_v [n_groups][k]); the model stays in the fm handle.
+int ref_sgda_learn(void* fm_h, void* train_h, void* val_h, void* test_h, const uint32_t* group, uint32_t n_groups,
+                   int task, double lr, int num_iter, double min_target, double max_target, double* reg_w,
+                   double* reg_v) {
+  RefFm* m = (RefFm*)fm_h;
+  RefData* tr = (RefData*)train_h;
+  RefData* va = (RefData*)val_h;
+  RefData* te = (RefData*)test_h;
+  return guarded([&]() {
+    CoutMute mute;
+    DataMetaInfo meta(m->fm.num_attribute);
+    for (uint i = 0; i < m->fm.num_attribute; i++) meta.attr_group(i) = group[i];
+    meta.num_attr_groups = n_groups;
+    meta.num_relations = 0;
+    fm_learn_sgd_element_adapt_reg l;
+    l.fm = &m->fm;
+    l.meta = &meta;
+    l.task = task;
+    l.min_target = min_target;
+    l.max_target = max_target;
+    l.num_iter = num_iter;
+    l.learn_rate = lr;
+    l.log = NULL;
+    l.validation = va->d;
+    l.init();
+    l.learn_rates.init(lr);
+    l.learn(*tr->d, *te->d);
+    for (uint g = 0; g < n_groups; g++) {
+      reg_w[g] = l.reg_w(g);
+      for (int f = 0; f < m->fm.num_factor; f++) reg_v[(size_t)g * m->fm.num_factor + f] = l.reg_v(g, f);
+    }
+  });
+}
 
 // fm_learn_mcmc::predict_data_and_write_to_eterms on one data set (no relations): e_out[c] is the
 // e-term = the model's score of case c, accumulated feature-major through the transposed copy

@@ -187,3 +187,33 @@ def test_mcmc_eterm_port_is_bit_identical_to_reference(case):
     assert np.array_equal(got, want)
     # same quantity as fm_model::predict, different association: equal to rounding only
     assert np.max(np.abs(got - p.predict(d, 0, 0, 0, transform=False))) < 1e-12
+
+
+@pytest.mark.parametrize("task", [0, 1])
+def test_sgda_port_is_bit_identical_to_reference(task):
+    """oracle/fm_oracle_sgda.c against the reference's own fm_learn_sgd_element_adapt_reg::learn
+    (4 epochs: the first without lambda-steps, validation cursor wrapping, two attribute groups)."""
+    from oracle import Ref, have_ref
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    full = synth.two_field(9000, 300, 200, seed=4, planted_k=3)
+    tr, rest = synth.split_rows(full, 6000)
+    va, te = synth.split_rows(rest, 2000)
+    if task == 1:
+        for d in (tr, va, te):
+            d.target[:] = np.where(d.target > 3, 1.0, -1.0)
+    n, k = full.num_feature, 5
+    group = (np.arange(n) >= 300).astype(np.uint32)
+    mn, mx = float(tr.target.min()), float(tr.target.max())
+    ref = Ref(n, k, seed=42, init_stdev=0.1)
+    w0, w, v = ref.get_params()
+    p = Port(n, k)
+    p.set_params(w0, w, v)
+    p.sgda_begin(group)
+    reg_w, reg_v = ref.sgda_learn(tr, va, te, group, task, 0.02, 4, mn, mx)
+    for e in range(4):
+        p.sgda_epoch(tr, va, task, 0.02, mn, mx, e > 0)
+    a0, aw, av = ref.get_params()
+    assert a0 == p.w0.value and np.array_equal(aw, p.w) and np.array_equal(av, p.v)
+    assert np.array_equal(reg_w, p.reg_w) and np.array_equal(reg_v, p.reg_v)
+    assert reg_w.max() > 0 and reg_v.max() > 0  # the lambda-steps did move the regularisation
