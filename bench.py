@@ -271,6 +271,7 @@ def extra_config(name, data, k, task, device, steps, warmup, flush, stream, torc
     l.push_hparams()
     l.upload(data, 0)
     launches0 = l.kernel_launches()
+    stream = torch.cuda.ExternalStream(l.stream(), device=device)  # this learner's own stream
     ms = timed_epochs(l, data, steps, warmup, flush, stream, torch)
     launches = l.kernel_launches() - launches0
     cfg = l.epoch_config()

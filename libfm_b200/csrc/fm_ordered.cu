@@ -3,6 +3,8 @@
 // entry naming the same feature, for every row the distance to the nearest earlier row it
 // depends on.  Both are pure functions of col[] / row_ptr[] (bit-exact ordering work) and
 // are built once per upload, on the device, the first time an ORDERED epoch needs them.
+#include <algorithm>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "fm_ordered.cuh"
@@ -47,24 +49,40 @@ __global__ void ord_link_kernel(const uint32_t* __restrict__ ids, const uint32_t
   }
 }
 
+// blockDim <= ORD_SMAX * GL (one group of GL lanes per example of a run): small k leaves the
+// register file to few threads (k <= 8: 128 threads)
 template <int GL, int KF, int TASK>
-__global__ void __launch_bounds__(ORD_MAX_THREADS, 1) fm_sgd_ordered_kernel(const OrderedArgs a) {
+__global__ void __launch_bounds__((ORD_SMAX * GL < ORD_MAX_THREADS ? ORD_SMAX * GL : ORD_MAX_THREADS), 1)
+    fm_sgd_ordered_kernel(const OrderedArgs a) {
   extern __shared__ __align__(128) unsigned char ord_smem[];
   ordered_epoch_body<GL, KF, TASK>(a, ord_smem);
 }
 
 using OrdFn = void (*)(const OrderedArgs);
 
+// (GL lanes per example, KF consecutive factors per lane): KF <= 8; k <= 8 runs one lane per example
+inline void ordered_shape(int k, int* GL, int* KF) {
+  if (k <= 8) {
+    *GL = 1;
+    *KF = k <= 1 ? 1 : (k <= 2 ? 2 : (k <= 4 ? 4 : 8));
+    return;
+  }
+  *KF = 8;
+  int g = 2;
+  while (g * 8 < k) g <<= 1;
+  *GL = g;
+}
+
 template <int TASK>
 OrdFn pick_kernel(int k) {
   if (k <= 1) return fm_sgd_ordered_kernel<1, 1, TASK>;
-  if (k <= 2) return fm_sgd_ordered_kernel<2, 1, TASK>;
-  if (k <= 4) return fm_sgd_ordered_kernel<4, 1, TASK>;
-  if (k <= 8) return fm_sgd_ordered_kernel<8, 1, TASK>;
-  if (k <= 16) return fm_sgd_ordered_kernel<16, 1, TASK>;
-  if (k <= 32) return fm_sgd_ordered_kernel<32, 1, TASK>;
-  if (k <= 64) return fm_sgd_ordered_kernel<32, 2, TASK>;
-  if (k <= 128) return fm_sgd_ordered_kernel<32, 4, TASK>;
+  if (k <= 2) return fm_sgd_ordered_kernel<1, 2, TASK>;
+  if (k <= 4) return fm_sgd_ordered_kernel<1, 4, TASK>;
+  if (k <= 8) return fm_sgd_ordered_kernel<1, 8, TASK>;
+  if (k <= 16) return fm_sgd_ordered_kernel<2, 8, TASK>;
+  if (k <= 32) return fm_sgd_ordered_kernel<4, 8, TASK>;
+  if (k <= 64) return fm_sgd_ordered_kernel<8, 8, TASK>;
+  if (k <= 128) return fm_sgd_ordered_kernel<16, 8, TASK>;
   return fm_sgd_ordered_kernel<32, 8, TASK>;
 }
 
@@ -200,14 +218,18 @@ cudaError_t launch_sgd_ordered(fmb200_ctx* c, DataSlot& d, bool* handled) {
   a.csr_bytes = ord_csr_bytes(TR, TE);
   a.rec_bytes = TE * (uint32_t)rs * 8u;
 
-  int threads = c->tune_threads ? c->tune_threads : 512;
+  int GL = 1, KF = 1;
+  ordered_shape(c->k, &GL, &KF);
+  // one group of GL lanes per example of a run: min(ORD_SMAX, 1024 / GL) examples
+  int threads = std::min(ORD_SMAX * GL, ORD_MAX_THREADS);
+  if (c->tune_threads)  // fewer threads = shorter runs (experiments); never more than the kernel is bounded for
+    threads = std::min(threads, std::max(32, (c->tune_threads / (32 > GL ? 32 : GL)) * (32 > GL ? 32 : GL)));
   OrdFn fn = c->hp.task == FMB200_TASK_REGRESSION ? pick_kernel<0>(c->k) : pick_kernel<1>(c->k);
   e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   fn<<<1, threads, smem, c->stream>>>(a);
   c->launches++;
-  c->last_cfg = EpochConfig{c->k <= 32 ? (c->k <= 1 ? 1 : (1 << (32 - __builtin_clz((unsigned)c->k - 1)))) : 32,
-                            ORD_SMAX, TR, 1, threads, (int)smem, 0};
+  c->last_cfg = EpochConfig{GL, std::min(ORD_SMAX, threads / GL), TR, 1, threads, (int)smem, 0};
   *handled = true;
   return cudaGetLastError();
 }

@@ -32,8 +32,12 @@
 //       entries (known from `link`) skip the fetch and read the record FORWARDED in shared
 //       memory: every write-back also lands in the writer's own ring slot.
 //
-// Thread mapping: GL lanes per example (GL = power of two covering k, at most 32; each
-// lane owns KF factors), 32/GL examples per warp, at most ORD_SMAX examples per run.
+// Thread mapping: GL lanes per example, each owning KF <= 8 CONSECUTIVE factors (k <= 8: one
+// lane per example, no cross-lane reduction at all), at most min(ORD_SMAX, 1024 / GL) examples
+// per run, blockDim = that many examples x GL.  The bias scan and the search for the next
+// run's length are done by warp 0 alone and published through shared memory: the r02 ncu capture
+// of the first version (every warp scanning redundantly, 8 lanes per example) showed an
+// ISSUE-bound kernel -- 204 warp instructions per row, 40% of them the 16 redundant scans.
 //
 // This header is also compiled for the host (tests/simt/: FMB_SIMT_HOST) and run thread
 // for thread against the sequential oracle.
@@ -46,9 +50,11 @@
 namespace fmb {
 
 constexpr uint32_t ORD_NONE = 0xffffffffu;
-constexpr int ORD_SMAX = 64;   // examples per run: 2 per lane in the bias scan
+constexpr int ORD_SMAX = 128;  // examples per run: ORD_EL per lane in the bias scan
+constexpr int ORD_EL = ORD_SMAX / 32;
 constexpr int ORD_NBUF = 3;    // ring depth (CSR stages and record buffers)
-constexpr int ORD_HDR_BYTES = 64 + ORD_SMAX * 8;  // [0,24) mbarriers | [64, 64+512) sR
+// [0,24) mbarriers | [32,36) next run length | [64, +1024) sR (scores) | [1088, +1024) sM (multipliers)
+constexpr int ORD_HDR_BYTES = 64 + 2 * ORD_SMAX * 8 + 64;
 constexpr int ORD_MAX_THREADS = 1024;
 
 struct OrderedArgs {
@@ -192,35 +198,62 @@ __device__ __forceinline__ int ord_state(double p, double lo, double hi, bool in
   return (p < lo) ? 1 : 0;
 }
 
-// first row (tile-relative) at which the run starting at t0 must stop
+// length of the run starting at tile-relative row t0 (executed by one whole warp): rows are
+// added while they depend on no row of the run (rd[r] = distance to the nearest earlier row
+// sharing a feature; 0 = the row names a feature twice and must run alone)
 __device__ __forceinline__ int ord_detect(const OrdStage& s, int t0, int nrows, int smax, int lane) {
-  bool c0, c1;
-  {
-    const int t = lane, r = t0 + t;
-    c0 = (t >= smax) || (r >= nrows);
-    if (!c0 && t > 0) c0 = s.rd[r] <= (uint32_t)t;
-    if (t == 0 && !c0 && s.rd[r] == 0u) c0 = false;
+  int P = smax;
+#pragma unroll
+  for (int q = ORD_EL - 1; q >= 0; q--) {
+    const int t = 32 * q + lane, r = t0 + t;
+    bool stop = (t >= smax) || (r >= nrows);
+    if (!stop && t > 0) stop = s.rd[r] <= (uint32_t)t;
+    const unsigned m = __ballot_sync(0xffffffffu, stop);
+    if (m) P = 32 * q + __ffs(m) - 1;
   }
-  {
-    const int t = 32 + lane, r = t0 + t;
-    c1 = (t >= smax) || (r >= nrows);
-    if (!c1) c1 = s.rd[r] <= (uint32_t)t;
-  }
-  const unsigned m0 = __ballot_sync(0xffffffffu, c0), m1 = __ballot_sync(0xffffffffu, c1);
-  int P = m0 ? (__ffs(m0) - 1) : (m1 ? 32 + __ffs(m1) - 1 : 64);
-  if (P < 1) P = 1;  // lane 0 never stops its own run (t0 < nrows is the caller's invariant)
+  if (P < 1) P = 1;
+  if (s.rd[t0] == 0u) P = 1;
   return P;
+}
+
+template <int KF>
+__device__ __forceinline__ void ord_load(const double* p, double (&v)[KF], int nvalid, bool vec) {
+  if (KF >= 2 && vec) {
+#pragma unroll
+    for (int q = 0; q < KF; q += 2) {
+      double2 t = make_double2(0.0, 0.0);
+      if (q < nvalid) t = *reinterpret_cast<const double2*>(p + q);
+      v[q] = t.x;
+      v[q + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < KF; q++) v[q] = (q < nvalid) ? p[q] : 0.0;
+  }
+}
+template <int KF>
+__device__ __forceinline__ void ord_store(double* p, const double (&v)[KF], int nvalid, bool vec) {
+  if (KF >= 2 && vec) {
+#pragma unroll
+    for (int q = 0; q < KF; q += 2)
+      if (q < nvalid) *reinterpret_cast<double2*>(p + q) = make_double2(v[q], v[q + 1]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < KF; q++)
+      if (q < nvalid) p[q] = v[q];
+  }
 }
 
 template <int GL, int KF, int TASK>
 __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigned char* smem) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
-  constexpr int EPW = 32 / GL;
-  const int gl = lane % GL;
-  const int grp = warp * EPW + lane / GL;  // example slot inside a run
-  const int smax = min(ORD_SMAX, (nthreads >> 5) * EPW);
+  const int gl = tid % GL;   // lane inside the example's group
+  const int grp = tid / GL;  // example slot inside a run
+  const int smax = min(ORD_SMAX, nthreads / GL);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  int* sP = reinterpret_cast<int*>(smem + 32);  // [2]: run lengths, double-buffered by run parity
   double* sR = reinterpret_cast<double*>(smem + 64);
+  double* sM = sR + ORD_SMAX;
   const unsigned full = 0xffffffffu;
 
   if (tid == 0) {
@@ -236,7 +269,10 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
   const bool inverted = hi < lo;
   const double a_mid = 1.0 - lr * (1.0 + reg0), a_out = 1.0 - lr * reg0;
   const uint32_t recb = (uint32_t)a.rs * 8u;
-  double w0 = k0 ? *a.w0 : 0.0;
+  const int f0 = gl * KF;                       // this lane's first factor
+  const int nf = max(0, min(KF, k - f0));       // ... and how many of its KF slots are real
+  const bool vec = ((k & 1) == 0) && (KF % 2 == 0);  // 16-byte aligned factor slices
+  double w0 = k0 ? *a.w0 : 0.0;                 // live in warp 0 only
   const uint32_t NT = a.n_tiles;
   const int TR = a.tile_rows;
 
@@ -273,17 +309,22 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
     }
     cp_async_commit();
     cp_async_wait_1();  // this thread's fetches for tile T have landed
-    __syncthreads();    // ... and everyone's; src[] of tile T is complete
-
     const OrdStage s = ord_stage(a, smem, T);
     const uint64_t r0 = (uint64_t)T * TR;
     const int nrows = (int)min((uint64_t)TR, a.n_rows - r0);
+    if (warp == 0) {  // length of the tile's first run (reads the CSR stage only: complete since the mbarrier)
+      const int P0 = ord_detect(s, 0, nrows, smax, lane);
+      if (lane == 0) sP[0] = P0;
+    }
+    __syncthreads();  // ... everyone's fetches; src[] of tile T; the first run length
+
     const uint64_t ab = s.rp[0] & ~3ull;
     const uint32_t rec = ord_rec_base(a, T);
 
     int t0 = 0;
-    int P = ord_detect(s, 0, nrows, smax, lane);
+    int pi = 0;  // parity of the run inside the tile
     while (t0 < nrows) {
+      const int P = sP[pi];
       // ---- scores of the run's examples: fm_model.h:105-127 with R_t = p_t - w0 ----------
       const bool act = grp < P;
       const int r = t0 + grp;
@@ -304,26 +345,22 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
           uint32_t jj = j;
           if (rowdup)  // a feature named twice: both entries score with the value before the row
             while (s.link[jj] != ORD_NONE && s.link[jj] <= jj - jb) jj -= s.link[jj];
-          const unsigned char* rp_ = smem + s.src[jj];
+          const double* rp_ = reinterpret_cast<const double*>(smem + s.src[jj]);
           const uint32_t id = s.col[j];
           const double x = (double)s.val[j];
           const uint32_t vo = (k & 1) ? (id & 1u) : 0u;
-          const double* vr = reinterpret_cast<const double*>(rp_) + vo;
+          double vv[KF];
+          ord_load<KF>(rp_ + vo + f0, vv, nf, vec);
 #pragma unroll
           for (int q = 0; q < KF; q++) {
-            const int f = gl + q * GL;
-            if (f < k) {
-              const double d = vr[f] * x;
-              sum[q] += d;
-              ssq[q] += d * d;
-            }
+            const double d = vv[q] * x;  // slots beyond k hold 0
+            sum[q] += d;
+            ssq[q] += d * d;
           }
-          if (k1 && (int)((j - jb) % GL) == gl)
-            Rloc += reinterpret_cast<const double*>(rp_)[kw + (id & 1u)] * x;
+          if (k1 && (int)((j - jb) % GL) == gl) Rloc += rp_[kw + (id & 1u)] * x;
         }
 #pragma unroll
-        for (int q = 0; q < KF; q++)
-          if (gl + q * GL < k) Rloc += 0.5 * (sum[q] * sum[q] - ssq[q]);
+        for (int q = 0; q < KF; q++) Rloc += 0.5 * (sum[q] * sum[q] - ssq[q]);
       }
 #pragma unroll
       for (int o = GL / 2; o > 0; o >>= 1) Rloc += ord_shfl_xor(Rloc, o);
@@ -333,69 +370,91 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
       if (k0) {
         if (act && gl == 0) sR[grp] = Rloc;
         __syncthreads();
-        if (TASK == 0) {
-          // ---- bias: affine prefix scan over the run, every warp redundantly ---------------
-          const int ta = 2 * lane, tb = ta + 1;
-          const bool va = ta < P, vb = tb < P;
-          const double Ra = va ? sR[ta] : 0.0, Rb = vb ? sR[tb] : 0.0;
-          const double ya = va ? (double)s.tg[t0 + ta] : 0.0, yb = vb ? (double)s.tg[t0 + tb] : 0.0;
-          int sa = ord_state(w0 + Ra, lo, hi, inverted), sb = ord_state(w0 + Rb, lo, hi, inverted);
-          double w0a = w0, w0b = w0, A = 1.0, B = 0.0;
-          for (int it = 0; it <= 2 * ORD_SMAX; it++) {
-            const double aa = va ? (sa == 0 ? a_mid : a_out) : 1.0;
-            const double ba = va ? -lr * ((sa == 0 ? Ra : (sa == 1 ? lo : hi)) - ya) : 0.0;
-            const double ab_ = vb ? (sb == 0 ? a_mid : a_out) : 1.0;
-            const double bb = vb ? -lr * ((sb == 0 ? Rb : (sb == 1 ? lo : hi)) - yb) : 0.0;
-            A = ab_ * aa;  // w0 -> ab_*(aa*w0 + ba) + bb
-            B = ab_ * ba + bb;
+        if (warp == 0) {
+          if (TASK == 0) {
+            // ---- bias: affine prefix scan over the run (lane l owns examples EL*l ..) --------
+            double R[ORD_EL], y[ORD_EL], aa[ORD_EL], bb[ORD_EL], wv[ORD_EL];
+            int st[ORD_EL];
+            bool on[ORD_EL];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              const double Ap = ord_shfl_up(A, o), Bp = ord_shfl_up(B, o);
-              if (lane >= o) {
-                B = A * Bp + B;
-                A = A * Ap;
+            for (int e = 0; e < ORD_EL; e++) {
+              const int t = ORD_EL * lane + e;
+              on[e] = t < P;
+              R[e] = on[e] ? sR[t] : 0.0;
+              y[e] = on[e] ? (double)s.tg[t0 + t] : 0.0;
+              st[e] = ord_state(w0 + R[e], lo, hi, inverted);
+            }
+            double A = 1.0, B = 0.0;
+            for (int it = 0; it <= 2 * ORD_SMAX; it++) {
+              A = 1.0;
+              B = 0.0;
+#pragma unroll
+              for (int e = 0; e < ORD_EL; e++) {
+                aa[e] = on[e] ? (st[e] == 0 ? a_mid : a_out) : 1.0;
+                bb[e] = on[e] ? -lr * ((st[e] == 0 ? R[e] : (st[e] == 1 ? lo : hi)) - y[e]) : 0.0;
+                B = aa[e] * B + bb[e];  // w -> aa*(A w + B) + bb
+                A = aa[e] * A;
               }
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) {
+                const double Ap = ord_shfl_up(A, o), Bp = ord_shfl_up(B, o);
+                if (lane >= o) {
+                  B = A * Bp + B;
+                  A = A * Ap;
+                }
+              }
+              double Ae = ord_shfl_up(A, 1), Be = ord_shfl_up(B, 1);
+              if (lane == 0) {
+                Ae = 1.0;
+                Be = 0.0;
+              }
+              double w = Ae * w0 + Be;
+              bool bad = false;
+#pragma unroll
+              for (int e = 0; e < ORD_EL; e++) {
+                wv[e] = w;  // the bias example e reads
+                const int ns = ord_state(w + R[e], lo, hi, inverted);
+                bad = bad || (on[e] && ns != st[e]);
+                st[e] = ns;
+                w = aa[e] * w + bb[e];
+              }
+              if (!__any_sync(full, bad)) break;
             }
-            double Ae = ord_shfl_up(A, 1), Be = ord_shfl_up(B, 1);
-            if (lane == 0) {
-              Ae = 1.0;
-              Be = 0.0;
+            // fm_learn_sgd_element.h:58-62: mult = -(y - clamp(p))
+#pragma unroll
+            for (int e = 0; e < ORD_EL; e++)
+              if (on[e]) sM[ORD_EL * lane + e] = (st[e] == 0 ? wv[e] + R[e] : (st[e] == 1 ? lo : hi)) - y[e];
+            w0 = ord_shfl(A, 31) * w0 + ord_shfl(B, 31);
+          } else {
+            // ---- classification: the chain walked serially (fm_learn_sgd_element.h:63-64) ----
+            for (int t = 0; t < P; t++) {
+              const double y = (double)s.tg[t0 + t];
+              const double p = w0 + sR[t];
+              const double m = -y * (1.0 - 1.0 / (1.0 + exp(-y * p)));
+              if (lane == (t & 31)) sM[t] = m;
+              w0 -= lr * (m + reg0 * w0);
             }
-            w0a = Ae * w0 + Be;
-            w0b = aa * w0a + ba;
-            const int na = ord_state(w0a + Ra, lo, hi, inverted);
-            const int nb_ = ord_state(w0b + Rb, lo, hi, inverted);
-            const bool bad = (va && na != sa) || (vb && nb_ != sb);
-            sa = na;
-            sb = nb_;
-            if (!__any_sync(full, bad)) break;
           }
-          // fm_learn_sgd_element.h:58-62: mult = -(y - clamp(p))
-          const double ma = (sa == 0 ? w0a + Ra : (sa == 1 ? lo : hi)) - ya;
-          const double mb = (sb == 0 ? w0b + Rb : (sb == 1 ? lo : hi)) - yb;
-          w0 = ord_shfl(A, 31) * w0 + ord_shfl(B, 31);
-          const double m0 = ord_shfl(ma, (grp >> 1) & 31), m1 = ord_shfl(mb, (grp >> 1) & 31);
-          mult = (grp & 1) ? m1 : m0;
-        } else {
-          // ---- classification: the chain walked serially (fm_learn_sgd_element.h:63-64) ----
-          for (int t = 0; t < P; t++) {
-            const double y = (double)s.tg[t0 + t];
-            const double p = w0 + sR[t];
-            const double m = -y * (1.0 - 1.0 / (1.0 + exp(-y * p)));
-            if (t == grp) mult = m;
-            w0 -= lr * (m + reg0 * w0);
+          const int Pn = (t0n < nrows) ? ord_detect(s, t0n, nrows, smax, lane) : 1;
+          if (lane == 0) sP[pi ^ 1] = Pn;
+        }
+        __syncthreads();
+        if (act) mult = sM[grp];
+      } else {
+        if (act) {
+          const double y = (double)s.tg[r];
+          if (TASK == 0) {
+            const int st = ord_state(Rloc, lo, hi, inverted);
+            mult = (st == 0 ? Rloc : (st == 1 ? lo : hi)) - y;
+          } else {
+            mult = -y * (1.0 - 1.0 / (1.0 + exp(-y * Rloc)));
           }
         }
-      } else if (act) {
-        const double y = (double)s.tg[r];
-        if (TASK == 0) {
-          const int st = ord_state(Rloc, lo, hi, inverted);
-          mult = (st == 0 ? Rloc : (st == 1 ? lo : hi)) - y;
-        } else {
-          mult = -y * (1.0 - 1.0 / (1.0 + exp(-y * Rloc)));
+        if (warp == 0) {  // the other parity: a slower warp may still be reading this run's length
+          const int Pn = (t0n < nrows) ? ord_detect(s, t0n, nrows, smax, lane) : 1;
+          if (lane == 0) sP[pi ^ 1] = Pn;
         }
       }
-      const int Pn = (t0n < nrows) ? ord_detect(s, t0n, nrows, smax, lane) : 1;
 
       // ---- fm_SGD (fm_sgd.h:38-50) for the lane's example: own ring slot + global ----------
       if (act) {
@@ -409,37 +468,32 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
           }
           // a repeated feature continues from the row's previous write (fm_sgd.h:46 reads v again)
           const uint32_t so = dupj ? rec + (j - s.link[j]) * recb : s.src[jj];
-          const unsigned char* rp_ = smem + so;
-          unsigned char* own = smem + rec + j * recb;
+          const double* rp_ = reinterpret_cast<const double*>(smem + so);
+          double* own = reinterpret_cast<double*>(smem + rec + j * recb);
           const uint32_t id = s.col[j];
           const double x = (double)s.val[j];
           const uint32_t vo = (k & 1) ? (id & 1u) : 0u;
-          const double* vr = reinterpret_cast<const double*>(rp_) + vo;
-          double* vown = reinterpret_cast<double*>(own) + vo;
-          double* gv = a.v + (size_t)id * k;
+          double c[KF];
+          ord_load<KF>(rp_ + vo + f0, c, nf, vec);
 #pragma unroll
           for (int q = 0; q < KF; q++) {
-            const int f = gl + q * GL;
-            if (f < k) {
-              double c = vr[f];
-              const double grad = sum[q] * x - c * x * x;
-              c -= lr * (mult * grad + regv * c);
-              vown[f] = c;
-              gv[f] = c;
-            }
+            const double grad = sum[q] * x - c[q] * x * x;
+            c[q] -= lr * (mult * grad + regv * c[q]);
           }
+          ord_store<KF>(own + vo + f0, c, nf, vec);
+          ord_store<KF>(a.v + (size_t)id * k + f0, c, nf, vec);
           const bool mine = rowdup ? (gl == 0) : ((int)((j - jb) % GL) == gl);
           if (k1 && mine) {
-            double c = reinterpret_cast<const double*>(rp_)[kw + (id & 1u)];
-            c -= lr * (mult * x + regw * c);
-            reinterpret_cast<double*>(own)[kw + (id & 1u)] = c;
-            a.w[id] = c;
+            double cw = rp_[kw + (id & 1u)];
+            cw -= lr * (mult * x + regw * cw);
+            own[kw + (id & 1u)] = cw;
+            a.w[id] = cw;
           }
         }
       }
-      __syncthreads();  // the run's ring slots are final before the next run reads them
+      __syncthreads();  // the run's ring slots (and the next length) are final before the next run reads them
       t0 = t0n;
-      P = Pn;
+      pi ^= 1;
     }
   }
   if (tid == 0 && k0) *a.w0 = w0;

@@ -1,6 +1,6 @@
 """Turn gpurun_out/*.ncu-rep / launch CSVs into the small tracked summaries under profiles/.
 
-    python scripts/summarize_ncu.py <round-tag> <launch_csv> <ncu-rep> [traffic_json_name]
+    python scripts/summarize_ncu.py <round-tag> <launch_csv | -> <ncu-rep> [traffic_json_name]
 """
 import csv
 import json
@@ -17,7 +17,7 @@ os.makedirs(out_dir, exist_ok=True)
 lines = ["# %s -- ncu summary" % tag, ""]
 
 # ---- launch list (cold-cache, serialised: compare SHARES, not absolutes) ----
-rows = [r for r in csv.reader(open(launches_csv)) if r and not r[0].startswith("==")]
+rows = [r for r in csv.reader(open(launches_csv)) if r and not r[0].startswith("==")] if launches_csv != "-" else [[]]
 hdr = rows[0]
 ci = {h: i for i, h in enumerate(hdr)}
 agg = OrderedDict()
@@ -31,12 +31,13 @@ for r in rows[1:]:
     a = agg.setdefault(name, [0, 0.0])
     a[0] += 1
     a[1] += v_us
-tot = sum(a[1] for a in agg.values())
-lines += ["## launch list of `%s` (gpu__time_duration.sum, --clock-control none)" % os.path.basename(launches_csv), "",
+tot = sum(a[1] for a in agg.values()) or 1.0
+if launches_csv != "-":
+  lines += ["## launch list of `%s` (gpu__time_duration.sum, --clock-control none)" % os.path.basename(launches_csv), "",
           "| kernel | launches | total us | share | avg us |", "|---|---:|---:|---:|---:|"]
-for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+  for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     lines.append("| `%s` | %d | %.1f | %.1f%% | %.1f |" % (name, n, us, 100 * us / tot, us / n))
-lines.append("")
+  lines.append("")
 
 # ---- full capture of the dominant kernel ----
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout

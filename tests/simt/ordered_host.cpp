@@ -133,13 +133,13 @@ void run_threads(const fmb::OrderedArgs& a, unsigned char* smem, int task, int n
 
 void dispatch(int k, const fmb::OrderedArgs& a, unsigned char* smem, int task, int nthreads) {
   if (k <= 1) run_threads<1, 1>(a, smem, task, nthreads);
-  else if (k <= 2) run_threads<2, 1>(a, smem, task, nthreads);
-  else if (k <= 4) run_threads<4, 1>(a, smem, task, nthreads);
-  else if (k <= 8) run_threads<8, 1>(a, smem, task, nthreads);
-  else if (k <= 16) run_threads<16, 1>(a, smem, task, nthreads);
-  else if (k <= 32) run_threads<32, 1>(a, smem, task, nthreads);
-  else if (k <= 64) run_threads<32, 2>(a, smem, task, nthreads);
-  else if (k <= 128) run_threads<32, 4>(a, smem, task, nthreads);
+  else if (k <= 2) run_threads<1, 2>(a, smem, task, nthreads);
+  else if (k <= 4) run_threads<1, 4>(a, smem, task, nthreads);
+  else if (k <= 8) run_threads<1, 8>(a, smem, task, nthreads);
+  else if (k <= 16) run_threads<2, 8>(a, smem, task, nthreads);
+  else if (k <= 32) run_threads<4, 8>(a, smem, task, nthreads);
+  else if (k <= 64) run_threads<8, 8>(a, smem, task, nthreads);
+  else if (k <= 128) run_threads<16, 8>(a, smem, task, nthreads);
   else run_threads<32, 8>(a, smem, task, nthreads);
 }
 
