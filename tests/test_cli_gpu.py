@@ -146,3 +146,25 @@ def test_reference_main_with_b200_learner(c1_files, task, fmt):
     val = lambda l: [float(t.split("=")[1]) for t in l.split("\t") if t.startswith(("Train", "Test"))]  # noqa: E731
     a, b = val(_iters(hw.stdout)[-1]), val(_iters(ref.stdout)[-1])
     assert abs(a[0] - b[0]) < 0.05 and abs(a[1] - b[1]) < 0.05, (a, b)
+
+
+@pytest.mark.parametrize("method", ["mcmc", "als"])
+def test_reference_mcmc_with_b200_eterm_pass(c1_files, method):
+    """SURVEY section 8 f3 through the reference's own main(): integration/fm_mcmc_eterms_b200.h swaps the
+    two call sites of fm_learn_mcmc::predict_data_and_write_to_eterms (fm_learn_mcmc_simultaneous.h:69,122)
+    for fmb200_mcmc_eterms.  The e-terms are bit-identical, the Gibbs draws are the reference's own code with
+    the same rand() stream: every #Iter= line and the -out file equal the stock binary's."""
+    _need()
+    if not os.path.exists(REF_CLI_B200):
+        pytest.skip("oracle/_ref/libFM_b200 not built")
+    base = ["-task", "r", "-train", "train.libfm", "-test", "test.libfm", "-method", method, "-dim", "1,1,8",
+            "-iter", "5", "-init_stdev", "0.1", "-seed", "42"]
+    ref = _run(REF_CLI, base + ["-out", "m_ref.txt"], c1_files)
+    assert ref.returncode == 0, ref.stderr
+    env = dict(os.environ, FMB200_MCMC_ETERMS="1")
+    ours = subprocess.run([REF_CLI_B200] + base + ["-out", "m_b200.txt"], capture_output=True, text=True,
+                          cwd=c1_files, timeout=600, env=env)
+    assert ours.returncode == 0 and "ERROR" not in ours.stderr, ours.stderr
+    assert _iters(ours.stdout) == _iters(ref.stdout) and len(_iters(ref.stdout)) >= 5
+    rd = lambda f: open(os.path.join(c1_files, f)).read()  # noqa: E731
+    assert rd("m_b200.txt") == rd("m_ref.txt")
