@@ -535,6 +535,7 @@ int fmb200_set_params(fmb200_ctx* c, double w0, const double* w, const double* v
     CK(cudaMemcpyAsync(c->p32.base, h32.data(), h32.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->peer_base_valid = false;
+    c->hogwild_fresh = true;
     return 0;
   });
 }

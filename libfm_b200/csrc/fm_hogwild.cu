@@ -437,6 +437,28 @@ static cudaError_t launch_rowlane(fmb200_ctx* c, const DataSlot& d, bool* handle
   a.w0_conc = (float)std::min<double>((double)d.n_rows, (double)grid * TR * (ws ? HW_NSTAGE : 1));
   // park a feature in the CTA's hot table when it is expected at least twice per tile
   a.hot_thr = (float)std::max(4.0, 2.0 * (double)d.n_rows / (double)TR);
+  // First epoch after the state was (re)set: the bias starts far from its equilibrium (w0 = 0 against a
+  // target mean of ~3.5 on ratings) and a window of grid*TR rows would all be scored with that bias -- the
+  // sequential loop corrects it within its first few hundred rows (fm_sgd.h:34-37: 1 - lr per row).  So
+  // the first kRampTiles tiles run on ONE CTA (window = one tile: the bias contracts as in the sequential
+  // loop), the rest on the full grid.  Costs ~40 us once; the epoch-0 RMSE gap to the oracle drops by an
+  // order of magnitude.
+  constexpr uint64_t kRampTiles = 4;
+  if (c->hogwild_fresh && c->k0 && c->tune_damp >= 0 && n_tiles > 8 * kRampTiles) {
+    HogwildArgs r = a;
+    r.n_rows = kRampTiles * (uint64_t)TR;
+    r.n_tiles = (uint32_t)kRampTiles;
+    r.conc_scale = (float)((double)TR / (double)d.n_rows);
+    r.w0_conc = (float)TR;
+    fn<<<1, launch_threads, smem_ws, c->stream>>>(r);
+    c->launches++;
+    const uint64_t skip = kRampTiles * (uint64_t)TR;  // a multiple of 32: TMA source alignment holds
+    a.row_ptr += skip;
+    a.target += skip;
+    a.n_rows -= skip;
+    a.n_tiles = (uint32_t)(n_tiles - kRampTiles);
+  }
+  c->hogwild_fresh = false;
   fn<<<grid, launch_threads, smem_ws, c->stream>>>(a);
   c->launches++;
   c->last_cfg = EpochConfig{1, (int)std::max<uint32_t>(1, d.max_row_nnz), TR, grid, launch_threads, smem_ws, damp ? 1 : 0};

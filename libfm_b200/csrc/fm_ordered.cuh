@@ -30,7 +30,8 @@
 //       (L2 -> shared, 16 B) into a 3-deep ring of record buffers.  A record fetched that
 //       early is stale if its feature is written by tile T or T+1 itself; exactly those
 //       entries (known from `link`) skip the fetch and read the record FORWARDED in shared
-//       memory: every write-back also lands in the writer's own ring slot.
+//       memory: every fm_SGD result lands in the writer's own ring slot, and the tile's final
+//       records are written back to global memory in one pass at the end of the tile.
 //
 // Thread mapping: GL lanes per example, each owning KF <= 8 CONSECUTIVE factors (k <= 8: one
 // lane per example, no cross-lane reduction at all), at most min(ORD_SMAX, 1024 / GL) examples
@@ -79,6 +80,7 @@ struct OrderedArgs {
   double lr, reg0, regw, regv, min_target, max_target;
   uint32_t csr_bytes;  // one CSR stage
   uint32_t rec_bytes;  // one record buffer = tile_cap * rs * 8
+  int debug;           // timing experiments only (results become wrong): 1 = no write-back to global
 };
 
 // ---- shared-memory layout (host and device agree through these) -------------------------
@@ -86,7 +88,8 @@ struct OrderedArgs {
 __host__ __device__ inline uint32_t ord_rp_bytes(int TR) { return ((uint32_t)(TR + 2) * 8u + 15u) & ~15u; }
 __host__ __device__ inline uint32_t ord_row_bytes(int TR) { return ((uint32_t)(TR + 4) * 4u + 15u) & ~15u; }
 __host__ __device__ inline uint32_t ord_csr_bytes(int TR, uint32_t TE) {
-  return ord_rp_bytes(TR) + 2u * ord_row_bytes(TR) + 4u * TE * 4u;
+  // rp | target | rowdep | col | val | link | src | superseded (1 byte per entry, TE is a multiple of 4)
+  return ord_rp_bytes(TR) + 2u * ord_row_bytes(TR) + 4u * TE * 4u + ((TE + 15u) & ~15u);
 }
 __host__ __device__ inline size_t ord_smem_bytes(int TR, uint32_t TE, int rs) {
   return (size_t)ORD_HDR_BYTES + (size_t)ORD_NBUF * ord_csr_bytes(TR, TE) +
@@ -101,6 +104,7 @@ struct OrdStage {  // views into one CSR stage
   const float* val;
   const uint32_t* link;
   uint32_t* src;          // byte offset (from the smem base) of the record each entry reads
+  unsigned char* sup;     // 1 = a later entry of the SAME tile rewrites this feature (no write-back)
 };
 
 __device__ __forceinline__ OrdStage ord_stage(const OrderedArgs& a, unsigned char* smem, uint32_t tile) {
@@ -116,6 +120,7 @@ __device__ __forceinline__ OrdStage ord_stage(const OrderedArgs& a, unsigned cha
   s.val = reinterpret_cast<const float*>(e + (size_t)a.tile_cap * 4);
   s.link = reinterpret_cast<const uint32_t*>(e + (size_t)a.tile_cap * 8);
   s.src = reinterpret_cast<uint32_t*>(e + (size_t)a.tile_cap * 12);
+  s.sup = e + (size_t)a.tile_cap * 16;
   return s;
 }
 
@@ -166,13 +171,17 @@ __device__ __forceinline__ void ord_prep(const OrderedArgs& a, unsigned char* sm
   const uint32_t rec = ord_rec_base(a, tile), recp = ord_rec_base(a, tile + ORD_NBUF - 1);
   const uint32_t recb = (uint32_t)a.rs * 8u;
   const int k = a.k, kw = a.kw;
+  for (uint32_t j = j0 + tid; j < j1; j += nthreads) s.sup[j] = 0;
+  __syncthreads();  // (all threads call ord_prep together)
   for (uint32_t j = j0 + tid; j < j1; j += nthreads) {
     const uint32_t L = s.link[j];
     const uint64_t e = ab + j;
     uint32_t src = rec + j * recb;
     if (L != ORD_NONE && (uint64_t)L <= e - E0p) {  // previous writer is inside the window
-      if (L <= j - j0) src = rec + (j - L) * recb;                          // this tile
-      else src = recp + (uint32_t)((e - L) - abp) * recb;                   // the previous tile
+      if (L <= j - j0) {  // this tile: that entry's value never needs to reach global memory
+        src = rec + (j - L) * recb;
+        s.sup[j - L] = 1;
+      } else src = recp + (uint32_t)((e - L) - abp) * recb;                 // the previous tile
     } else {
       const uint32_t id = s.col[j];
       const uint32_t vo = (k & 1) ? (id & 1u) : 0u;
@@ -481,13 +490,11 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
             c[q] -= lr * (mult * grad + regv * c[q]);
           }
           ord_store<KF>(own + vo + f0, c, nf, vec);
-          ord_store<KF>(a.v + (size_t)id * k + f0, c, nf, vec);
           const bool mine = rowdup ? (gl == 0) : ((int)((j - jb) % GL) == gl);
           if (k1 && mine) {
             double cw = rp_[kw + (id & 1u)];
             cw -= lr * (mult * x + regw * cw);
             own[kw + (id & 1u)] = cw;
-            a.w[id] = cw;
           }
         }
       }
@@ -495,6 +502,41 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
       t0 = t0n;
       pi ^= 1;
     }
+    // ---- write-back: the tile's FINAL records go to global memory in one pass.  Per-update stores
+    // made every run's barrier wait for their acknowledgement (r02 ncu: half of all stall samples on
+    // the barriers, 5 200 cycles per run); an entry whose feature is rewritten later in this tile
+    // (sup) never needs to leave the SM.  The next tile's fetches are issued behind the barrier of
+    // ord_prep, i.e. after these stores.
+    if (!(a.debug & 1)) {
+      const uint32_t j0 = (uint32_t)(s.rp[0] - ab), j1 = (uint32_t)(s.rp[nrows] - ab);
+      if ((k & 1) == 0) {
+        // consecutive threads write consecutive 16-byte pieces of one record: coalesced rows
+        const uint32_t pieces = (uint32_t)(kw / 2) + 1u;  // kw/2 factor pairs + the linear weight
+        const uint32_t total = (j1 - j0) * pieces;
+        for (uint32_t i = tid; i < total; i += nthreads) {
+          const uint32_t j = j0 + i / pieces, pc = i % pieces;
+          if (s.sup[j]) continue;
+          const double* own = reinterpret_cast<const double*>(smem + rec + j * recb);
+          const uint32_t id = s.col[j];
+          if (pc < pieces - 1u) {
+            *reinterpret_cast<double2*>(a.v + (size_t)id * k + 2u * pc) = *reinterpret_cast<const double2*>(own + 2u * pc);
+          } else if (k1) {
+            a.w[id] = own[kw + (id & 1u)];
+          }
+        }
+      } else {
+        for (uint32_t j = j0 + tid; j < j1; j += nthreads) {
+          if (s.sup[j]) continue;
+          const double* own = reinterpret_cast<const double*>(smem + rec + j * recb);
+          const uint32_t id = s.col[j];
+          const uint32_t vo = id & 1u;
+          double* gv = a.v + (size_t)id * k;
+          for (int q = 0; q < k; q++) gv[q] = own[vo + q];
+          if (k1) a.w[id] = own[kw + (id & 1u)];
+        }
+      }
+    }
+    __syncthreads();  // stage T%3 is read above and refilled by the TMA issue at the top of tile T+1
   }
   if (tid == 0 && k0) *a.w0 = w0;
 }

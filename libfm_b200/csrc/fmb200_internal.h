@@ -109,6 +109,7 @@ struct fmb200_ctx {
   // behind the two state buffers: theta0 (comm_buf_bytes) | counts (comm_cnt_floats) | |V|^2 partials (2 x 512)
   size_t comm_cnt_floats = 0;
   bool peer_base_valid = false;  // theta0 holds the state the running epoch started from
+  bool hogwild_fresh = true;     // no HOGWILD epoch has run since the state was last set (bias ramp)
   int peer_part_cur = 0, peer_n_part = 0;
   unsigned char* peer_base[FMB200_MAX_PEERS] = {nullptr};
   bool peer_ipc[FMB200_MAX_PEERS] = {false};

@@ -227,6 +227,7 @@ bool run_case(const Case& c) {
   a.max_target = c.task == 0 ? 5.0 : 1.0;
   a.csr_bytes = fmb::ord_csr_bytes(TR, TE);
   a.rec_bytes = TE * (uint32_t)rs * 8u;
+  a.debug = 0;
 
   const int epochs = 2;
   for (int ep = 0; ep < epochs; ep++) {
