@@ -349,7 +349,13 @@ def run_gpu_arm(args):
             else:
                 collective = "nccl"
         if collective == "nccl":
+            # fallback exchange through torch.distributed: the same mean-field rule as the peer kernel
+            # (libfm_b200/dist.py::combine_meanfield_), or the plain mean with --exchange mean
+            from libfm_b200 import dist as fdist
             params = torch.as_tensor(_DevBuf(ptr, n_floats), device=torch.device("cuda", local_rank))
+            theta0 = params.clone()
+            counts_t = torch.as_tensor(np.bincount(data.col, minlength=n).astype(np.float32), device=params.device)
+            layout = lrn.params_layout()
 
     # the combine rule of the peer exchange: mean-field weighted delta sum (default) or plain mean
     peer_exchange = lib.fmb200_allreduce_meanfield if args.exchange == "meanfield" else lib.fmb200_allreduce_mean
@@ -359,10 +365,17 @@ def run_gpu_arm(args):
         if rc == 0 and collective == "p2p":
             rc = peer_exchange(ctx)
         elif rc == 0 and collective == "nccl":
-            dist.all_reduce(params)  # sum over ranks on the library's stream
-            rc = lib.fmb200_scale_params(ctx, 1.0 / world)
+            rc = nccl_exchange()
         if rc != 0:
             raise RuntimeError(lib.fmb200_last_error().decode())
+
+    def nccl_exchange():
+        if args.exchange == "mean":
+            dist.all_reduce(params)  # sum over ranks on the library's stream
+            return lib.fmb200_scale_params(ctx, 1.0 / world)
+        fdist.combine_meanfield_(params, theta0, counts_t, data.num_cases, layout, LEARN_RATE, world=world)
+        theta0.copy_(params)
+        return 0
 
     def barrier():
         if world > 1:
@@ -440,8 +453,7 @@ def run_gpu_arm(args):
             rc = peer_exchange(ctx)
         elif exchange and rc == 0 and collective == "nccl":
             with torch.cuda.stream(stream):
-                dist.all_reduce(params)
-            rc = lib.fmb200_scale_params(ctx, 1.0 / world)
+                rc = nccl_exchange()
         if rc == 0:
             rc = lib.fmb200_get_params(ctx, C.byref(w0), P(w_out, C.c_double), P(v_out, C.c_double))
         if rc != 0:

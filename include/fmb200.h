@@ -155,6 +155,8 @@ int fmb200_sgda_get_reg(fmb200_ctx* ctx, double* reg_w, double* reg_v);
  * (NCCL) and calls fmb200_scale_params(1/G).  Both run on fmb200_stream(). */
 int fmb200_params_device(fmb200_ctx* ctx, void** device_ptr, uint64_t* n_floats);
 int fmb200_scale_params(fmb200_ctx* ctx, double factor);
+/* geometry of the packed fp32 state: w0 at [0], w[i] at [off_w + i*ws], V[i][f] at [off_v + i*kp + f] */
+int fmb200_params_layout(fmb200_ctx* ctx, uint64_t* off_w, int* ws, uint64_t* off_v, int* kp);
 int fmb200_stream(fmb200_ctx* ctx, void** cuda_stream);
 
 /* The same exchange without NCCL, over NVLink peer memory: every rank maps the

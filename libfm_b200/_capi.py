@@ -47,6 +47,7 @@ SYMBOLS = {
     "fmb200_mcmc_eterms": (C.c_int, [_ctx, C.c_int, _f64p]),
     "fmb200_params_device": (C.c_int, [_ctx, C.POINTER(C.c_void_p), _u64p]),
     "fmb200_scale_params": (C.c_int, [_ctx, C.c_double]),
+    "fmb200_params_layout": (C.c_int, [_ctx, _u64p, _intp, _u64p, _intp]),
     "fmb200_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),
     "fmb200_peer_export": (C.c_int, [_ctx, C.c_void_p]),
     "fmb200_peer_attach_ipc": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_void_p]),

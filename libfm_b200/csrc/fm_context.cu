@@ -801,6 +801,15 @@ int fmb200_params_device(fmb200_ctx* c, void** device_ptr, uint64_t* n_floats) {
   return 0;
 }
 
+int fmb200_params_layout(fmb200_ctx* c, uint64_t* off_w, int* ws, uint64_t* off_v, int* kp) {
+  NEED_CTX(c);
+  if (off_w) *off_w = c->p32.off_w;
+  if (ws) *ws = c->p32.ws;
+  if (off_v) *off_v = c->p32.off_v;
+  if (kp) *kp = c->kp;
+  return 0;
+}
+
 int fmb200_scale_params(fmb200_ctx* c, double factor) {
   NEED_CTX(c);
   if (c->mode != FMB200_MODE_HOGWILD) return fail("scale_params applies to the HOGWILD state");

@@ -253,6 +253,70 @@ __device__ __forceinline__ void ord_store(double* p, const double (&v)[KF], int 
   }
 }
 
+// The bias chain of one run, regression (executed by ONE warp): EL consecutive examples per lane
+// (EL*32 >= P).  Returns the bias after the run; sM[t] receives example t's multiplier
+// (fm_learn_sgd_element.h:58-62: mult = -(y - clamp(w0_t + R_t))).
+struct OrdBias {
+  double lr, lo, hi, a_mid, a_out;
+  bool inverted;
+};
+template <int EL>
+__device__ __forceinline__ double ord_bias_scan(const OrdBias& c, double w0, int P, const double* sR,
+                                                const float* tg, double* sM, int lane) {
+  const unsigned full = 0xffffffffu;
+  double R[EL], y[EL], aa[EL], bb[EL], wv[EL];
+  int st[EL];
+  bool on[EL];
+#pragma unroll
+  for (int e = 0; e < EL; e++) {
+    const int t = EL * lane + e;
+    on[e] = t < P;
+    R[e] = on[e] ? sR[t] : 0.0;
+    y[e] = on[e] ? (double)tg[t] : 0.0;
+    st[e] = ord_state(w0 + R[e], c.lo, c.hi, c.inverted);
+  }
+  double A = 1.0, B = 0.0;
+  for (int it = 0; it <= 2 * ORD_SMAX; it++) {
+    A = 1.0;
+    B = 0.0;
+#pragma unroll
+    for (int e = 0; e < EL; e++) {
+      aa[e] = on[e] ? (st[e] == 0 ? c.a_mid : c.a_out) : 1.0;
+      bb[e] = on[e] ? -c.lr * ((st[e] == 0 ? R[e] : (st[e] == 1 ? c.lo : c.hi)) - y[e]) : 0.0;
+      B = aa[e] * B + bb[e];  // w -> aa*(A w + B) + bb
+      A = aa[e] * A;
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double Ap = ord_shfl_up(A, o), Bp = ord_shfl_up(B, o);
+      if (lane >= o) {
+        B = A * Bp + B;
+        A = A * Ap;
+      }
+    }
+    double Ae = ord_shfl_up(A, 1), Be = ord_shfl_up(B, 1);
+    if (lane == 0) {
+      Ae = 1.0;
+      Be = 0.0;
+    }
+    double w = Ae * w0 + Be;
+    bool bad = false;
+#pragma unroll
+    for (int e = 0; e < EL; e++) {
+      wv[e] = w;  // the bias example e reads
+      const int ns = ord_state(w + R[e], c.lo, c.hi, c.inverted);
+      bad = bad || (on[e] && ns != st[e]);
+      st[e] = ns;
+      w = aa[e] * w + bb[e];
+    }
+    if (!__any_sync(full, bad)) break;
+  }
+#pragma unroll
+  for (int e = 0; e < EL; e++)
+    if (on[e]) sM[EL * lane + e] = (st[e] == 0 ? wv[e] + R[e] : (st[e] == 1 ? c.lo : c.hi)) - y[e];
+  return ord_shfl(A, 31) * w0 + ord_shfl(B, 31);
+}
+
 template <int GL, int KF, int TASK>
 __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigned char* smem) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
@@ -263,7 +327,7 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
   int* sP = reinterpret_cast<int*>(smem + 32);  // [2]: run lengths, double-buffered by run parity
   double* sR = reinterpret_cast<double*>(smem + 64);
   double* sM = sR + ORD_SMAX;
-  const unsigned full = 0xffffffffu;
+  const int dwarp = nthreads > 32 ? 1 : 0;  // the warp that searches the next run
 
   if (tid == 0) {
     for (int i = 0; i < ORD_NBUF; i++) mbar_init(bars + i, 1);
@@ -277,6 +341,13 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
   const double lo = a.min_target, hi = a.max_target;
   const bool inverted = hi < lo;
   const double a_mid = 1.0 - lr * (1.0 + reg0), a_out = 1.0 - lr * reg0;
+  OrdBias bias;
+  bias.lr = lr;
+  bias.lo = lo;
+  bias.hi = hi;
+  bias.a_mid = a_mid;
+  bias.a_out = a_out;
+  bias.inverted = inverted;
   const uint32_t recb = (uint32_t)a.rs * 8u;
   const int f0 = gl * KF;                       // this lane's first factor
   const int nf = max(0, min(KF, k - f0));       // ... and how many of its KF slots are real
@@ -381,59 +452,10 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
         __syncthreads();
         if (warp == 0) {
           if (TASK == 0) {
-            // ---- bias: affine prefix scan over the run (lane l owns examples EL*l ..) --------
-            double R[ORD_EL], y[ORD_EL], aa[ORD_EL], bb[ORD_EL], wv[ORD_EL];
-            int st[ORD_EL];
-            bool on[ORD_EL];
-#pragma unroll
-            for (int e = 0; e < ORD_EL; e++) {
-              const int t = ORD_EL * lane + e;
-              on[e] = t < P;
-              R[e] = on[e] ? sR[t] : 0.0;
-              y[e] = on[e] ? (double)s.tg[t0 + t] : 0.0;
-              st[e] = ord_state(w0 + R[e], lo, hi, inverted);
-            }
-            double A = 1.0, B = 0.0;
-            for (int it = 0; it <= 2 * ORD_SMAX; it++) {
-              A = 1.0;
-              B = 0.0;
-#pragma unroll
-              for (int e = 0; e < ORD_EL; e++) {
-                aa[e] = on[e] ? (st[e] == 0 ? a_mid : a_out) : 1.0;
-                bb[e] = on[e] ? -lr * ((st[e] == 0 ? R[e] : (st[e] == 1 ? lo : hi)) - y[e]) : 0.0;
-                B = aa[e] * B + bb[e];  // w -> aa*(A w + B) + bb
-                A = aa[e] * A;
-              }
-#pragma unroll
-              for (int o = 1; o < 32; o <<= 1) {
-                const double Ap = ord_shfl_up(A, o), Bp = ord_shfl_up(B, o);
-                if (lane >= o) {
-                  B = A * Bp + B;
-                  A = A * Ap;
-                }
-              }
-              double Ae = ord_shfl_up(A, 1), Be = ord_shfl_up(B, 1);
-              if (lane == 0) {
-                Ae = 1.0;
-                Be = 0.0;
-              }
-              double w = Ae * w0 + Be;
-              bool bad = false;
-#pragma unroll
-              for (int e = 0; e < ORD_EL; e++) {
-                wv[e] = w;  // the bias example e reads
-                const int ns = ord_state(w + R[e], lo, hi, inverted);
-                bad = bad || (on[e] && ns != st[e]);
-                st[e] = ns;
-                w = aa[e] * w + bb[e];
-              }
-              if (!__any_sync(full, bad)) break;
-            }
-            // fm_learn_sgd_element.h:58-62: mult = -(y - clamp(p))
-#pragma unroll
-            for (int e = 0; e < ORD_EL; e++)
-              if (on[e]) sM[ORD_EL * lane + e] = (st[e] == 0 ? wv[e] + R[e] : (st[e] == 1 ? lo : hi)) - y[e];
-            w0 = ord_shfl(A, 31) * w0 + ord_shfl(B, 31);
+            // ---- bias: affine prefix scan over the run, as few examples per lane as the run needs ----
+            if (P <= 32) w0 = ord_bias_scan<1>(bias, w0, P, sR, s.tg + t0, sM, lane);
+            else if (P <= 64) w0 = ord_bias_scan<2>(bias, w0, P, sR, s.tg + t0, sM, lane);
+            else w0 = ord_bias_scan<ORD_EL>(bias, w0, P, sR, s.tg + t0, sM, lane);
           } else {
             // ---- classification: the chain walked serially (fm_learn_sgd_element.h:63-64) ----
             for (int t = 0; t < P; t++) {
@@ -444,6 +466,8 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
               w0 -= lr * (m + reg0 * w0);
             }
           }
+        }
+        if (warp == dwarp) {  // the next run's length: warp 1 searches while warp 0 scans
           const int Pn = (t0n < nrows) ? ord_detect(s, t0n, nrows, smax, lane) : 1;
           if (lane == 0) sP[pi ^ 1] = Pn;
         }

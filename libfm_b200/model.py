@@ -391,6 +391,12 @@ class FmLearnSgdElement:
         self._check(self.lib.fmb200_params_device(self._ctx, C.byref(ptr), C.byref(n)))
         return ptr.value, n.value
 
+    def params_layout(self) -> dict:
+        off_w, off_v, ws, kp = C.c_uint64(), C.c_uint64(), C.c_int(), C.c_int()
+        self._check(self.lib.fmb200_params_layout(self._ctx, C.byref(off_w), C.byref(ws), C.byref(off_v), C.byref(kp)))
+        return {"off_w": off_w.value, "ws": ws.value, "off_v": off_v.value, "kp": kp.value,
+                "n": self.fm.num_attribute}
+
     def stream(self) -> int:
         s = C.c_void_p()
         self._check(self.lib.fmb200_stream(self._ctx, C.byref(s)))

@@ -151,6 +151,36 @@ d = synth.ragged(101, 30, 5, seed=1)
 mine = fdist.shard(d, world, rank)
 sq, ab, ok, n = fdist.sum_metrics(float(mine.num_cases), 2.0, mine.num_cases, mine.num_cases, world)
 assert n == d.num_cases and ok == d.num_cases and sq == float(d.num_cases) and ab == 4.0
+# the mean-field exchange (same rule as fm_peer_meanfield_kernel): two replicas that moved away from a common
+# theta0 on their own shards combine to theta0 + gamma_i * (delta_0 + delta_1); both ranks end identical and
+# equal to a numpy restatement computed from the same seeds
+import numpy as np
+n_f, kp, ws = 12, 4, 8
+off_w, off_v = 4, 4 + n_f * ws
+size = off_v + n_f * kp
+g0 = np.random.default_rng(5)
+theta0 = torch.tensor(g0.standard_normal(size).astype(np.float32) * 0.1)
+deltas = [np.random.default_rng(10 + r).standard_normal(size).astype(np.float32) * 0.01 for r in range(2)]
+counts = [np.random.default_rng(20 + r).integers(0, 400, n_f).astype(np.float32) for r in range(2)]
+rows = [1000, 1200]
+mine_p = theta0 + torch.tensor(deltas[rank])
+lay = dict(off_w=off_w, ws=ws, off_v=off_v, kp=kp, n=n_f)
+fdist.combine_meanfield_(mine_p, theta0, torch.tensor(counts[rank]), rows[rank], lay, lr=0.01, regw=0.001, regv=0.002, world=2)
+def gam(u, G=2.0):
+    u = np.asarray(u, dtype=np.float64); out = np.ones_like(u); m = u > 1e-6
+    out[m] = -np.expm1(-G * u[m]) / (G * -np.expm1(-u[m])); return out
+t0 = theta0.numpy().astype(np.float64)
+cm = (counts[0] + counts[1]) / 2.0
+hv = float((t0[off_v:] ** 2).sum()) / n_f
+gamma = np.zeros(size)
+gamma[0] = gam(np.array([0.01 * np.mean(rows)]))[0]
+gamma[off_w:off_v:ws] = gam(0.01 * 1.001 * cm)
+gamma[off_v:] = np.repeat(gam(0.01 * (hv + 0.002) * cm), kp)
+want = t0 + gamma * (deltas[0].astype(np.float64) + deltas[1].astype(np.float64))
+assert np.allclose(mine_p.numpy(), want, atol=2e-6), np.abs(mine_p.numpy() - want).max()
+both = [torch.zeros_like(mine_p) for _ in range(2)]
+dist.all_gather(both, mine_p)
+assert torch.equal(both[0], both[1])
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
