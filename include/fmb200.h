@@ -194,9 +194,6 @@ int fmb200_last_epoch_config(fmb200_ctx* ctx, int* lanes_per_row, int* slots, in
  * of the epoch kernel, 1 = sub-warp row-group kernel, 2 = one-lane-per-row kernel
  * (k <= 8, rows of <= 4 entries; ignored when not applicable), 3 = its warp-specialised
  * form (producer warp + mbarrier hand-offs; bias read three tiles ahead).
- * Variants 5/6/7 pick experimental forms of the one-lane-per-row kernel (5: bias read a tile
- * ahead, 6: that + 64 registers for 4 CTAs per SM, 7: 64 registers alone; measured r02: none is
- * faster than the default).
  * INORDER mode runs the wavefront schedule of the sequential epoch for k <= 8 and rows of <= 4
  * entries (conflict-free runs of examples gather and scatter in parallel, only the bias chain
  * stays serial; bit-identical to the row-at-a-time kernel, verified on the device); variant 1

@@ -62,6 +62,7 @@ void free_slot(DataSlot& s) {
   if (s.feat_cnt) cudaFree(s.feat_cnt);
   if (s.link) cudaFree(s.link);
   if (s.rowdep) cudaFree(s.rowdep);
+  if (s.ord_scratch) cudaFree(s.ord_scratch);
   if (s.d_flag) cudaFree(s.d_flag);
   if (s.h_flag) cudaFreeHost(s.h_flag);
   if (s.ready) cudaEventDestroy(s.ready);
@@ -548,12 +549,17 @@ int fmb200_get_params(fmb200_ctx* c, double* w0, double* w, double* v) {
   const uint32_t n = c->n;
     const int k = c->k, kp = c->kp;
     if (c->mode != FMB200_MODE_HOGWILD) {
-      std::vector<double> h(c->p64.n_doubles);
-      CK(cudaMemcpyAsync(h.data(), c->p64.base, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      std::vector<double> pageable;
+      double* h = static_cast<double*>(c->h_stage);  // pinned staging for small models
+      if (h == nullptr) {
+        pageable.resize(c->p64.n_doubles);
+        h = pageable.data();
+      }
+      CK(cudaMemcpyAsync(h, c->p64.base, c->p64.n_doubles * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
       *w0 = h[0];
       for (uint32_t i = 0; i < n; i++) w[i] = h[Params64::off_w + i];
-      const double* hv = h.data() + c->p64.off_v;
+      const double* hv = h + c->p64.off_v;
       for (int f = 0; f < k; f++)
         for (uint32_t i = 0; i < n; i++) v[(size_t)f * n + i] = hv[(size_t)i * k + f];
     } else {

@@ -410,13 +410,6 @@ static cudaError_t launch_rowlane(fmb200_ctx* c, const DataSlot& d, bool* handle
   const bool ws = c->tune_variant == 3;
   HogwildKernelFn fn = ws ? pick_rowlane_ws_kernel(gp, (int)d.max_row_nnz, damp, combine)
                           : pick_rowlane_kernel(gp, (int)d.max_row_nnz, damp, combine);
-  // variants 5/6/7 (plain kernels only): 5 = bias read a tile ahead, 6 = that + 64 registers
-  // (4 CTAs per SM), 7 = 64 registers alone
-  if (!ws && !damp && !combine && c->tune_variant >= 5 && c->tune_variant <= 7) {
-    HogwildKernelFn alt = pick_rowlane_ba_kernel(gp, (int)d.max_row_nnz, c->tune_variant != 7,
-                                                 c->tune_variant >= 6 ? 4 : 3);
-    if (alt != nullptr) fn = alt;
-  }
   if (fn == nullptr) return cudaSuccess;
   const int hdr = ws ? 512 : HW_HDR_BYTES;
   // COMBINE (non-WS): two 128-slot hot-feature tables of 64-byte entries behind the ring

@@ -150,9 +150,6 @@ using HogwildKernelFn = void (*)(const HogwildArgs);
 
 // fm_rowlane.cu: kernel for (float4 chunks per row gp in {1,2}, rows of at most Z entries)
 HogwildKernelFn pick_rowlane_kernel(int gp, int max_row_nnz, bool damp, bool combine);
-// plain kernels (no damping, no merging) with the bias read a tile ahead (bias_ahead) and / or
-// compiled for min_blocks resident CTAs per SM (4 -> 64 registers); nullptr if neither applies
-HogwildKernelFn pick_rowlane_ba_kernel(int gp, int max_row_nnz, bool bias_ahead, int min_blocks);
 // warp-specialised variant: blockDim = rows_per_tile + 32, smem header 512 B
 HogwildKernelFn pick_rowlane_ws_kernel(int gp, int max_row_nnz, bool damp, bool combine);
 

@@ -52,7 +52,7 @@ __global__ void ord_link_kernel(const uint32_t* __restrict__ ids, const uint32_t
 // blockDim <= ORD_SMAX * GL (one group of GL lanes per example of a run): small k leaves the
 // register file to few threads (k <= 8: 128 threads)
 template <int GL, int KF, int TASK>
-__global__ void __launch_bounds__((ORD_SMAX * GL < ORD_MAX_THREADS ? ORD_SMAX * GL : ORD_MAX_THREADS), 1)
+__global__ void __launch_bounds__((ORD_SMAX * GL < 512 ? 512 : (ORD_SMAX * GL < ORD_MAX_THREADS ? ORD_SMAX * GL : ORD_MAX_THREADS)), 1)
     fm_sgd_ordered_kernel(const OrderedArgs a) {
   extern __shared__ __align__(128) unsigned char ord_smem[];
   ordered_epoch_body<GL, KF, TASK>(a, ord_smem);
@@ -107,36 +107,40 @@ cudaError_t build_ordered_links(fmb200_ctx* c, DataSlot& d) {
   if ((e = cudaMemsetAsync(d.link, 0xff, cap_e * sizeof(uint32_t), c->stream)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(d.rowdep, 0xff, cap_r * sizeof(uint32_t), c->stream)) != cudaSuccess) return e;
   if (d.nnz > 0) {
-    uint32_t *ids = nullptr, *ent_in = nullptr, *ent = nullptr;
-    void* tmp = nullptr;
-    size_t tmp_bytes = 0;
     int bits = 1;
     while (bits < 32 && (1ull << bits) < (uint64_t)c->n) bits++;
-    e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d.col, ids, ent_in, ent, (uint64_t)d.nnz, 0, bits,
-                                        c->stream);
+    size_t tmp_bytes = 0;
+    e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d.col, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                        (uint32_t*)nullptr, (uint64_t)d.nnz, 0, bits, c->stream);
     if (e != cudaSuccess) return e;
-    if ((e = cudaMalloc(&ids, d.nnz * sizeof(uint32_t))) == cudaSuccess &&
-        (e = cudaMalloc(&ent_in, d.nnz * sizeof(uint32_t))) == cudaSuccess &&
-        (e = cudaMalloc(&ent, d.nnz * sizeof(uint32_t))) == cudaSuccess &&
-        (e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16)) == cudaSuccess) {
-      ord_iota_kernel<<<grid_for(c, d.nnz), 256, 0, c->stream>>>(ent_in, d.nnz);
-      e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, d.col, ids, ent_in, ent, (uint64_t)d.nnz, 0, bits,
-                                          c->stream);
-      if (e == cudaSuccess) {
-        ord_link_kernel<<<grid_for(c, d.nnz), 256, 0, c->stream>>>(ids, ent, d.nnz, d.row_ptr, d.n_rows, d.link,
-                                                                  d.rowdep);
-        e = cudaGetLastError();
-        c->launches += 3;  // iota, link + the library's sort passes counted as one
-      }
+    // scratch of the index build: [ids | ent_in | ent | sort temp].  Kept with the slot for data sets up to
+    // 64 M entries (a re-upload then rebuilds its index without a single allocation or host sync -- the
+    // end-to-end path uploads a fresh data set every step); larger ones release it right away.
+    const size_t words = ((size_t)d.nnz + 63) & ~(size_t)63;
+    const size_t need = 3 * words * sizeof(uint32_t) + ((tmp_bytes + 255) & ~(size_t)255) + 256;
+    if (d.ord_scratch_bytes < need) {
+      if (d.ord_scratch) cudaFree(d.ord_scratch);
+      d.ord_scratch = nullptr;
+      d.ord_scratch_bytes = 0;
+      if ((e = cudaMalloc(&d.ord_scratch, need)) != cudaSuccess) return e;
+      d.ord_scratch_bytes = need;
     }
-    // stream-ordered release would need a pool; this is a once-per-upload step
-    cudaError_t e2 = cudaStreamSynchronize(c->stream);
-    cudaFree(ids);
-    cudaFree(ent_in);
-    cudaFree(ent);
-    cudaFree(tmp);
+    uint32_t* ids = static_cast<uint32_t*>(d.ord_scratch);
+    uint32_t* ent_in = ids + words;
+    uint32_t* ent = ent_in + words;
+    void* tmp = ent + words;
+    ord_iota_kernel<<<grid_for(c, d.nnz), 256, 0, c->stream>>>(ent_in, d.nnz);
+    e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, d.col, ids, ent_in, ent, (uint64_t)d.nnz, 0, bits, c->stream);
     if (e != cudaSuccess) return e;
-    if (e2 != cudaSuccess) return e2;
+    ord_link_kernel<<<grid_for(c, d.nnz), 256, 0, c->stream>>>(ids, ent, d.nnz, d.row_ptr, d.n_rows, d.link, d.rowdep);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    c->launches += 3;  // iota, link + the library's sort passes counted as one
+    if (d.nnz > (64ull << 20)) {
+      if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return e;
+      cudaFree(d.ord_scratch);
+      d.ord_scratch = nullptr;
+      d.ord_scratch_bytes = 0;
+    }
   }
   d.links_ready = true;
   return cudaSuccess;
@@ -223,8 +227,9 @@ cudaError_t launch_sgd_ordered(fmb200_ctx* c, DataSlot& d, bool* handled) {
   ordered_shape(c->k, &GL, &KF);
   // one group of GL lanes per example of a run: min(ORD_SMAX, 1024 / GL) examples
   int threads = std::min(ORD_SMAX * GL, ORD_MAX_THREADS);
-  if (c->tune_threads)  // fewer threads = shorter runs (experiments); never more than the kernel is bounded for
-    threads = std::min(threads, std::max(32, (c->tune_threads / (32 > GL ? 32 : GL)) * (32 > GL ? 32 : GL)));
+  const int bound = std::max(threads, 512);  // the kernel's launch bound
+  if (c->tune_threads)  // fewer threads = shorter runs; more = helper warps for the fetch issue / write-back
+    threads = std::min(bound, std::max(32, (c->tune_threads / (32 > GL ? 32 : GL)) * (32 > GL ? 32 : GL)));
   OrdFn fn = c->hp.task == FMB200_TASK_REGRESSION ? pick_kernel<0>(c->k) : pick_kernel<1>(c->k);
   e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

@@ -80,7 +80,8 @@ struct OrderedArgs {
   double lr, reg0, regw, regv, min_target, max_target;
   uint32_t csr_bytes;  // one CSR stage
   uint32_t rec_bytes;  // one record buffer = tile_cap * rs * 8
-  int debug;           // timing experiments only (results become wrong): 1 = no write-back to global
+  int debug;           // timing experiments only (results become wrong): 1 = no write-back to global,
+                       // 2 = no bias scan (multiplier 0), 4 = no fm_SGD phase, 8 = no score phase
 };
 
 // ---- shared-memory layout (host and device agree through these) -------------------------
@@ -171,8 +172,7 @@ __device__ __forceinline__ void ord_prep(const OrderedArgs& a, unsigned char* sm
   const uint32_t rec = ord_rec_base(a, tile), recp = ord_rec_base(a, tile + ORD_NBUF - 1);
   const uint32_t recb = (uint32_t)a.rs * 8u;
   const int k = a.k, kw = a.kw;
-  for (uint32_t j = j0 + tid; j < j1; j += nthreads) s.sup[j] = 0;
-  __syncthreads();  // (all threads call ord_prep together)
+  // (s.sup[] is all zero here: zeroed at kernel start and re-zeroed by the write-back that read it)
   for (uint32_t j = j0 + tid; j < j1; j += nthreads) {
     const uint32_t L = s.link[j];
     const uint64_t e = ab + j;
@@ -333,6 +333,10 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
     for (int i = 0; i < ORD_NBUF; i++) mbar_init(bars + i, 1);
     fence_mbar_init();
   }
+  for (uint32_t t = 0; t < (uint32_t)ORD_NBUF; t++) {
+    unsigned char* sup = ord_stage(a, smem, t).sup;
+    for (uint32_t j = tid; j < a.tile_cap; j += nthreads) sup[j] = 0;
+  }
   __syncthreads();
 
   const int k = a.k, kw = a.kw;
@@ -418,6 +422,8 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
         jb = (uint32_t)(s.rp[r] - ab);
         je = (uint32_t)(s.rp[r + 1] - ab);
         rowdup = s.rd[r] == 0u;
+      }
+      if (act && !(a.debug & 8)) {
         double ssq[KF];
 #pragma unroll
         for (int q = 0; q < KF; q++) ssq[q] = 0.0;
@@ -451,7 +457,11 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
         if (act && gl == 0) sR[grp] = Rloc;
         __syncthreads();
         if (warp == 0) {
-          if (TASK == 0) {
+          if (a.debug & 2) {
+            if (lane < ORD_EL) {
+              for (int t = lane; t < P; t += ORD_EL) sM[t] = 0.0;
+            }
+          } else if (TASK == 0) {
             // ---- bias: affine prefix scan over the run, as few examples per lane as the run needs ----
             if (P <= 32) w0 = ord_bias_scan<1>(bias, w0, P, sR, s.tg + t0, sM, lane);
             else if (P <= 64) w0 = ord_bias_scan<2>(bias, w0, P, sR, s.tg + t0, sM, lane);
@@ -489,8 +499,8 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
         }
       }
 
-      // ---- fm_SGD (fm_sgd.h:38-50) for the lane's example: own ring slot + global ----------
-      if (act) {
+      // ---- fm_SGD (fm_sgd.h:38-50) for the lane's example: result into the own ring slot -------
+      if (act && !(a.debug & 4)) {
         for (uint32_t j = jb; j < je; j++) {
           uint32_t jj = j;
           bool dupj = false;
@@ -534,23 +544,47 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
     if (!(a.debug & 1)) {
       const uint32_t j0 = (uint32_t)(s.rp[0] - ab), j1 = (uint32_t)(s.rp[nrows] - ab);
       if ((k & 1) == 0) {
-        // consecutive threads write consecutive 16-byte pieces of one record: coalesced rows
-        const uint32_t pieces = (uint32_t)(kw / 2) + 1u;  // kw/2 factor pairs + the linear weight
-        const uint32_t total = (j1 - j0) * pieces;
-        for (uint32_t i = tid; i < total; i += nthreads) {
-          const uint32_t j = j0 + i / pieces, pc = i % pieces;
-          if (s.sup[j]) continue;
-          const double* own = reinterpret_cast<const double*>(smem + rec + j * recb);
-          const uint32_t id = s.col[j];
-          if (pc < pieces - 1u) {
-            *reinterpret_cast<double2*>(a.v + (size_t)id * k + 2u * pc) = *reinterpret_cast<const double2*>(own + 2u * pc);
-          } else if (k1) {
-            a.w[id] = own[kw + (id & 1u)];
+        // 2^lg consecutive threads write the 16-byte pieces of one record (kw/2 factor pairs + the
+        // linear weight): coalesced rows, no division
+        const uint32_t pieces = (uint32_t)(kw / 2) + 1u;
+        uint32_t lg = 0;
+        while ((1u << lg) < pieces) lg++;
+        const uint32_t pc = tid & ((1u << lg) - 1u);
+        const uint32_t step = (uint32_t)nthreads >> lg;  // records per sweep of the CTA
+        if (step == 0) {  // more pieces than threads (k > 2 * blockDim): one thread per record
+          for (uint32_t j = j0 + tid; j < j1; j += nthreads) {
+            const unsigned char sup = s.sup[j];
+            s.sup[j] = 0;
+            if (sup) continue;
+            const double* own = reinterpret_cast<const double*>(smem + rec + j * recb);
+            const uint32_t id = s.col[j];
+            for (int q = 0; q < k; q += 2)
+              *reinterpret_cast<double2*>(a.v + (size_t)id * k + q) = *reinterpret_cast<const double2*>(own + q);
+            if (k1) a.w[id] = own[kw + (id & 1u)];
           }
+        } else {
+          for (uint32_t j = j0 + ((uint32_t)tid >> lg); j < j1; j += step) {
+            if (!s.sup[j]) {
+              const double* own = reinterpret_cast<const double*>(smem + rec + j * recb);
+              const uint32_t id = s.col[j];
+              for (uint32_t q = pc; q < pieces; q += (1u << lg)) {
+                if (q < pieces - 1u) {
+                  *reinterpret_cast<double2*>(a.v + (size_t)id * k + 2u * q) =
+                      *reinterpret_cast<const double2*>(own + 2u * q);
+                } else if (k1) {
+                  a.w[id] = own[kw + (id & 1u)];
+                }
+              }
+            }
+          }
+          __syncthreads();  // every lane of a record has read its flag
+          for (uint32_t j = j0 + tid; j < j1; j += nthreads) s.sup[j] = 0;
         }
       } else {
         for (uint32_t j = j0 + tid; j < j1; j += nthreads) {
-          if (s.sup[j]) continue;
+          const unsigned char sup = s.sup[j];
+          s.sup[j] = 0;
+          if (sup) continue;
           const double* own = reinterpret_cast<const double*>(smem + rec + j * recb);
           const uint32_t id = s.col[j];
           const uint32_t vo = id & 1u;
@@ -559,6 +593,9 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
           if (k1) a.w[id] = own[kw + (id & 1u)];
         }
       }
+    } else {
+      const uint32_t j0 = (uint32_t)(s.rp[0] - ab), j1 = (uint32_t)(s.rp[nrows] - ab);
+      for (uint32_t j = j0 + tid; j < j1; j += nthreads) s.sup[j] = 0;
     }
     __syncthreads();  // stage T%3 is read above and refilled by the TMA issue at the top of tile T+1
   }

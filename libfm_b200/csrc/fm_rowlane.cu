@@ -269,14 +269,8 @@ __device__ __forceinline__ void rowlane_tile(const HogwildArgs& a, const uint64_
   hjoint_out = valid ? hjoint : 0.f;
 }
 
-// BA ("bias ahead"): the tile's bias comes from shared memory, where lane 0 left it a tile ago: the
-// load of the globally hammered w0 line is issued once the tile's sums are formed and lands
-// while the write-back is being issued; the end-of-tile barrier publishes it.  The multiplier
-// -- and with it every reduction of the tile -- no longer waits for that load behind a named
-// barrier (r01 ncu: 42% of the stall samples sat on the bias hand-off).  MINB: resident CTAs
-// per SM the register allocation is bounded for (4 -> 64 registers).
-template <int GP, int Z, bool DAMP, bool COMBINE, bool BA = false, int MINB = 3>
-__global__ void __launch_bounds__(HW_MAX_THREADS, MINB) fm_sgd_rowlane_kernel(const HogwildArgs a) {
+template <int GP, int Z, bool DAMP, bool COMBINE>
+__global__ void __launch_bounds__(HW_MAX_THREADS, 3) fm_sgd_rowlane_kernel(const HogwildArgs a) {
   constexpr int K = 4 * GP;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -322,7 +316,6 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, MINB) fm_sgd_rowlane_kernel(co
     }
     claim_raw = sched.fire();
   }
-  if (BA && tid == 0) reinterpret_cast<float*>(smem + 192)[0] = a.use_w0 ? ld_cg_f(a.w0) : 0.f;
   __syncthreads();
 
   const float4* V4 = reinterpret_cast<const float4*>(a.v);
@@ -349,8 +342,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, MINB) fm_sgd_rowlane_kernel(co
     }
     BiasFetch bias;
     bias.slot = reinterpret_cast<float*>(smem + 192);
-    if (!BA) bias.issue(a, use_w0, tid);
-    float w0_next = 0.f;  // BA, thread 0: the bias of the next tile, in flight
+    bias.issue(a, use_w0, tid);
     mbar_wait(bars + stage, parity);
 
     unsigned char* sb = stage_base(smem, a, stage);
@@ -365,16 +357,8 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, MINB) fm_sgd_rowlane_kernel(co
     float mult, hj, w0 = 0.f;
     rowlane_tile<GP, Z, DAMP, COMBINE>(
         a, rp, ys, ids, xs, rows_here, tid,
-        [&]() {
-          if (BA) {
-            w0 = bias.slot[it & 1];
-            if (use_w0 && tid == 0) w0_next = ld_cg_f(a.w0);
-            return w0;
-          }
-          return w0 = bias.get(use_w0, tid, it, (int)blockDim.x);
-        },
-        mult, hj, COMBINE ? hot + (it & 1) * HOT_SLOTS : nullptr);
-    if (BA && tid == 0) bias.slot[(it + 1) & 1] = w0_next;
+        [&]() { return w0 = bias.get(use_w0, tid, it, (int)blockDim.x); }, mult, hj,
+        COMBINE ? hot + (it & 1) * HOT_SLOTS : nullptr);
     // ---- bias: one damped reduction into the global w0 per tile ----
     float2* s_part = reinterpret_cast<float2*>(s_acc) + (it & 1) * 8;  // [2 slots][8 warps]
     if (use_w0) {
@@ -567,30 +551,6 @@ HogwildKernelFn pick_rowlane_kernel(int gp, int max_row_nnz, bool damp, bool com
   if (gp == 1) return pick_z<1>(max_row_nnz, damp, combine);
   if (gp == 2) return pick_z<2>(max_row_nnz, damp, combine);
   return nullptr;
-}
-
-// plain (undamped, unmerged) kernels with the bias read a tile ahead and / or bounded to 64
-// registers for 4 resident CTAs per SM
-template <int GP, bool BA, int MINB>
-static HogwildKernelFn pick_z_ba(int z) {
-  if (z <= 1) return fm_sgd_rowlane_kernel<GP, 1, false, false, BA, MINB>;
-  if (z <= 2) return fm_sgd_rowlane_kernel<GP, 2, false, false, BA, MINB>;
-  if (z <= 4) return fm_sgd_rowlane_kernel<GP, 4, false, false, BA, MINB>;
-  return nullptr;
-}
-
-HogwildKernelFn pick_rowlane_ba_kernel(int gp, int max_row_nnz, bool bias_ahead, int min_blocks) {
-  if (gp < 1 || gp > 2) return nullptr;
-#define FMB_BA(GPV)                                                          \
-  if (bias_ahead && min_blocks >= 4) return pick_z_ba<GPV, true, 4>(max_row_nnz); \
-  if (bias_ahead) return pick_z_ba<GPV, true, 3>(max_row_nnz);               \
-  if (min_blocks >= 4) return pick_z_ba<GPV, false, 4>(max_row_nnz);         \
-  return nullptr;
-  if (gp == 1) {
-    FMB_BA(1)
-  }
-  FMB_BA(2)
-#undef FMB_BA
 }
 
 }  // namespace fmb

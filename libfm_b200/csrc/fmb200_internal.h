@@ -34,6 +34,8 @@ struct DataSlot {
   uint32_t* link = nullptr;
   uint32_t* rowdep = nullptr;
   bool links_ready = false;
+  void* ord_scratch = nullptr;  // scratch of the index build (kept for re-uploads of moderate size)
+  size_t ord_scratch_bytes = 0;
 };
 
 // Packed fp32 state: [w0, 0, 0, 0 | w[n*ws] padded to a multiple of 4 | V[n][kp]].

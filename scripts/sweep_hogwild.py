@@ -36,10 +36,8 @@ def main():
     print("oracle trajectory (train, test):", ["%.5f/%.5f" % r for r in ref], flush=True)
 
     # (ctas_per_sm, rows_per_tile, threads, damp, variant)
-    tunings = [(0, 0, 0, 0, 0), (0, 0, 0, 0, 5), (0, 0, 0, 0, 6), (0, 0, 0, 0, 7), (0, 0, 0, 0, 3),
-               (0, 0, 128, 0, 0), (0, 0, 128, 0, 5), (0, 0, 128, 0, 6), (0, 0, 64, 0, 6),
-               (2, 0, 0, 0, 5), (1, 0, 0, 0, 5), (2, 0, 128, 0, 6), (1, 0, 128, 0, 6), (1, 0, 64, 0, 6),
-               (1, 0, 32, 0, 6)]
+    tunings = [(0, 0, 0, 0, 0), (0, 0, 0, 0, 3), (0, 0, 128, 0, 0), (0, 0, 64, 0, 0), (2, 0, 0, 0, 0), (1, 0, 0, 0, 0),
+               (2, 0, 128, 0, 0), (1, 0, 128, 0, 0), (1, 0, 64, 0, 0), (1, 0, 32, 0, 0)]
     rows = []
     for t in tunings:
         fm = FmModel(n, k)
