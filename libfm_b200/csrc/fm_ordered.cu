@@ -51,11 +51,11 @@ __global__ void ord_link_kernel(const uint32_t* __restrict__ ids, const uint32_t
 
 // blockDim <= ORD_SMAX * GL (one group of GL lanes per example of a run): small k leaves the
 // register file to few threads (k <= 8: 128 threads)
-template <int GL, int KF, int TASK>
+template <int GL, int KF, int TASK, int ZF = 0>
 __global__ void __launch_bounds__((ORD_SMAX * GL < 512 ? 512 : (ORD_SMAX * GL < ORD_MAX_THREADS ? ORD_SMAX * GL : ORD_MAX_THREADS)), 1)
     fm_sgd_ordered_kernel(const OrderedArgs a) {
   extern __shared__ __align__(128) unsigned char ord_smem[];
-  ordered_epoch_body<GL, KF, TASK>(a, ord_smem);
+  ordered_epoch_body<GL, KF, TASK, ZF>(a, ord_smem);
 }
 
 using OrdFn = void (*)(const OrderedArgs);
@@ -71,6 +71,17 @@ inline void ordered_shape(int k, int* GL, int* KF) {
   int g = 2;
   while (g * 8 < k) g <<= 1;
   *GL = g;
+}
+
+// register-resident fast path: k in {2,4,8} exactly, rows of at most 2 / 4 entries
+template <int TASK>
+OrdFn pick_fast_kernel(int k, uint32_t max_row_nnz) {
+  if (max_row_nnz < 1 || max_row_nnz > 4) return nullptr;
+  const bool z2 = max_row_nnz <= 2;
+  if (k == 2) return z2 ? fm_sgd_ordered_kernel<1, 2, TASK, 2> : fm_sgd_ordered_kernel<1, 2, TASK, 4>;
+  if (k == 4) return z2 ? fm_sgd_ordered_kernel<1, 4, TASK, 2> : fm_sgd_ordered_kernel<1, 4, TASK, 4>;
+  if (k == 8) return z2 ? fm_sgd_ordered_kernel<1, 8, TASK, 2> : fm_sgd_ordered_kernel<1, 8, TASK, 4>;
+  return nullptr;
 }
 
 template <int TASK>
@@ -231,6 +242,11 @@ cudaError_t launch_sgd_ordered(fmb200_ctx* c, DataSlot& d, bool* handled) {
   if (c->tune_threads)  // fewer threads = shorter runs; more = helper warps for the fetch issue / write-back
     threads = std::min(bound, std::max(32, (c->tune_threads / (32 > GL ? 32 : GL)) * (32 > GL ? 32 : GL)));
   OrdFn fn = c->hp.task == FMB200_TASK_REGRESSION ? pick_kernel<0>(c->k) : pick_kernel<1>(c->k);
+  if (c->tune_variant != 1) {  // variant 1 forces the general path
+    OrdFn fast = c->hp.task == FMB200_TASK_REGRESSION ? pick_fast_kernel<0>(c->k, d.max_row_nnz)
+                                                      : pick_fast_kernel<1>(c->k, d.max_row_nnz);
+    if (fast != nullptr) fn = fast;
+  }
   e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   fn<<<1, threads, smem, c->stream>>>(a);

@@ -202,9 +202,8 @@ __device__ __forceinline__ double ord_shfl_xor(double v, int m) { return __shfl_
 // fmin(max, p) then fmax(min, .) (fm_learn_sgd_element.h:60-61): NaN or too large -> max,
 // then anything below min -> min.
 __device__ __forceinline__ int ord_state(double p, double lo, double hi, bool inverted) {
-  const bool h = !(p <= hi);
-  if (h) return inverted ? 1 : 2;
-  return (p < lo) ? 1 : 0;
+  const bool h = !(p <= hi), l = p < lo;
+  return h ? (inverted ? 1 : 2) : (l ? 1 : 0);  // selects, no branches: this sits on the scan's critical path
 }
 
 // length of the run starting at tile-relative row t0 (executed by one whole warp): rows are
@@ -317,17 +316,343 @@ __device__ __forceinline__ double ord_bias_scan(const OrdBias& c, double w0, int
   return ord_shfl(A, 31) * w0 + ord_shfl(B, 31);
 }
 
-template <int GL, int KF, int TASK>
-__device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigned char* smem) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+// barrier over one role's threads: the whole CTA (0), or a named barrier over the role (WS)
+template <bool WS>
+__device__ __forceinline__ void ord_group_sync(int id, int nthreads) {
+  if (WS) named_bar_sync(id, nthreads);
+  else __syncthreads();
+}
+
+struct OrdConsts {
+  int k, kw;
+  bool k0, k1;
+  double lr, reg0, regw, regv, lo, hi;
+  bool inverted;
+  OrdBias bias;
+  uint32_t recb;
+};
+__device__ __forceinline__ OrdConsts ord_consts(const OrderedArgs& a) {
+  OrdConsts c;
+  c.k = a.k;
+  c.kw = a.kw;
+  c.k0 = a.use_w0 != 0;
+  c.k1 = a.use_w != 0;
+  c.lr = a.lr;
+  c.reg0 = a.reg0;
+  c.regw = a.regw;
+  c.regv = a.regv;
+  c.lo = a.min_target;
+  c.hi = a.max_target;
+  c.inverted = c.hi < c.lo;
+  c.bias.lr = c.lr;
+  c.bias.lo = c.lo;
+  c.bias.hi = c.hi;
+  c.bias.a_mid = 1.0 - c.lr * (1.0 + c.reg0);
+  c.bias.a_out = 1.0 - c.lr * c.reg0;
+  c.bias.inverted = c.inverted;
+  c.recb = (uint32_t)a.rs * 8u;
+  return c;
+}
+
+// ZF > 0 selects the register-resident fast path: one lane per example (GL == 1), k == KF even, every
+// row of the data set at most ZF entries.  The rows' records are loaded once with 16-byte accesses, kept
+// in registers across the bias scan and written back to the ring from there -- no per-entry loop, no
+// second read.  Rows that name a feature twice (singleton runs) take the general path.
+//
+// All runs of tile T, executed by the `nthreads` compute threads (tid in [0, nthreads)); sP[0] holds the
+// length of the tile's first run.  w0 is live in warp 0.
+template <int GL, int KF, int TASK, int ZF, bool WS>
+__device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned char* smem, const OrdConsts& cc,
+                                              uint32_t T, int tid, int nthreads, double& w0) {
+  const int lane = tid & 31, warp = tid >> 5;
   const int gl = tid % GL;   // lane inside the example's group
   const int grp = tid / GL;  // example slot inside a run
   const int smax = min(ORD_SMAX, nthreads / GL);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   int* sP = reinterpret_cast<int*>(smem + 32);  // [2]: run lengths, double-buffered by run parity
   double* sR = reinterpret_cast<double*>(smem + 64);
   double* sM = sR + ORD_SMAX;
   const int dwarp = nthreads > 32 ? 1 : 0;  // the warp that searches the next run
+  const int k = cc.k, kw = cc.kw;
+  const bool k0 = cc.k0, k1 = cc.k1;
+  const double lr = cc.lr, reg0 = cc.reg0, regw = cc.regw, regv = cc.regv, lo = cc.lo, hi = cc.hi;
+  const bool inverted = cc.inverted;
+  const OrdBias& bias = cc.bias;
+  const uint32_t recb = cc.recb;
+  const int f0 = gl * KF;                       // this lane's first factor
+  const int nf = max(0, min(KF, k - f0));       // ... and how many of its KF slots are real
+  const bool vec = ((k & 1) == 0) && (KF % 2 == 0);  // 16-byte aligned factor slices
+  const OrdStage s = ord_stage(a, smem, T);
+  const uint64_t r0 = (uint64_t)T * a.tile_rows;
+  const int nrows = (int)min((uint64_t)a.tile_rows, a.n_rows - r0);
+  const uint64_t ab = s.rp[0] & ~3ull;
+  const uint32_t rec = ord_rec_base(a, T);
+
+  int t0 = 0;
+  int pi = 0;  // parity of the run inside the tile
+  while (t0 < nrows) {
+    const int P = sP[pi];
+    // ---- scores of the run's examples: fm_model.h:105-127 with R_t = p_t - w0 ----------
+    const bool act = grp < P;
+    const int r = t0 + grp;
+    uint32_t jb = 0, je = 0;
+    bool rowdup = false;
+    double sum[KF];
+#pragma unroll
+    for (int q = 0; q < KF; q++) sum[q] = 0.0;
+    double Rloc = 0.0;
+    if (act) {
+      jb = (uint32_t)(s.rp[r] - ab);
+      je = (uint32_t)(s.rp[r + 1] - ab);
+      rowdup = s.rd[r] == 0u;
+    }
+    constexpr int ZR = ZF > 0 ? ZF : 1;
+    double fv[ZR][KF], fw[ZR], fx[ZR];  // fast path: the row's records, weights and values
+    uint32_t fid[ZR];
+    const bool fast = (ZF > 0) && (s.rd[t0] != 0u);  // uniform: a row naming a feature twice runs alone
+    if (fast) {
+      if (act && !(a.debug & 8)) {
+        const uint32_t cnt = je - jb;
+#pragma unroll
+        for (int e = 0; e < ZR; e++) {
+          const bool on = (uint32_t)e < cnt;
+          const uint32_t j = jb + (on ? e : 0);
+          const double* rp_ = reinterpret_cast<const double*>(smem + s.src[j]);
+          fid[e] = s.col[j];
+          fx[e] = on ? (double)s.val[j] : 0.0;
+#pragma unroll
+          for (int q = 0; q < KF; q += 2) {
+            const double2 t2 = *reinterpret_cast<const double2*>(rp_ + q);
+            fv[e][q] = on ? t2.x : 0.0;
+            fv[e][q + 1] = on ? t2.y : 0.0;
+          }
+          fw[e] = (on && k1) ? rp_[kw + (fid[e] & 1u)] : 0.0;
+        }
+        double ssq[KF];
+#pragma unroll
+        for (int q = 0; q < KF; q++) ssq[q] = 0.0;
+#pragma unroll
+        for (int e = 0; e < ZR; e++) {
+#pragma unroll
+          for (int q = 0; q < KF; q++) {
+            const double d = fv[e][q] * fx[e];
+            sum[q] += d;
+            ssq[q] += d * d;
+          }
+          Rloc += fw[e] * fx[e];
+        }
+#pragma unroll
+        for (int q = 0; q < KF; q++) Rloc += 0.5 * (sum[q] * sum[q] - ssq[q]);
+      }
+    } else if (act && !(a.debug & 8)) {
+      double ssq[KF];
+#pragma unroll
+      for (int q = 0; q < KF; q++) ssq[q] = 0.0;
+      for (uint32_t j = jb; j < je; j++) {
+        uint32_t jj = j;
+        if (rowdup)  // a feature named twice: both entries score with the value before the row
+          while (s.link[jj] != ORD_NONE && s.link[jj] <= jj - jb) jj -= s.link[jj];
+        const double* rp_ = reinterpret_cast<const double*>(smem + s.src[jj]);
+        const uint32_t id = s.col[j];
+        const double x = (double)s.val[j];
+        const uint32_t vo = (k & 1) ? (id & 1u) : 0u;
+        double vv[KF];
+        ord_load<KF>(rp_ + vo + f0, vv, nf, vec);
+#pragma unroll
+        for (int q = 0; q < KF; q++) {
+          const double d = vv[q] * x;  // slots beyond k hold 0
+          sum[q] += d;
+          ssq[q] += d * d;
+        }
+        if (k1 && (int)((j - jb) % GL) == gl) Rloc += rp_[kw + (id & 1u)] * x;
+      }
+#pragma unroll
+      for (int q = 0; q < KF; q++) Rloc += 0.5 * (sum[q] * sum[q] - ssq[q]);
+    }
+#pragma unroll
+    for (int o = GL / 2; o > 0; o >>= 1) Rloc += ord_shfl_xor(Rloc, o);
+
+    const int t0n = t0 + P;
+    double mult = 0.0;
+    if (k0) {
+      if (act && gl == 0) sR[grp] = Rloc;
+      ord_group_sync<WS>(1, nthreads);
+      if (warp == 0) {
+        if (a.debug & 2) {
+          if (lane < ORD_EL) {
+            for (int t = lane; t < P; t += ORD_EL) sM[t] = 0.0;
+          }
+        } else if (TASK == 0) {
+          // ---- bias: affine prefix scan over the run, as few examples per lane as the run needs ----
+          if (P <= 32) w0 = ord_bias_scan<1>(bias, w0, P, sR, s.tg + t0, sM, lane);
+          else if (P <= 64) w0 = ord_bias_scan<2>(bias, w0, P, sR, s.tg + t0, sM, lane);
+          else w0 = ord_bias_scan<ORD_EL>(bias, w0, P, sR, s.tg + t0, sM, lane);
+        } else {
+          // ---- classification: the chain walked serially (fm_learn_sgd_element.h:63-64) ----
+          for (int t = 0; t < P; t++) {
+            const double y = (double)s.tg[t0 + t];
+            const double p = w0 + sR[t];
+            const double m = -y * (1.0 - 1.0 / (1.0 + exp(-y * p)));
+            if (lane == (t & 31)) sM[t] = m;
+            w0 -= lr * (m + reg0 * w0);
+          }
+        }
+      }
+      if (warp == dwarp) {  // the next run's length: warp 1 searches while warp 0 scans
+        const int Pn = (t0n < nrows) ? ord_detect(s, t0n, nrows, smax, lane) : 1;
+        if (lane == 0) sP[pi ^ 1] = Pn;
+      }
+      ord_group_sync<WS>(1, nthreads);
+      if (act) mult = sM[grp];
+    } else {
+      if (act) {
+        const double y = (double)s.tg[r];
+        if (TASK == 0) {
+          const int st = ord_state(Rloc, lo, hi, inverted);
+          mult = (st == 0 ? Rloc : (st == 1 ? lo : hi)) - y;
+        } else {
+          mult = -y * (1.0 - 1.0 / (1.0 + exp(-y * Rloc)));
+        }
+      }
+      if (warp == 0) {  // the other parity: a slower warp may still be reading this run's length
+        const int Pn = (t0n < nrows) ? ord_detect(s, t0n, nrows, smax, lane) : 1;
+        if (lane == 0) sP[pi ^ 1] = Pn;
+      }
+    }
+
+    // ---- fm_SGD (fm_sgd.h:38-50) for the lane's example: result into the own ring slot -------
+    if (fast) {
+      if (act && !(a.debug & 4)) {
+        const uint32_t cnt = je - jb;
+#pragma unroll
+        for (int e = 0; e < ZR; e++) {
+          if ((uint32_t)e < cnt) {
+            double* own = reinterpret_cast<double*>(smem + rec + (jb + e) * recb);
+            const double x = fx[e], x2 = x * x;
+#pragma unroll
+            for (int q = 0; q < KF; q += 2) {
+              double c0 = fv[e][q], c1 = fv[e][q + 1];
+              c0 -= lr * (mult * (sum[q] * x - c0 * x2) + regv * c0);
+              c1 -= lr * (mult * (sum[q + 1] * x - c1 * x2) + regv * c1);
+              *reinterpret_cast<double2*>(own + q) = make_double2(c0, c1);
+            }
+            if (k1) {
+              double cw = fw[e];
+              cw -= lr * (mult * x + regw * cw);
+              own[kw + (fid[e] & 1u)] = cw;
+            }
+          }
+        }
+      }
+    } else if (act && !(a.debug & 4)) {
+      for (uint32_t j = jb; j < je; j++) {
+        uint32_t jj = j;
+        bool dupj = false;
+        if (rowdup) {
+          dupj = s.link[j] != ORD_NONE && s.link[j] <= j - jb;
+          if (!dupj)
+            while (s.link[jj] != ORD_NONE && s.link[jj] <= jj - jb) jj -= s.link[jj];
+        }
+        // a repeated feature continues from the row's previous write (fm_sgd.h:46 reads v again)
+        const uint32_t so = dupj ? rec + (j - s.link[j]) * recb : s.src[jj];
+        const double* rp_ = reinterpret_cast<const double*>(smem + so);
+        double* own = reinterpret_cast<double*>(smem + rec + j * recb);
+        const uint32_t id = s.col[j];
+        const double x = (double)s.val[j];
+        const uint32_t vo = (k & 1) ? (id & 1u) : 0u;
+        double c[KF];
+        ord_load<KF>(rp_ + vo + f0, c, nf, vec);
+#pragma unroll
+        for (int q = 0; q < KF; q++) {
+          const double grad = sum[q] * x - c[q] * x * x;
+          c[q] -= lr * (mult * grad + regv * c[q]);
+        }
+        ord_store<KF>(own + vo + f0, c, nf, vec);
+        const bool mine = rowdup ? (gl == 0) : ((int)((j - jb) % GL) == gl);
+        if (k1 && mine) {
+          double cw = rp_[kw + (id & 1u)];
+          cw -= lr * (mult * x + regw * cw);
+          own[kw + (id & 1u)] = cw;
+        }
+      }
+    }
+    ord_group_sync<WS>(1, nthreads);  // the run's ring slots (and the next length) are final before the next run reads them
+    t0 = t0n;
+    pi ^= 1;
+  }
+}
+
+// Write-back of tile T by `nthreads` threads (tid in [0, nthreads)): the tile's FINAL records go to global
+// memory in one pass.  Per-update stores made every run's barrier wait behind them (r02 ncu); an entry
+// whose feature is rewritten later in this tile (sup) never needs to leave the SM.  Also re-zeroes sup[].
+template <bool WS>
+__device__ __forceinline__ void ord_writeback(const OrderedArgs& a, unsigned char* smem, const OrdConsts& cc,
+                                              uint32_t T, int tid, int nthreads) {
+  const int k = cc.k, kw = cc.kw;
+  const bool k1 = cc.k1;
+  const uint32_t recb = cc.recb;
+  const OrdStage s = ord_stage(a, smem, T);
+  const uint64_t r0 = (uint64_t)T * a.tile_rows;
+  const int nrows = (int)min((uint64_t)a.tile_rows, a.n_rows - r0);
+  const uint64_t ab = s.rp[0] & ~3ull;
+  const uint32_t rec = ord_rec_base(a, T);
+  // ---- write-back: the tile's FINAL records go to global memory in one pass.  Per-update stores
+  // made every run's barrier wait for their acknowledgement (r02 ncu: half of all stall samples on
+  // the barriers, 5 200 cycles per run); an entry whose feature is rewritten later in this tile
+  // (sup) never needs to leave the SM.  The next tile's fetches are issued behind the barrier of
+  // ord_prep, i.e. after these stores.
+  if (!(a.debug & 1)) {
+    const uint32_t j0 = (uint32_t)(s.rp[0] - ab), j1 = (uint32_t)(s.rp[nrows] - ab);
+    if ((k & 1) == 0) {
+      // consecutive threads write consecutive 16-byte pieces (kw/2 factor pairs + the linear weight) of
+      // consecutive records: every lane busy, rows coalesced; (record, piece) advance without a division
+      const uint32_t pieces = (uint32_t)(kw / 2) + 1u;
+      const uint32_t dj = (uint32_t)nthreads / pieces, dp = (uint32_t)nthreads % pieces;
+      uint32_t j = j0 + (uint32_t)tid / pieces, pc = (uint32_t)tid % pieces;
+      while (j < j1) {
+        if (!s.sup[j]) {
+          const double* own = reinterpret_cast<const double*>(smem + rec + j * recb);
+          const uint32_t id = s.col[j];
+          if (pc < pieces - 1u) {
+            *reinterpret_cast<double2*>(a.v + (size_t)id * k + 2u * pc) = *reinterpret_cast<const double2*>(own + 2u * pc);
+          } else if (k1) {
+            a.w[id] = own[kw + (id & 1u)];
+          }
+        }
+        j += dj;
+        pc += dp;
+        if (pc >= pieces) {
+          pc -= pieces;
+          j++;
+        }
+      }
+      ord_group_sync<WS>(2, nthreads);  // every piece of a record has read its flag
+      for (uint32_t jz = j0 + tid; jz < j1; jz += nthreads) s.sup[jz] = 0;
+    } else {
+      for (uint32_t j = j0 + tid; j < j1; j += nthreads) {
+        const unsigned char sup = s.sup[j];
+        s.sup[j] = 0;
+        if (sup) continue;
+        const double* own = reinterpret_cast<const double*>(smem + rec + j * recb);
+        const uint32_t id = s.col[j];
+        const uint32_t vo = id & 1u;
+        double* gv = a.v + (size_t)id * k;
+        for (int q = 0; q < k; q++) gv[q] = own[vo + q];
+        if (k1) a.w[id] = own[kw + (id & 1u)];
+      }
+    }
+  } else {
+    const uint32_t j0 = (uint32_t)(s.rp[0] - ab), j1 = (uint32_t)(s.rp[nrows] - ab);
+    for (uint32_t j = j0 + tid; j < j1; j += nthreads) s.sup[j] = 0;
+  }
+}
+
+// ---- driver 1: every thread does everything, phases separated by CTA barriers ------------------------
+template <int GL, int KF, int TASK, int ZF = 0>
+__device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigned char* smem) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+  const int smax = min(ORD_SMAX, nthreads / GL);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  int* sP = reinterpret_cast<int*>(smem + 32);
 
   if (tid == 0) {
     for (int i = 0; i < ORD_NBUF; i++) mbar_init(bars + i, 1);
@@ -339,24 +664,8 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
   }
   __syncthreads();
 
-  const int k = a.k, kw = a.kw;
-  const bool k0 = a.use_w0 != 0, k1 = a.use_w != 0;
-  const double lr = a.lr, reg0 = a.reg0, regw = a.regw, regv = a.regv;
-  const double lo = a.min_target, hi = a.max_target;
-  const bool inverted = hi < lo;
-  const double a_mid = 1.0 - lr * (1.0 + reg0), a_out = 1.0 - lr * reg0;
-  OrdBias bias;
-  bias.lr = lr;
-  bias.lo = lo;
-  bias.hi = hi;
-  bias.a_mid = a_mid;
-  bias.a_out = a_out;
-  bias.inverted = inverted;
-  const uint32_t recb = (uint32_t)a.rs * 8u;
-  const int f0 = gl * KF;                       // this lane's first factor
-  const int nf = max(0, min(KF, k - f0));       // ... and how many of its KF slots are real
-  const bool vec = ((k & 1) == 0) && (KF % 2 == 0);  // 16-byte aligned factor slices
-  double w0 = k0 ? *a.w0 : 0.0;                 // live in warp 0 only
+  const OrdConsts cc = ord_consts(a);
+  double w0 = cc.k0 ? *a.w0 : 0.0;  // live in warp 0 only
   const uint32_t NT = a.n_tiles;
   const int TR = a.tile_rows;
 
@@ -393,213 +702,18 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
     }
     cp_async_commit();
     cp_async_wait_1();  // this thread's fetches for tile T have landed
-    const OrdStage s = ord_stage(a, smem, T);
-    const uint64_t r0 = (uint64_t)T * TR;
-    const int nrows = (int)min((uint64_t)TR, a.n_rows - r0);
-    if (warp == 0) {  // length of the tile's first run (reads the CSR stage only: complete since the mbarrier)
+    if (warp == 0) {    // length of the tile's first run (reads the CSR stage only: complete since the mbarrier)
+      const OrdStage s = ord_stage(a, smem, T);
+      const int nrows = (int)min((uint64_t)TR, a.n_rows - (uint64_t)T * TR);
       const int P0 = ord_detect(s, 0, nrows, smax, lane);
       if (lane == 0) sP[0] = P0;
     }
     __syncthreads();  // ... everyone's fetches; src[] of tile T; the first run length
-
-    const uint64_t ab = s.rp[0] & ~3ull;
-    const uint32_t rec = ord_rec_base(a, T);
-
-    int t0 = 0;
-    int pi = 0;  // parity of the run inside the tile
-    while (t0 < nrows) {
-      const int P = sP[pi];
-      // ---- scores of the run's examples: fm_model.h:105-127 with R_t = p_t - w0 ----------
-      const bool act = grp < P;
-      const int r = t0 + grp;
-      uint32_t jb = 0, je = 0;
-      bool rowdup = false;
-      double sum[KF];
-#pragma unroll
-      for (int q = 0; q < KF; q++) sum[q] = 0.0;
-      double Rloc = 0.0;
-      if (act) {
-        jb = (uint32_t)(s.rp[r] - ab);
-        je = (uint32_t)(s.rp[r + 1] - ab);
-        rowdup = s.rd[r] == 0u;
-      }
-      if (act && !(a.debug & 8)) {
-        double ssq[KF];
-#pragma unroll
-        for (int q = 0; q < KF; q++) ssq[q] = 0.0;
-        for (uint32_t j = jb; j < je; j++) {
-          uint32_t jj = j;
-          if (rowdup)  // a feature named twice: both entries score with the value before the row
-            while (s.link[jj] != ORD_NONE && s.link[jj] <= jj - jb) jj -= s.link[jj];
-          const double* rp_ = reinterpret_cast<const double*>(smem + s.src[jj]);
-          const uint32_t id = s.col[j];
-          const double x = (double)s.val[j];
-          const uint32_t vo = (k & 1) ? (id & 1u) : 0u;
-          double vv[KF];
-          ord_load<KF>(rp_ + vo + f0, vv, nf, vec);
-#pragma unroll
-          for (int q = 0; q < KF; q++) {
-            const double d = vv[q] * x;  // slots beyond k hold 0
-            sum[q] += d;
-            ssq[q] += d * d;
-          }
-          if (k1 && (int)((j - jb) % GL) == gl) Rloc += rp_[kw + (id & 1u)] * x;
-        }
-#pragma unroll
-        for (int q = 0; q < KF; q++) Rloc += 0.5 * (sum[q] * sum[q] - ssq[q]);
-      }
-#pragma unroll
-      for (int o = GL / 2; o > 0; o >>= 1) Rloc += ord_shfl_xor(Rloc, o);
-
-      const int t0n = t0 + P;
-      double mult = 0.0;
-      if (k0) {
-        if (act && gl == 0) sR[grp] = Rloc;
-        __syncthreads();
-        if (warp == 0) {
-          if (a.debug & 2) {
-            if (lane < ORD_EL) {
-              for (int t = lane; t < P; t += ORD_EL) sM[t] = 0.0;
-            }
-          } else if (TASK == 0) {
-            // ---- bias: affine prefix scan over the run, as few examples per lane as the run needs ----
-            if (P <= 32) w0 = ord_bias_scan<1>(bias, w0, P, sR, s.tg + t0, sM, lane);
-            else if (P <= 64) w0 = ord_bias_scan<2>(bias, w0, P, sR, s.tg + t0, sM, lane);
-            else w0 = ord_bias_scan<ORD_EL>(bias, w0, P, sR, s.tg + t0, sM, lane);
-          } else {
-            // ---- classification: the chain walked serially (fm_learn_sgd_element.h:63-64) ----
-            for (int t = 0; t < P; t++) {
-              const double y = (double)s.tg[t0 + t];
-              const double p = w0 + sR[t];
-              const double m = -y * (1.0 - 1.0 / (1.0 + exp(-y * p)));
-              if (lane == (t & 31)) sM[t] = m;
-              w0 -= lr * (m + reg0 * w0);
-            }
-          }
-        }
-        if (warp == dwarp) {  // the next run's length: warp 1 searches while warp 0 scans
-          const int Pn = (t0n < nrows) ? ord_detect(s, t0n, nrows, smax, lane) : 1;
-          if (lane == 0) sP[pi ^ 1] = Pn;
-        }
-        __syncthreads();
-        if (act) mult = sM[grp];
-      } else {
-        if (act) {
-          const double y = (double)s.tg[r];
-          if (TASK == 0) {
-            const int st = ord_state(Rloc, lo, hi, inverted);
-            mult = (st == 0 ? Rloc : (st == 1 ? lo : hi)) - y;
-          } else {
-            mult = -y * (1.0 - 1.0 / (1.0 + exp(-y * Rloc)));
-          }
-        }
-        if (warp == 0) {  // the other parity: a slower warp may still be reading this run's length
-          const int Pn = (t0n < nrows) ? ord_detect(s, t0n, nrows, smax, lane) : 1;
-          if (lane == 0) sP[pi ^ 1] = Pn;
-        }
-      }
-
-      // ---- fm_SGD (fm_sgd.h:38-50) for the lane's example: result into the own ring slot -------
-      if (act && !(a.debug & 4)) {
-        for (uint32_t j = jb; j < je; j++) {
-          uint32_t jj = j;
-          bool dupj = false;
-          if (rowdup) {
-            dupj = s.link[j] != ORD_NONE && s.link[j] <= j - jb;
-            if (!dupj)
-              while (s.link[jj] != ORD_NONE && s.link[jj] <= jj - jb) jj -= s.link[jj];
-          }
-          // a repeated feature continues from the row's previous write (fm_sgd.h:46 reads v again)
-          const uint32_t so = dupj ? rec + (j - s.link[j]) * recb : s.src[jj];
-          const double* rp_ = reinterpret_cast<const double*>(smem + so);
-          double* own = reinterpret_cast<double*>(smem + rec + j * recb);
-          const uint32_t id = s.col[j];
-          const double x = (double)s.val[j];
-          const uint32_t vo = (k & 1) ? (id & 1u) : 0u;
-          double c[KF];
-          ord_load<KF>(rp_ + vo + f0, c, nf, vec);
-#pragma unroll
-          for (int q = 0; q < KF; q++) {
-            const double grad = sum[q] * x - c[q] * x * x;
-            c[q] -= lr * (mult * grad + regv * c[q]);
-          }
-          ord_store<KF>(own + vo + f0, c, nf, vec);
-          const bool mine = rowdup ? (gl == 0) : ((int)((j - jb) % GL) == gl);
-          if (k1 && mine) {
-            double cw = rp_[kw + (id & 1u)];
-            cw -= lr * (mult * x + regw * cw);
-            own[kw + (id & 1u)] = cw;
-          }
-        }
-      }
-      __syncthreads();  // the run's ring slots (and the next length) are final before the next run reads them
-      t0 = t0n;
-      pi ^= 1;
-    }
-    // ---- write-back: the tile's FINAL records go to global memory in one pass.  Per-update stores
-    // made every run's barrier wait for their acknowledgement (r02 ncu: half of all stall samples on
-    // the barriers, 5 200 cycles per run); an entry whose feature is rewritten later in this tile
-    // (sup) never needs to leave the SM.  The next tile's fetches are issued behind the barrier of
-    // ord_prep, i.e. after these stores.
-    if (!(a.debug & 1)) {
-      const uint32_t j0 = (uint32_t)(s.rp[0] - ab), j1 = (uint32_t)(s.rp[nrows] - ab);
-      if ((k & 1) == 0) {
-        // 2^lg consecutive threads write the 16-byte pieces of one record (kw/2 factor pairs + the
-        // linear weight): coalesced rows, no division
-        const uint32_t pieces = (uint32_t)(kw / 2) + 1u;
-        uint32_t lg = 0;
-        while ((1u << lg) < pieces) lg++;
-        const uint32_t pc = tid & ((1u << lg) - 1u);
-        const uint32_t step = (uint32_t)nthreads >> lg;  // records per sweep of the CTA
-        if (step == 0) {  // more pieces than threads (k > 2 * blockDim): one thread per record
-          for (uint32_t j = j0 + tid; j < j1; j += nthreads) {
-            const unsigned char sup = s.sup[j];
-            s.sup[j] = 0;
-            if (sup) continue;
-            const double* own = reinterpret_cast<const double*>(smem + rec + j * recb);
-            const uint32_t id = s.col[j];
-            for (int q = 0; q < k; q += 2)
-              *reinterpret_cast<double2*>(a.v + (size_t)id * k + q) = *reinterpret_cast<const double2*>(own + q);
-            if (k1) a.w[id] = own[kw + (id & 1u)];
-          }
-        } else {
-          for (uint32_t j = j0 + ((uint32_t)tid >> lg); j < j1; j += step) {
-            if (!s.sup[j]) {
-              const double* own = reinterpret_cast<const double*>(smem + rec + j * recb);
-              const uint32_t id = s.col[j];
-              for (uint32_t q = pc; q < pieces; q += (1u << lg)) {
-                if (q < pieces - 1u) {
-                  *reinterpret_cast<double2*>(a.v + (size_t)id * k + 2u * q) =
-                      *reinterpret_cast<const double2*>(own + 2u * q);
-                } else if (k1) {
-                  a.w[id] = own[kw + (id & 1u)];
-                }
-              }
-            }
-          }
-          __syncthreads();  // every lane of a record has read its flag
-          for (uint32_t j = j0 + tid; j < j1; j += nthreads) s.sup[j] = 0;
-        }
-      } else {
-        for (uint32_t j = j0 + tid; j < j1; j += nthreads) {
-          const unsigned char sup = s.sup[j];
-          s.sup[j] = 0;
-          if (sup) continue;
-          const double* own = reinterpret_cast<const double*>(smem + rec + j * recb);
-          const uint32_t id = s.col[j];
-          const uint32_t vo = id & 1u;
-          double* gv = a.v + (size_t)id * k;
-          for (int q = 0; q < k; q++) gv[q] = own[vo + q];
-          if (k1) a.w[id] = own[kw + (id & 1u)];
-        }
-      }
-    } else {
-      const uint32_t j0 = (uint32_t)(s.rp[0] - ab), j1 = (uint32_t)(s.rp[nrows] - ab);
-      for (uint32_t j = j0 + tid; j < j1; j += nthreads) s.sup[j] = 0;
-    }
+    ord_tile_runs<GL, KF, TASK, ZF, false>(a, smem, cc, T, tid, nthreads, w0);
+    ord_writeback<false>(a, smem, cc, T, tid, nthreads);
     __syncthreads();  // stage T%3 is read above and refilled by the TMA issue at the top of tile T+1
   }
-  if (tid == 0 && k0) *a.w0 = w0;
+  if (tid == 0 && cc.k0) *a.w0 = w0;
 }
 
 }  // namespace fmb

@@ -114,7 +114,7 @@ void build_links(const Csr& d, uint32_t n_feat, std::vector<uint32_t>& link, std
     }
 }
 
-template <int GL, int KF>
+template <int GL, int KF, int ZF = 0>
 void run_threads(const fmb::OrderedArgs& a, unsigned char* smem, int task, int nthreads) {
   simt::bdim.x = (unsigned)nthreads;
   pthread_barrier_init(&simt::cta_barrier, nullptr, nthreads);
@@ -123,15 +123,19 @@ void run_threads(const fmb::OrderedArgs& a, unsigned char* smem, int task, int n
   for (int t = 0; t < nthreads; t++)
     th.emplace_back([&, t]() {
       simt::tid.x = (unsigned)t;
-      if (task == 0) fmb::ordered_epoch_body<GL, KF, 0>(a, smem);
-      else fmb::ordered_epoch_body<GL, KF, 1>(a, smem);
+      if (task == 0) fmb::ordered_epoch_body<GL, KF, 0, ZF>(a, smem);
+      else fmb::ordered_epoch_body<GL, KF, 1, ZF>(a, smem);
     });
   for (auto& x : th) x.join();
   pthread_barrier_destroy(&simt::cta_barrier);
   for (int w = 0; w < nthreads / 32; w++) pthread_barrier_destroy(&simt::warp_barrier[w]);
 }
 
-void dispatch(int k, const fmb::OrderedArgs& a, unsigned char* smem, int task, int nthreads) {
+void dispatch(int k, const fmb::OrderedArgs& a, unsigned char* smem, int task, int nthreads, int max_nnz) {
+  // the register-resident fast path where the launcher would pick it (fm_ordered.cu::pick_fast_kernel)
+  if (k == 8 && max_nnz >= 1 && max_nnz <= 2) return run_threads<1, 8, 2>(a, smem, task, nthreads);
+  if (k == 8 && max_nnz >= 1 && max_nnz <= 4) return run_threads<1, 8, 4>(a, smem, task, nthreads);
+  if (k == 4 && max_nnz >= 1 && max_nnz <= 4) return run_threads<1, 4, 4>(a, smem, task, nthreads);
   if (k <= 1) run_threads<1, 1>(a, smem, task, nthreads);
   else if (k <= 2) run_threads<1, 2>(a, smem, task, nthreads);
   else if (k <= 4) run_threads<1, 4>(a, smem, task, nthreads);
@@ -229,9 +233,11 @@ bool run_case(const Case& c) {
   a.rec_bytes = TE * (uint32_t)rs * 8u;
   a.debug = 0;
 
+  int max_nnz = 0;
+  for (uint64_t i = 0; i < N; i++) max_nnz = std::max<int>(max_nnz, (int)(d.row_ptr[i + 1] - d.row_ptr[i]));
   const int epochs = 2;
   for (int ep = 0; ep < epochs; ep++) {
-    if (N > 0) dispatch(k, a, smem, c.task, c.warps * 32);
+    if (N > 0) dispatch(k, a, smem, c.task, c.warps * 32, max_nnz);
     fmo_sgd_epoch(n, k, c.k0, c.k1, &ow0, ow.data(), ov.data(), c.lr, c.regs[0], c.regs[1], c.regs[2], c.task,
                   a.min_target, a.max_target, N, d.row_ptr.data(), d.col.data(), d.val.data(), d.target.data());
   }
