@@ -127,5 +127,7 @@ inline void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* 
 inline void cp_async_16(void* dst, const void* src) { memcpy(dst, src, 16); }
 inline void cp_async_commit() {}
 inline void cp_async_wait_1() {}
+// the single-role driver never takes the named-barrier branch (WS == false)
+inline void named_bar_sync(int, int) { __builtin_trap(); }
 
 }  // namespace fmb
