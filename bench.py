@@ -20,8 +20,8 @@ parity : RMSE trajectory of the timed mode against the sequential oracle on a pl
          C2-shaped set from the same initial model (N == 1).
 tolerance_mode : the same workload in FMB200_MODE_ORDERED (sequentially consistent, fp64, inside
          the 1e-5 RMSE gate): examples/s device-timed and end to end, and its parity numbers.
-extra  : BASELINE configs C3 (k=64, 39 nnz/row, 1M features, 10M rows) and C2 with Zipf(1) ids,
-         each with its own roofline object (N == 1; --no-extras skips them).
+extra  : BASELINE configs C3 (k=64, 39 nnz/row, 1M features, 10M rows), C2 with Zipf(1) ids and C4 (the MCMC
+         e-term pass, k=16, ML-10M shape), each with its own roofline object (N == 1; --no-extras skips them).
 """
 from __future__ import annotations
 
@@ -289,6 +289,56 @@ def extra_config(name, data, k, task, device, steps, warmup, flush, stream, torc
             "kernel_geometry": cfg}
 
 
+def extra_c4(device, rows, passes=5):
+    """BASELINE config C4: the data-parallel part of -method mcmc, the per-iteration e-term pass
+    (fm_learn_mcmc.h:148-378) over a MovieLens-10M-shaped set, k=16, through fmb200_mcmc_eterms with a HOST
+    result buffer (the Gibbs draws stay on the host, so the read-back belongs to the step)."""
+    import numpy as np
+    import oracle
+    from libfm_b200 import FmLearnSgdElement, FmModel, MODE_INORDER, synth
+    d = synth.two_field(rows, 71_567, 10_681, seed=5)
+    k = 16
+    fm = FmModel(d.num_feature, k)
+    fm.init_stdev = 0.1
+    fm.init_numpy(42)
+    fm.w = np.random.default_rng(1).standard_normal(d.num_feature) * 0.1
+    l = FmLearnSgdElement(fm, device=device, mode=MODE_INORDER)
+    l.push_hparams()
+    l.upload(d, 0)
+    launches0 = l.kernel_launches()
+    got = l.mcmc_eterms(d)  # warm-up
+    ts = []
+    for _ in range(passes):
+        t0 = time.perf_counter()
+        got = l.mcmc_eterms(d)
+        ts.append(time.perf_counter() - t0)
+    launches = (l.kernel_launches() - launches0) // (passes + 1)
+    l.close()
+    # the oracle port (pinned bit-identical to the reference's pass) on a bounded sample, 1 core
+    sample = d.rows(0, min(rows, 1_000_000))
+    port = oracle.Port(d.num_feature, k)
+    port.set_params(fm.w0, fm.w, fm.v)
+    t0 = time.perf_counter()
+    want = port.mcmc_eterms(sample)
+    cpu_s = time.perf_counter() - t0
+    ms = 1e3 * statistics.median(ts)
+    peak, peak_src = hbm_peak()
+    bpe = 2 * k * 2 * 4
+    achieved = rows * bpe / (ms * 1e-3) / 1e9
+    return {"workload": "C4: MCMC/ALS e-term pass, k=16, MovieLens-10M-shaped CSR (71567 users x 10681 items, "
+                        "%d cases, 2 nnz/row); fp64, bit-identical to the reference's accumulation order" % rows,
+            "rows": rows, "k": k, "value": rows / (ms * 1e-3), "unit": "cases/s", "ms_per_step": ms, "steps": passes,
+            "timing": "wall clock around fmb200_mcmc_eterms incl. the device->host copy of the e-terms",
+            "d2h_bytes_per_step": int(got.nbytes), "gpu_launches": int(launches), "dtype": "f64",
+            "bit_identical_to_oracle_on_sample": bool(np.array_equal(got[:sample.num_cases], want)),
+            "cpu_baseline": {"value": sample.num_cases / cpu_s, "unit": "cases/s", "cores": 1, "kind": "port",
+                             "sample": "%d cases" % sample.num_cases},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_example": bpe,
+                         "kernel": "fm_eterm64_kernel (one thread per case, fp64, --fmad=false)",
+                         "note": "the step is bound by the 8 B/case read-back over PCIe, not by HBM"}}
+
+
 # --------------------------------------------------------------------------
 # the GPU arm
 # --------------------------------------------------------------------------
@@ -543,6 +593,7 @@ def run_gpu_arm(args):
                                            "-task c, Hogwild" % args.c3_rows, d3, 64, 1, local_rank, 5, 3, flush,
                                            stream, torch, "c3")
                 del d3
+                extra["c4"] = extra_c4(local_rank, args.c4_rows)
             except Exception as exc:  # an extra must never cost the headline line
                 extra["error"] = repr(exc)
 
@@ -592,6 +643,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-tolerance-mode", action="store_true")
     ap.add_argument("--c3-rows", type=int, default=10_000_000)
+    ap.add_argument("--c4-rows", type=int, default=10_000_054)
     ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--exchange", default="meanfield", choices=["meanfield", "mean"])
     args = ap.parse_args()

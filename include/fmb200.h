@@ -174,7 +174,10 @@ int fmb200_allreduce_mean(fmb200_ctx* ctx);
  * relative size of one shard-epoch's step on parameter i (from the per-feature counts every upload
  * builds): parameters a shard-epoch already converges (the bias, hot features) are averaged, barely
  * touched ones are summed.  8 shards then follow the single-stream trajectory instead of advancing
- * 1/8 epoch per epoch.  Call after every epoch, like fmb200_allreduce_mean. */
+ * 1/8 epoch per epoch.  Call after every epoch, like fmb200_allreduce_mean.
+ * State of 8 MB and more takes the SLICED form: rank r combines slice r (read from all replicas) and pushes
+ * it into every rank's buffers -- 2(G-1)/G x state bytes over NVLink per rank instead of (G-1) x -- followed
+ * by a peer barrier (fmb200_set_tuning variant 8 forces it, 9 forces the one-shot kernel). */
 int fmb200_allreduce_meanfield(fmb200_ctx* ctx);
 /* stream-ordered barrier across the attached peers (no data); used to align ranks */
 int fmb200_peer_barrier(fmb200_ctx* ctx);

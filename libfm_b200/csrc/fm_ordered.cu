@@ -52,7 +52,7 @@ __global__ void ord_link_kernel(const uint32_t* __restrict__ ids, const uint32_t
 // blockDim <= ORD_SMAX * GL (one group of GL lanes per example of a run): small k leaves the
 // register file to few threads (k <= 8: 128 threads)
 template <int GL, int KF, int TASK, int ZF = 0>
-__global__ void __launch_bounds__((ORD_SMAX * GL < 512 ? 512 : (ORD_SMAX * GL < ORD_MAX_THREADS ? ORD_SMAX * GL : ORD_MAX_THREADS)), 1)
+__global__ void __launch_bounds__((ORD_SMAX * GL < 256 ? 256 : (ORD_SMAX * GL < ORD_MAX_THREADS ? ORD_SMAX * GL : ORD_MAX_THREADS)), 1)
     fm_sgd_ordered_kernel(const OrderedArgs a) {
   extern __shared__ __align__(128) unsigned char ord_smem[];
   ordered_epoch_body<GL, KF, TASK, ZF>(a, ord_smem);
@@ -238,7 +238,7 @@ cudaError_t launch_sgd_ordered(fmb200_ctx* c, DataSlot& d, bool* handled) {
   ordered_shape(c->k, &GL, &KF);
   // one group of GL lanes per example of a run: min(ORD_SMAX, 1024 / GL) examples
   int threads = std::min(ORD_SMAX * GL, ORD_MAX_THREADS);
-  const int bound = std::max(threads, 512);  // the kernel's launch bound
+  const int bound = std::max(threads, 256);  // the kernel's launch bound
   if (c->tune_threads)  // fewer threads = shorter runs; more = helper warps for the fetch issue / write-back
     threads = std::min(bound, std::max(32, (c->tune_threads / (32 > GL ? 32 : GL)) * (32 > GL ? 32 : GL)));
   OrdFn fn = c->hp.task == FMB200_TASK_REGRESSION ? pick_kernel<0>(c->k) : pick_kernel<1>(c->k);

@@ -54,8 +54,11 @@ constexpr uint32_t ORD_NONE = 0xffffffffu;
 constexpr int ORD_SMAX = 128;  // examples per run: ORD_EL per lane in the bias scan
 constexpr int ORD_EL = ORD_SMAX / 32;
 constexpr int ORD_NBUF = 3;    // ring depth (CSR stages and record buffers)
-// [0,24) mbarriers | [32,36) next run length | [64, +1024) sR (scores) | [1088, +1024) sM (multipliers)
-constexpr int ORD_HDR_BYTES = 64 + 2 * ORD_SMAX * 8 + 64;
+// [0,24) mbarriers | [32,40) run lengths | [40,48) first contradicted clamp guess, by iteration parity |
+// [64, +2048) sAB: per example (a_t, b_t) of its bias step w -> a_t w + b_t   (classification: sR scores | sM
+// multipliers) | [2112, +1032) sW: the bias each example of the run reads, sW[P] = the bias after the run
+constexpr int ORD_HDR_BYTES = 3200;
+constexpr int ORD_SW_OFF = 64 + 2 * ORD_SMAX * 8;
 constexpr int ORD_MAX_THREADS = 1024;
 
 struct OrderedArgs {
@@ -252,68 +255,41 @@ __device__ __forceinline__ void ord_store(double* p, const double (&v)[KF], int 
   }
 }
 
-// The bias chain of one run, regression (executed by ONE warp): EL consecutive examples per lane
-// (EL*32 >= P).  Returns the bias after the run; sM[t] receives example t's multiplier
-// (fm_learn_sgd_element.h:58-62: mult = -(y - clamp(w0_t + R_t))).
+// The bias chain of one run, regression.  The step  w0' = w0 - lr((clamp(w0 + R_t) - y_t) + reg0 w0)
+// (fm_learn_sgd_element.h:58-62, fm_sgd.h:34-37) is affine in w0 once the example's clamp state (inside / at
+// min / at max) is fixed: w0' = a_t w0 + b_t.  Every example's own thread GUESSES its state from the bias at
+// the start of the run and publishes (a_t, b_t); ONE thread then walks  w <- fma(a_t, w, b_t)  -- one
+// dependent DFMA per example (8 cycles on B200; the Kogge-Stone scan this replaces spent 270 dependent
+// instructions, ~2 700 cycles, per run: profiles/r02_ordered_v5_ncu_summary.md) -- and leaves in sW[t] the bias
+// example t reads.  The examples' threads then check their guess against that bias in parallel; the first
+// contradicted one corrects its pair and the chain is walked again from there (a consistent assignment IS the
+// sequential answer, by induction over t; every pass finalises at least one more example).
 struct OrdBias {
   double lr, lo, hi, a_mid, a_out;
   bool inverted;
 };
-template <int EL>
-__device__ __forceinline__ double ord_bias_scan(const OrdBias& c, double w0, int P, const double* sR,
-                                                const float* tg, double* sM, int lane) {
-  const unsigned full = 0xffffffffu;
-  double R[EL], y[EL], aa[EL], bb[EL], wv[EL];
-  int st[EL];
-  bool on[EL];
-#pragma unroll
-  for (int e = 0; e < EL; e++) {
-    const int t = EL * lane + e;
-    on[e] = t < P;
-    R[e] = on[e] ? sR[t] : 0.0;
-    y[e] = on[e] ? (double)tg[t] : 0.0;
-    st[e] = ord_state(w0 + R[e], c.lo, c.hi, c.inverted);
+__device__ __forceinline__ double2 ord_bias_pair(const OrdBias& c, int st, double R, double y) {
+  return make_double2(st == 0 ? c.a_mid : c.a_out, -c.lr * ((st == 0 ? R : (st == 1 ? c.lo : c.hi)) - y));
+}
+__device__ __forceinline__ void ord_bias_chain(const double2* sAB, double* sW, int from, int P, double w) {
+  int t = from;
+  for (; t + 4 <= P; t += 4) {  // the loads do not depend on the chain: issued ahead of it
+    const double2 p0 = sAB[t], p1 = sAB[t + 1], p2 = sAB[t + 2], p3 = sAB[t + 3];
+    sW[t] = w;
+    w = fma(p0.x, w, p0.y);
+    sW[t + 1] = w;
+    w = fma(p1.x, w, p1.y);
+    sW[t + 2] = w;
+    w = fma(p2.x, w, p2.y);
+    sW[t + 3] = w;
+    w = fma(p3.x, w, p3.y);
   }
-  double A = 1.0, B = 0.0;
-  for (int it = 0; it <= 2 * ORD_SMAX; it++) {
-    A = 1.0;
-    B = 0.0;
-#pragma unroll
-    for (int e = 0; e < EL; e++) {
-      aa[e] = on[e] ? (st[e] == 0 ? c.a_mid : c.a_out) : 1.0;
-      bb[e] = on[e] ? -c.lr * ((st[e] == 0 ? R[e] : (st[e] == 1 ? c.lo : c.hi)) - y[e]) : 0.0;
-      B = aa[e] * B + bb[e];  // w -> aa*(A w + B) + bb
-      A = aa[e] * A;
-    }
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double Ap = ord_shfl_up(A, o), Bp = ord_shfl_up(B, o);
-      if (lane >= o) {
-        B = A * Bp + B;
-        A = A * Ap;
-      }
-    }
-    double Ae = ord_shfl_up(A, 1), Be = ord_shfl_up(B, 1);
-    if (lane == 0) {
-      Ae = 1.0;
-      Be = 0.0;
-    }
-    double w = Ae * w0 + Be;
-    bool bad = false;
-#pragma unroll
-    for (int e = 0; e < EL; e++) {
-      wv[e] = w;  // the bias example e reads
-      const int ns = ord_state(w + R[e], c.lo, c.hi, c.inverted);
-      bad = bad || (on[e] && ns != st[e]);
-      st[e] = ns;
-      w = aa[e] * w + bb[e];
-    }
-    if (!__any_sync(full, bad)) break;
+  for (; t < P; t++) {
+    const double2 p0 = sAB[t];
+    sW[t] = w;
+    w = fma(p0.x, w, p0.y);
   }
-#pragma unroll
-  for (int e = 0; e < EL; e++)
-    if (on[e]) sM[EL * lane + e] = (st[e] == 0 ? wv[e] + R[e] : (st[e] == 1 ? c.lo : c.hi)) - y[e];
-  return ord_shfl(A, 31) * w0 + ord_shfl(B, 31);
+  sW[P] = w;
 }
 
 // barrier over one role's threads: the whole CTA (0), or a named barrier over the role (WS)
@@ -360,17 +336,20 @@ __device__ __forceinline__ OrdConsts ord_consts(const OrderedArgs& a) {
 // second read.  Rows that name a feature twice (singleton runs) take the general path.
 //
 // All runs of tile T, executed by the `nthreads` compute threads (tid in [0, nthreads)); sP[0] holds the
-// length of the tile's first run.  w0 is live in warp 0.
+// length of the tile's first run.  Every thread carries the bias w0 (the clamp guesses start from it).
 template <int GL, int KF, int TASK, int ZF, bool WS>
 __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned char* smem, const OrdConsts& cc,
-                                              uint32_t T, int tid, int nthreads, double& w0) {
+                                              uint32_t T, int tid, int nthreads, double& w0, uint32_t& it) {
   const int lane = tid & 31, warp = tid >> 5;
   const int gl = tid % GL;   // lane inside the example's group
   const int grp = tid / GL;  // example slot inside a run
   const int smax = min(ORD_SMAX, nthreads / GL);
   int* sP = reinterpret_cast<int*>(smem + 32);  // [2]: run lengths, double-buffered by run parity
+  int* sBad = reinterpret_cast<int*>(smem + 40);  // [2]: first contradicted guess, by pass parity
   double* sR = reinterpret_cast<double*>(smem + 64);
   double* sM = sR + ORD_SMAX;
+  double2* sAB = reinterpret_cast<double2*>(smem + 64);
+  double* sW = reinterpret_cast<double*>(smem + ORD_SW_OFF);
   const int dwarp = nthreads > 32 ? 1 : 0;  // the warp that searches the next run
   const int k = cc.k, kw = cc.kw;
   const bool k0 = cc.k0, k1 = cc.k1;
@@ -414,18 +393,26 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
         const uint32_t cnt = je - jb;
 #pragma unroll
         for (int e = 0; e < ZR; e++) {
-          const bool on = (uint32_t)e < cnt;
-          const uint32_t j = jb + (on ? e : 0);
-          const double* rp_ = reinterpret_cast<const double*>(smem + s.src[j]);
-          fid[e] = s.col[j];
-          fx[e] = on ? (double)s.val[j] : 0.0;
+          // slots beyond the row's length hold zeros and touch nothing: an empty row's jb may lie past the
+          // tile's last entry, where src[] was never written (a misaligned shared-memory address on the device)
+          fid[e] = 0u;
+          fx[e] = 0.0;
+          fw[e] = 0.0;
 #pragma unroll
-          for (int q = 0; q < KF; q += 2) {
-            const double2 t2 = *reinterpret_cast<const double2*>(rp_ + q);
-            fv[e][q] = on ? t2.x : 0.0;
-            fv[e][q + 1] = on ? t2.y : 0.0;
+          for (int q = 0; q < KF; q++) fv[e][q] = 0.0;
+          if ((uint32_t)e < cnt) {
+            const uint32_t j = jb + e;
+            const double* rp_ = reinterpret_cast<const double*>(smem + s.src[j]);
+            fid[e] = s.col[j];
+            fx[e] = (double)s.val[j];
+#pragma unroll
+            for (int q = 0; q < KF; q += 2) {
+              const double2 t2 = *reinterpret_cast<const double2*>(rp_ + q);
+              fv[e][q] = t2.x;
+              fv[e][q + 1] = t2.y;
+            }
+            if (k1) fw[e] = rp_[kw + (fid[e] & 1u)];
           }
-          fw[e] = (on && k1) ? rp_[kw + (fid[e] & 1u)] : 0.0;
         }
         double ssq[KF];
 #pragma unroll
@@ -472,38 +459,148 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
     for (int o = GL / 2; o > 0; o >>= 1) Rloc += ord_shfl_xor(Rloc, o);
 
     const int t0n = t0 + P;
-    double mult = 0.0;
-    if (k0) {
-      if (act && gl == 0) sR[grp] = Rloc;
-      ord_group_sync<WS>(1, nthreads);
-      if (warp == 0) {
-        if (a.debug & 2) {
-          if (lane < ORD_EL) {
-            for (int t = lane; t < P; t += ORD_EL) sM[t] = 0.0;
+
+    // ---- fm_SGD (fm_sgd.h:38-50) for the lane's example with multiplier `mult`: result into the own ring slot
+    auto sgd_update = [&](double mult) {
+      if (fast) {
+        if (act && !(a.debug & 4)) {
+          const uint32_t cnt = je - jb;
+#pragma unroll
+          for (int e = 0; e < ZR; e++) {
+            if ((uint32_t)e < cnt) {
+              double* own = reinterpret_cast<double*>(smem + rec + (jb + e) * recb);
+              const double x = fx[e], x2 = x * x;
+#pragma unroll
+              for (int q = 0; q < KF; q += 2) {
+                double c0 = fv[e][q], c1 = fv[e][q + 1];
+                c0 -= lr * (mult * (sum[q] * x - c0 * x2) + regv * c0);
+                c1 -= lr * (mult * (sum[q + 1] * x - c1 * x2) + regv * c1);
+                *reinterpret_cast<double2*>(own + q) = make_double2(c0, c1);
+              }
+              if (k1) {
+                double cw = fw[e];
+                cw -= lr * (mult * x + regw * cw);
+                own[kw + (fid[e] & 1u)] = cw;
+              }
+            }
           }
-        } else if (TASK == 0) {
-          // ---- bias: affine prefix scan over the run, as few examples per lane as the run needs ----
-          if (P <= 32) w0 = ord_bias_scan<1>(bias, w0, P, sR, s.tg + t0, sM, lane);
-          else if (P <= 64) w0 = ord_bias_scan<2>(bias, w0, P, sR, s.tg + t0, sM, lane);
-          else w0 = ord_bias_scan<ORD_EL>(bias, w0, P, sR, s.tg + t0, sM, lane);
-        } else {
-          // ---- classification: the chain walked serially (fm_learn_sgd_element.h:63-64) ----
-          for (int t = 0; t < P; t++) {
-            const double y = (double)s.tg[t0 + t];
-            const double p = w0 + sR[t];
-            const double m = -y * (1.0 - 1.0 / (1.0 + exp(-y * p)));
-            if (lane == (t & 31)) sM[t] = m;
-            w0 -= lr * (m + reg0 * w0);
+        }
+      } else if (act && !(a.debug & 4)) {
+        for (uint32_t j = jb; j < je; j++) {
+          uint32_t jj = j;
+          bool dupj = false;
+          if (rowdup) {
+            dupj = s.link[j] != ORD_NONE && s.link[j] <= j - jb;
+            if (!dupj)
+              while (s.link[jj] != ORD_NONE && s.link[jj] <= jj - jb) jj -= s.link[jj];
+          }
+          // a repeated feature continues from the row's previous write (fm_sgd.h:46 reads v again)
+          const uint32_t so = dupj ? rec + (j - s.link[j]) * recb : s.src[jj];
+          const double* rp_ = reinterpret_cast<const double*>(smem + so);
+          double* own = reinterpret_cast<double*>(smem + rec + j * recb);
+          const uint32_t id = s.col[j];
+          const double x = (double)s.val[j];
+          const uint32_t vo = (k & 1) ? (id & 1u) : 0u;
+          double c[KF];
+          ord_load<KF>(rp_ + vo + f0, c, nf, vec);
+#pragma unroll
+          for (int q = 0; q < KF; q++) {
+            const double grad = sum[q] * x - c[q] * x * x;
+            c[q] -= lr * (mult * grad + regv * c[q]);
+          }
+          ord_store<KF>(own + vo + f0, c, nf, vec);
+          const bool mine = rowdup ? (gl == 0) : ((int)((j - jb) % GL) == gl);
+          if (k1 && mine) {
+            double cw = rp_[kw + (id & 1u)];
+            cw -= lr * (mult * x + regw * cw);
+            own[kw + (id & 1u)] = cw;
           }
         }
       }
-      if (warp == dwarp) {  // the next run's length: warp 1 searches while warp 0 scans
+    };
+
+    if (k0 && TASK == 0) {
+      // ---- regression: the bias chain (see ord_bias_chain) ----------------------------------------------
+      constexpr bool SPEC = ZF > 0;  // (a ZF kernel's general-path runs are single rows: never redone)
+      const double y = act ? (double)s.tg[r] : 0.0;
+      int st = ord_state(w0 + Rloc, lo, hi, inverted);  // guess: the bias at the start of the run
+      if (act && gl == 0) sAB[grp] = ord_bias_pair(bias, st, Rloc, y);
+      ord_group_sync<WS>(1, nthreads);
+      int from = 0;  // examples below `from` are final
+      for (;;) {
+        if (tid == 0) {
+          if (a.debug & 2) {
+            for (int t = 0; t <= P; t++) sW[t] = 0.0;
+          } else {
+            ord_bias_chain(sAB, sW, from, P, from == 0 ? w0 : sW[from]);
+          }
+        }
+        if (from == 0 && warp == dwarp) {  // the next run's length: warp 1 searches while thread 0 walks the chain
+          const int Pn = (t0n < nrows) ? ord_detect(s, t0n, nrows, smax, lane) : 1;
+          if (lane == 0) sP[pi ^ 1] = Pn;
+        }
+        ord_group_sync<WS>(1, nthreads);
+        // the next pass' flag word: its last readers (after the previous pass' closing barrier) are past the
+        // barrier above, its next writers come after the barrier below
+        if (tid == 0) sBad[(it + 1) & 1] = 0x7fffffff;
+        double mult = 0.0;
+        bool pending = false;
+        if (act && grp >= from) {
+          const double wt = sW[grp];
+          const double p = wt + Rloc;
+          const int ns = (a.debug & 2) ? st : ord_state(p, lo, hi, inverted);
+          if (ns != st) {  // the guess is contradicted: correct the pair; everything behind it is walked again
+            st = ns;
+            if (gl == 0) {
+              sAB[grp] = ord_bias_pair(bias, ns, Rloc, y);
+              atomicMin(&sBad[it & 1], grp);
+            }
+          }
+          // fm_learn_sgd_element.h:58-62: mult = -(y - clamp(p)).  wt is final for the first contradicted
+          // example and everything before it, so is their multiplier; later examples are checked again.
+          mult = (a.debug & 2) ? 0.0 : (ns == 0 ? p : (ns == 1 ? lo : hi)) - y;
+          // The register-resident path updates right away: its inputs stay in registers, so an example that
+          // turns out to lie behind a contradicted guess simply writes its slots again in the next pass.  The
+          // general path fetched its records INTO the slots it writes: it updates only once wt is known final.
+          if (SPEC) sgd_update(mult);
+          else pending = true;
+        }
+        ord_group_sync<WS>(1, nthreads);  // ring slots, sAB corrections, the flag, the next run length
+        const int bad = sBad[it & 1];
+        it++;
+        if (!SPEC && pending && grp <= bad) sgd_update(mult);
+        if (bad >= P) break;
+        from = bad + 1;
+        if (tid == 0) sW[from] = fma(sAB[bad].x, sW[bad], sAB[bad].y);  // thread 0 restarts the chain here
+        // (no barrier needed: only thread 0 reads sW[from] before the next one)
+      }
+      if (!SPEC) ord_group_sync<WS>(1, nthreads);  // the general path's ring slots are final
+      w0 = sW[P];  // every thread: the next run's guess
+    } else if (k0) {
+      // ---- classification: the chain walked serially by warp 0 (fm_learn_sgd_element.h:63-64) ----
+      if (act && gl == 0) sR[grp] = Rloc;
+      ord_group_sync<WS>(1, nthreads);
+      if (warp == 0) {
+        double wc = w0;
+        for (int t = 0; t < P; t++) {
+          const double y = (double)s.tg[t0 + t];
+          const double p = wc + sR[t];
+          const double m = (a.debug & 2) ? 0.0 : -y * (1.0 - 1.0 / (1.0 + exp(-y * p)));
+          if (lane == (t & 31)) sM[t] = m;
+          wc -= lr * (m + reg0 * wc);
+        }
+        if (lane == 0) sW[P] = wc;
+      }
+      if (warp == dwarp) {
         const int Pn = (t0n < nrows) ? ord_detect(s, t0n, nrows, smax, lane) : 1;
         if (lane == 0) sP[pi ^ 1] = Pn;
       }
       ord_group_sync<WS>(1, nthreads);
-      if (act) mult = sM[grp];
+      sgd_update(act ? sM[grp] : 0.0);
+      ord_group_sync<WS>(1, nthreads);
+      w0 = sW[P];
     } else {
+      double mult = 0.0;
       if (act) {
         const double y = (double)s.tg[r];
         if (TASK == 0) {
@@ -517,65 +614,9 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
         const int Pn = (t0n < nrows) ? ord_detect(s, t0n, nrows, smax, lane) : 1;
         if (lane == 0) sP[pi ^ 1] = Pn;
       }
+      sgd_update(mult);
+      ord_group_sync<WS>(1, nthreads);  // the run's ring slots (and the next length) are final before the next run reads them
     }
-
-    // ---- fm_SGD (fm_sgd.h:38-50) for the lane's example: result into the own ring slot -------
-    if (fast) {
-      if (act && !(a.debug & 4)) {
-        const uint32_t cnt = je - jb;
-#pragma unroll
-        for (int e = 0; e < ZR; e++) {
-          if ((uint32_t)e < cnt) {
-            double* own = reinterpret_cast<double*>(smem + rec + (jb + e) * recb);
-            const double x = fx[e], x2 = x * x;
-#pragma unroll
-            for (int q = 0; q < KF; q += 2) {
-              double c0 = fv[e][q], c1 = fv[e][q + 1];
-              c0 -= lr * (mult * (sum[q] * x - c0 * x2) + regv * c0);
-              c1 -= lr * (mult * (sum[q + 1] * x - c1 * x2) + regv * c1);
-              *reinterpret_cast<double2*>(own + q) = make_double2(c0, c1);
-            }
-            if (k1) {
-              double cw = fw[e];
-              cw -= lr * (mult * x + regw * cw);
-              own[kw + (fid[e] & 1u)] = cw;
-            }
-          }
-        }
-      }
-    } else if (act && !(a.debug & 4)) {
-      for (uint32_t j = jb; j < je; j++) {
-        uint32_t jj = j;
-        bool dupj = false;
-        if (rowdup) {
-          dupj = s.link[j] != ORD_NONE && s.link[j] <= j - jb;
-          if (!dupj)
-            while (s.link[jj] != ORD_NONE && s.link[jj] <= jj - jb) jj -= s.link[jj];
-        }
-        // a repeated feature continues from the row's previous write (fm_sgd.h:46 reads v again)
-        const uint32_t so = dupj ? rec + (j - s.link[j]) * recb : s.src[jj];
-        const double* rp_ = reinterpret_cast<const double*>(smem + so);
-        double* own = reinterpret_cast<double*>(smem + rec + j * recb);
-        const uint32_t id = s.col[j];
-        const double x = (double)s.val[j];
-        const uint32_t vo = (k & 1) ? (id & 1u) : 0u;
-        double c[KF];
-        ord_load<KF>(rp_ + vo + f0, c, nf, vec);
-#pragma unroll
-        for (int q = 0; q < KF; q++) {
-          const double grad = sum[q] * x - c[q] * x * x;
-          c[q] -= lr * (mult * grad + regv * c[q]);
-        }
-        ord_store<KF>(own + vo + f0, c, nf, vec);
-        const bool mine = rowdup ? (gl == 0) : ((int)((j - jb) % GL) == gl);
-        if (k1 && mine) {
-          double cw = rp_[kw + (id & 1u)];
-          cw -= lr * (mult * x + regw * cw);
-          own[kw + (id & 1u)] = cw;
-        }
-      }
-    }
-    ord_group_sync<WS>(1, nthreads);  // the run's ring slots (and the next length) are final before the next run reads them
     t0 = t0n;
     pi ^= 1;
   }
@@ -657,6 +698,8 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
   if (tid == 0) {
     for (int i = 0; i < ORD_NBUF; i++) mbar_init(bars + i, 1);
     fence_mbar_init();
+    reinterpret_cast<int*>(smem + 40)[0] = 0x7fffffff;
+    reinterpret_cast<int*>(smem + 40)[1] = 0x7fffffff;
   }
   for (uint32_t t = 0; t < (uint32_t)ORD_NBUF; t++) {
     unsigned char* sup = ord_stage(a, smem, t).sup;
@@ -665,7 +708,8 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
   __syncthreads();
 
   const OrdConsts cc = ord_consts(a);
-  double w0 = cc.k0 ? *a.w0 : 0.0;  // live in warp 0 only
+  double w0 = cc.k0 ? *a.w0 : 0.0;  // every thread follows the bias (the clamp guesses start from it)
+  uint32_t it = 0;                   // passes of the bias chain so far (parity selects the flag word)
   const uint32_t NT = a.n_tiles;
   const int TR = a.tile_rows;
 
@@ -709,7 +753,7 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
       if (lane == 0) sP[0] = P0;
     }
     __syncthreads();  // ... everyone's fetches; src[] of tile T; the first run length
-    ord_tile_runs<GL, KF, TASK, ZF, false>(a, smem, cc, T, tid, nthreads, w0);
+    ord_tile_runs<GL, KF, TASK, ZF, false>(a, smem, cc, T, tid, nthreads, w0, it);
     ord_writeback<false>(a, smem, cc, T, tid, nthreads);
     __syncthreads();  // stage T%3 is read above and refilled by the TMA issue at the top of tile T+1
   }

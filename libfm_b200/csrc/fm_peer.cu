@@ -109,9 +109,10 @@ __device__ __forceinline__ float mf_gamma(float u, float G) {
   return a / (G * b);
 }
 
-__global__ void __launch_bounds__(256) fm_peer_meanfield_kernel(const MeanFieldArgs a) {
+// header of both mean-field kernels: the leading barrier, h_V from the previous exchange's partials
+// (fixed order: identical in every block of every rank), the bias' gamma.  Returns (hv, g0).
+__device__ __forceinline__ void mf_prologue(const MeanFieldArgs& a, float* s_red, float* hv_out, float* g0_out) {
   const PeerArgs& p = a.p;
-  __shared__ float s_red[256];
   if (blockIdx.x == 0 && threadIdx.x < p.world) st_release_sys(p.flags[threadIdx.x] + p.rank, p.seq);
   if (threadIdx.x < p.world) {
     const unsigned int* mine = p.flags[p.rank] + threadIdx.x;
@@ -120,8 +121,6 @@ __global__ void __launch_bounds__(256) fm_peer_meanfield_kernel(const MeanFieldA
   }
   __syncthreads();
   const float G = (float)p.world;
-  // h_V: mean squared factor-row norm of theta0, from the partials of the previous exchange
-  // (fixed order: identical in every block of every rank)
   float acc = 0.f;
   for (int i = threadIdx.x; i < a.n_part; i += 256) acc += a.part_in[i];
   s_red[threadIdx.x] = acc;
@@ -130,70 +129,122 @@ __global__ void __launch_bounds__(256) fm_peer_meanfield_kernel(const MeanFieldA
     if ((int)threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
     __syncthreads();
   }
-  const float hv = a.n ? s_red[0] / (float)a.n : 0.f;
+  *hv_out = a.n ? s_red[0] / (float)a.n : 0.f;
   __syncthreads();
   // rows per shard (header words [64, 64+world)), averaged
   float rows = 0.f;
   for (int q = 0; q < p.world; q++) rows += (float)__ldcv(p.flags[q] + 64 + q);
   rows /= G;
-  const float g0 = mf_gamma(a.lr * (1.f + a.reg0) * rows, G);
+  *g0_out = mf_gamma(a.lr * (1.f + a.reg0) * rows, G);
+}
 
-  float sq = 0.f;  // |V|^2 of what this thread writes
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < p.n_vec;
-       i += (uint64_t)gridDim.x * blockDim.x) {
-    const float4 b4 = a.base_local[i];
-    float b[4] = {b4.x, b4.y, b4.z, b4.w};
-    float d[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int q = 0; q < p.world; q++) {
-      const float4 v = __ldcv(p.cur[q] + i);
-      d[0] += v.x - b[0];
-      d[1] += v.y - b[1];
-      d[2] += v.z - b[2];
-      d[3] += v.w - b[3];
-    }
-    const uint64_t e0 = i * 4;
-    float g[4];
-    if (e0 < a.off_w) {
-      g[0] = g0;
-      g[1] = g[2] = g[3] = 0.f;
-    } else if (e0 < a.off_v) {
+// the combined value of float4 element i (the same arithmetic, in the same order, in both kernels)
+__device__ __forceinline__ float4 mf_combine(const MeanFieldArgs& a, uint64_t i, float hv, float g0, float* sq) {
+  const PeerArgs& p = a.p;
+  const float G = (float)p.world;
+  const float4 b4 = a.base_local[i];
+  float b[4] = {b4.x, b4.y, b4.z, b4.w};
+  float d[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int q = 0; q < p.world; q++) {
+    const float4 v = __ldcv(p.cur[q] + i);  // never from a stale L1 line
+    d[0] += v.x - b[0];
+    d[1] += v.y - b[1];
+    d[2] += v.z - b[2];
+    d[3] += v.w - b[3];
+  }
+  const uint64_t e0 = i * 4;
+  float g[4];
+  if (e0 < a.off_w) {
+    g[0] = g0;
+    g[1] = g[2] = g[3] = 0.f;
+  } else if (e0 < a.off_v) {
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint64_t rel = e0 + j - a.off_w;
-        const uint64_t f = rel / a.ws;
-        g[j] = 0.f;
-        if (rel % a.ws == 0 && f < a.n) {
-          float c = 0.f;
-          for (int q = 0; q < p.world; q++) c += __ldcv(a.cnt[q] + f);
-          g[j] = mf_gamma(a.lr * (1.f + a.regw) * (c / G), G);
-        }
-      }
-    } else {
-      const uint64_t f = (e0 - a.off_v) / a.kp;  // kp is a multiple of 4: one row per float4
-      float gv = 0.f;
-      if (f < a.n) {
+    for (int j = 0; j < 4; j++) {
+      const uint64_t rel = e0 + j - a.off_w;
+      const uint64_t f = rel / a.ws;
+      g[j] = 0.f;
+      if (rel % a.ws == 0 && f < a.n) {
         float c = 0.f;
         for (int q = 0; q < p.world; q++) c += __ldcv(a.cnt[q] + f);
-        gv = mf_gamma(a.lr * (hv + a.regv) * (c / G), G);
+        g[j] = mf_gamma(a.lr * (1.f + a.regw) * (c / G), G);
       }
-      g[0] = g[1] = g[2] = g[3] = gv;
     }
-    float4 o;
-    o.x = b[0] + g[0] * d[0];
-    o.y = b[1] + g[1] * d[1];
-    o.z = b[2] + g[2] * d[2];
-    o.w = b[3] + g[3] * d[3];
-    if (e0 >= a.off_v) sq += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
-    p.next_local[i] = o;
-    a.base_local[i] = o;
+  } else {
+    const uint64_t f = (e0 - a.off_v) / a.kp;  // kp is a multiple of 4: one row per float4
+    float gv = 0.f;
+    if (f < a.n) {
+      float c = 0.f;
+      for (int q = 0; q < p.world; q++) c += __ldcv(a.cnt[q] + f);
+      gv = mf_gamma(a.lr * (hv + a.regv) * (c / G), G);
+    }
+    g[0] = g[1] = g[2] = g[3] = gv;
   }
-  s_red[threadIdx.x] = sq;
+  float4 o;
+  o.x = b[0] + g[0] * d[0];
+  o.y = b[1] + g[1] * d[1];
+  o.z = b[2] + g[2] * d[2];
+  o.w = b[3] + g[3] * d[3];
+  if (e0 >= a.off_v) *sq += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+  return o;
+}
+
+__device__ __forceinline__ float mf_block_sum(float v, float* s_red) {
+  s_red[threadIdx.x] = v;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) a.part_out[blockIdx.x] = s_red[0];
+  return s_red[0];
+}
+
+// one-shot: every rank reads all G replicas whole and keeps the combination (small state: one barrier,
+// G x state bytes over NVLink per rank)
+__global__ void __launch_bounds__(256) fm_peer_meanfield_kernel(const MeanFieldArgs a) {
+  const PeerArgs& p = a.p;
+  __shared__ float s_red[256];
+  float hv, g0;
+  mf_prologue(a, s_red, &hv, &g0);
+  float sq = 0.f;  // |V|^2 of what this thread writes
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < p.n_vec;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const float4 o = mf_combine(a, i, hv, g0, &sq);
+    p.next_local[i] = o;
+    a.base_local[i] = o;
+  }
+  const float tot = mf_block_sum(sq, s_red);
+  if (threadIdx.x == 0) a.part_out[blockIdx.x] = tot;
+}
+
+// sliced (reduce-scatter + all-gather in one kernel): rank r combines only slice r of the state -- reading
+// that slice from all G replicas -- and PUSHES the result into every rank's `next` and theta0 buffers
+// (st over NVLink), the |V|^2 partials of its slice into every rank's partial table.  2 (G-1)/G x state
+// bytes over NVLink per rank instead of (G-1) x; the C5-sized state (516 MB, G = 8) moves 0.9 GB per rank
+// instead of 3.6 GB.  The pushes must have landed everywhere before any rank trains on: the launcher puts
+// fm_peer_barrier_kernel behind this kernel (stream order = this kernel's stores are performed).
+struct MeanFieldPush {
+  float4* next[FMB200_MAX_PEERS];
+  float4* base[FMB200_MAX_PEERS];
+  float* part[FMB200_MAX_PEERS];
+};
+__global__ void __launch_bounds__(256) fm_peer_meanfield_sliced_kernel(const MeanFieldArgs a, const MeanFieldPush t) {
+  const PeerArgs& p = a.p;
+  __shared__ float s_red[256];
+  float hv, g0;
+  mf_prologue(a, s_red, &hv, &g0);
+  const uint64_t per = (p.n_vec + (uint64_t)p.world - 1) / (uint64_t)p.world;
+  const uint64_t lo = min(p.n_vec, per * (uint64_t)p.rank), hi = min(p.n_vec, lo + per);
+  float sq = 0.f;
+  for (uint64_t i = lo + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < hi;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const float4 o = mf_combine(a, i, hv, g0, &sq);
+    for (int q = 0; q < p.world; q++) {
+      t.next[q][i] = o;
+      t.base[q][i] = o;
+    }
+  }
+  const float tot = mf_block_sum(sq, s_red);
+  if ((int)threadIdx.x < p.world) t.part[threadIdx.x][(size_t)p.rank * gridDim.x + blockIdx.x] = tot;
 }
 
 // theta0 := the current state, its |V|^2 partials, this rank's counts and row count into the
@@ -261,7 +312,7 @@ cudaError_t peer_before_epoch(fmb200_ctx* c, const DataSlot& d) {
   if (!c->peer_base_valid) {
     const int grid = peer_grid(c, n_vec);
     fm_peer_capture_kernel<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(c->p32.base), base, n_vec,
-                                                        c->p32.off_v / 4, part + (size_t)c->peer_part_cur * 512);
+                                                        c->p32.off_v / 4, part + (size_t)c->peer_part_cur * FMB_PEER_PART);
     c->peer_n_part = grid;
     c->peer_base_valid = true;
     c->launches++;
@@ -293,8 +344,8 @@ cudaError_t launch_peer_meanfield(fmb200_ctx* c) {
   a.p.inv_world = 1.f / (float)c->peer_world;
   a.base_local = reinterpret_cast<float4*>(c->comm_base + extra);
   float* part = reinterpret_cast<float*>(c->comm_base + extra + c->comm_buf_bytes) + c->comm_cnt_floats;
-  a.part_in = part + (size_t)c->peer_part_cur * 512;
-  a.part_out = part + (size_t)(c->peer_part_cur ^ 1) * 512;
+  a.part_in = part + (size_t)c->peer_part_cur * FMB_PEER_PART;
+  a.part_out = part + (size_t)(c->peer_part_cur ^ 1) * FMB_PEER_PART;
   a.n_part = c->peer_n_part;
   a.off_w = c->p32.off_w;
   a.off_v = c->p32.off_v;
@@ -305,10 +356,31 @@ cudaError_t launch_peer_meanfield(fmb200_ctx* c) {
   a.reg0 = (float)c->hp.reg0;
   a.regw = (float)c->hp.regw;
   a.regv = (float)c->hp.regv;
-  const int grid = peer_grid(c, a.p.n_vec);
-  fm_peer_meanfield_kernel<<<grid, 256, 0, c->stream>>>(a);
-  c->launches++;
-  c->peer_n_part = grid;
+  // small state: one-shot (one barrier); large state: sliced (1/G of the reads; + a trailing barrier)
+  bool sliced = a.p.n_vec * 16ull >= (8ull << 20);
+  if (c->tune_variant == 8) sliced = true;
+  if (c->tune_variant == 9) sliced = false;
+  if (sliced) {
+    MeanFieldPush t;
+    for (int q = 0; q < c->peer_world; q++) {
+      t.next[q] = reinterpret_cast<float4*>(c->peer_base[q] + c->comm_hdr + (size_t)(cur ^ 1) * c->comm_buf_bytes);
+      t.base[q] = reinterpret_cast<float4*>(c->peer_base[q] + extra);
+      t.part[q] = reinterpret_cast<float*>(c->peer_base[q] + extra + c->comm_buf_bytes) + c->comm_cnt_floats +
+                  (size_t)(c->peer_part_cur ^ 1) * FMB_PEER_PART;
+    }
+    const uint64_t per = (a.p.n_vec + c->peer_world - 1) / c->peer_world;
+    const int grid = std::min(peer_grid(c, per), FMB_PEER_PART / c->peer_world);
+    fm_peer_meanfield_sliced_kernel<<<grid, 256, 0, c->stream>>>(a, t);
+    c->launches++;
+    c->peer_n_part = grid * c->peer_world;
+    cudaError_t e = launch_peer_barrier(c);
+    if (e != cudaSuccess) return e;
+  } else {
+    const int grid = peer_grid(c, a.p.n_vec);
+    fm_peer_meanfield_kernel<<<grid, 256, 0, c->stream>>>(a);
+    c->launches++;
+    c->peer_n_part = grid;
+  }
   c->peer_part_cur ^= 1;
   c->peer_cur = cur ^ 1;
   c->p32.base = reinterpret_cast<float*>(c->comm_base + c->comm_hdr + (size_t)c->peer_cur * c->comm_buf_bytes);

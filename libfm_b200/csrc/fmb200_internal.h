@@ -71,6 +71,10 @@ struct HParams {
   double min_target = 0, max_target = 0;
 };
 
+// per-block |V|^2 partials of the mean-field exchange: two tables of this many floats in the comm block
+// (the sliced exchange needs world x grid entries)
+constexpr int FMB_PEER_PART = 4096;
+
 struct EpochConfig {
   int lanes_per_row = 0, slots = 0, rows_per_tile = 0, grid = 0, block = 0, smem = 0, damp = 0;
 };
@@ -108,7 +112,7 @@ struct fmb200_ctx {
   // peer-memory parameter averaging (fm_peer.cu).  comm block = [flags | buf0 | buf1]
   unsigned char* comm_base = nullptr;
   size_t comm_hdr = 1024, comm_buf_bytes = 0;
-  // behind the two state buffers: theta0 (comm_buf_bytes) | counts (comm_cnt_floats) | |V|^2 partials (2 x 512)
+  // behind the two state buffers: theta0 (comm_buf_bytes) | counts (comm_cnt_floats) | |V|^2 partials (2 x FMB_PEER_PART)
   size_t comm_cnt_floats = 0;
   bool peer_base_valid = false;  // theta0 holds the state the running epoch started from
   bool hogwild_fresh = true;     // no HOGWILD epoch has run since the state was last set (bias ramp)

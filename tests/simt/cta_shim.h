@@ -98,6 +98,12 @@ inline unsigned __ballot_sync(unsigned, bool pred) {
 }
 inline bool __any_sync(unsigned mask, bool pred) { return __ballot_sync(mask, pred) != 0u; }
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+inline int atomicMin(int* p, int v) {
+  int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (old > v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_ACQ_REL, __ATOMIC_RELAXED)) {
+  }
+  return old;
+}
 
 // ---- the device primitives of fm_device.cuh the ordered kernel uses -------------------------
 namespace fmb {

@@ -485,6 +485,28 @@ def test_peer_meanfield_two_contexts(built_lib):
     for l in ls:
         l.close()
 
+    # --- the sliced exchange (reduce-scatter + all-gather in one kernel, the path of C5-sized state) gives
+    # the one-shot kernel's result: same per-element arithmetic; only h_V's partial sums are cut differently ---
+    finals = {}
+    for variant in (9, 8):  # 9 = one-shot, 8 = sliced
+        ls = pair()
+        for l in ls:
+            l.set_tuning(variant=variant)
+        for _ in range(3):
+            for l, d in zip(ls, shards):
+                l.sgd_epoch(d)
+            exchange(ls, "fmb200_allreduce_meanfield")
+        for l in ls:
+            l.pull_params()
+        assert ls[0].fm.w0 == ls[1].fm.w0 and np.array_equal(ls[0].fm.w, ls[1].fm.w) and \
+            np.array_equal(ls[0].fm.v, ls[1].fm.v), "sliced replicas diverged" if variant == 8 else "one-shot"
+        finals[variant] = (ls[0].fm.w0, ls[0].fm.w.copy(), ls[0].fm.v.copy())
+        for l in ls:
+            l.close()
+    # HOGWILD epochs are not bit-reproducible run to run (reduction order), so the bar is the run-to-run one
+    assert abs(finals[8][0] - finals[9][0]) < 2e-3
+    assert np.sqrt(np.mean((finals[8][2] - finals[9][2]) ** 2)) < 2e-3
+
     # --- trajectories: single stream (oracle) vs mean-field vs plain averaging, 3 epochs ---
     p = _port(cfg, init)
     rmse = {}
