@@ -531,6 +531,44 @@ def run_gpu_arm(args):
     cfg = lrn.epoch_config()
     launches_total = lrn.kernel_launches()
 
+    # ---- N > 1: what the sharded epochs LEARN, against one sequential stream over all the rows ---------
+    # (examples/s alone would hide an exchange that advances the model 1/N epoch per epoch)
+    parity_multi = None
+    if world > 1 and collective == "p2p" and not args.no_parity:
+        ep_n = 4
+        full, te = synth.split_rows(synth.two_field(world * rows + 100_000, 6040, 3706, seed=7, planted_k=4),
+                                    world * rows)
+        shard = full.rows(rank * rows, (rank + 1) * rows)
+        v0 = np.random.default_rng(42).standard_normal((K_FACTORS, n)) * 0.1
+        lrn.fm.w0, lrn.fm.w, lrn.fm.v = 0.0, np.zeros(n), v0.copy()
+        lrn.min_target, lrn.max_target = full.min_target, full.max_target
+        lrn.push_hparams()
+        lrn.push_params()
+        lrn.upload(shard, 4)
+        traj = []
+        for _ in range(ep_n):
+            rc = lib.fmb200_sgd_epoch_async(ctx, 4)
+            if rc == 0:
+                rc = peer_exchange(ctx)
+            if rc != 0:
+                raise RuntimeError(lib.fmb200_last_error().decode())
+            traj.append(lrn.evaluate(te))  # every rank: the replicas are bit-identical after the exchange
+        if rank == 0:
+            from oracle import Port
+            port = Port(n, K_FACTORS)
+            port.set_params(0.0, np.zeros(n), v0)
+            ref = []
+            for _ in range(ep_n):
+                port.sgd_epoch(full, 0, LEARN_RATE, full.min_target, full.max_target)
+                ref.append(port.metric(te, 0, full.min_target, full.max_target))
+            parity_multi = {"data": "planted rank-4 signal, %d rows in %d shards of %d, 100000 held-out rows"
+                                    % (world * rows, world, rows),
+                            "exchange": args.exchange, "epochs": ep_n, "heldout_rmse_gpu": traj,
+                            "heldout_rmse_one_sequential_stream": ref,
+                            "max_abs_gap": max(abs(g - r) for g, r in zip(traj, ref)),
+                            "note": "statistical parity only (HOGWILD inside a shard, one combine per epoch)"}
+        del full, te, shard
+
     # ---- the tolerance mode: the same workload, sequentially consistent (N == 1) -------------
     tol = None
     if world == 1 and not args.no_tolerance_mode:
@@ -622,6 +660,7 @@ def run_gpu_arm(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "parity": parity,
+        "parity_multi_gpu": parity_multi,
         "tolerance_mode": tol,
         "extra": extra,
         "timed_region_wall_s": wall,

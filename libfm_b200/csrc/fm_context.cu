@@ -862,6 +862,7 @@ int fmb200_peer_attach_ipc(fmb200_ctx* c, int world, int rank, const void* handl
     c->peer_base[q] = static_cast<unsigned char*>(p);
     c->peer_ipc[q] = true;
   }
+  CK(peer_preload_kernels());
   c->peer_world = world;
   c->peer_rank = rank;
   return 0;
@@ -885,6 +886,7 @@ int fmb200_peer_attach_local(fmb200_ctx* c, int world, int rank, fmb200_ctx* con
     }
     c->peer_base[q] = all[q]->comm_base;
   }
+  CK(peer_preload_kernels());
   c->peer_world = world;
   c->peer_rank = rank;
   return 0;

@@ -80,6 +80,7 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 // all but the most recent group of this thread have landed
 __device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // ---- parameter traffic ------------------------------------------------------
 // Parameters are mutated concurrently by other SMs through L2 reductions, so

@@ -49,6 +49,19 @@ __global__ void ord_link_kernel(const uint32_t* __restrict__ ids, const uint32_t
   }
 }
 
+// shape[0]: bit 0 = every value is exactly 1, bit 1 = every row has exactly z entries (the one-hot two-field
+// shape of ratings data); the epoch kernel reads the word and takes its one-hot path when both hold
+__global__ void ord_shape_kernel(const float* __restrict__ val, uint64_t nnz, const uint64_t* __restrict__ rp,
+                                 uint64_t n_rows, uint32_t z, uint32_t* shape) {
+  uint32_t clear = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nnz; i += (uint64_t)gridDim.x * blockDim.x)
+    if (val[i] != 1.0f) clear |= 1u;
+  for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n_rows;
+       r += (uint64_t)gridDim.x * blockDim.x)
+    if (rp[r + 1] - rp[r] != z) clear |= 2u;
+  if (clear) atomicAnd(shape, ~clear);
+}
+
 // blockDim <= ORD_SMAX * GL (one group of GL lanes per example of a run): small k leaves the
 // register file to few threads (k <= 8: 128 threads)
 template <int GL, int KF, int TASK, int ZF = 0>
@@ -56,6 +69,14 @@ __global__ void __launch_bounds__((ORD_SMAX * GL < 256 ? 256 : (ORD_SMAX * GL < 
     fm_sgd_ordered_kernel(const OrderedArgs a) {
   extern __shared__ __align__(128) unsigned char ord_smem[];
   ordered_epoch_body<GL, KF, TASK, ZF>(a, ord_smem);
+}
+
+// warp-specialised form: ORD_SMAX * GL compute threads + ORD_HELPERS helper threads (write-back, fetch)
+constexpr int ORD_HELPERS = 128;
+template <int GL, int KF, int TASK, int ZF = 0>
+__global__ void __launch_bounds__(ORD_SMAX * GL + ORD_HELPERS, 1) fm_sgd_ordered_ws_kernel(const OrderedArgs a) {
+  extern __shared__ __align__(128) unsigned char ord_smem[];
+  ordered_epoch_body_ws<GL, KF, TASK, ZF>(a, ord_smem, ORD_SMAX * GL);
 }
 
 using OrdFn = void (*)(const OrderedArgs);
@@ -81,6 +102,31 @@ OrdFn pick_fast_kernel(int k, uint32_t max_row_nnz) {
   if (k == 2) return z2 ? fm_sgd_ordered_kernel<1, 2, TASK, 2> : fm_sgd_ordered_kernel<1, 2, TASK, 4>;
   if (k == 4) return z2 ? fm_sgd_ordered_kernel<1, 4, TASK, 2> : fm_sgd_ordered_kernel<1, 4, TASK, 4>;
   if (k == 8) return z2 ? fm_sgd_ordered_kernel<1, 8, TASK, 2> : fm_sgd_ordered_kernel<1, 8, TASK, 4>;
+  return nullptr;
+}
+
+// warp-specialised kernels: k <= 32 (GL <= 4: 128 GL compute threads + 128 helpers fit one CTA)
+template <int TASK>
+OrdFn pick_ws_kernel(int k, uint32_t max_row_nnz, int* ncompute) {
+  *ncompute = ORD_SMAX;
+  if (max_row_nnz >= 1 && max_row_nnz <= 4 && (k == 2 || k == 4 || k == 8)) {
+    const bool z2 = max_row_nnz <= 2;
+    if (k == 2) return z2 ? fm_sgd_ordered_ws_kernel<1, 2, TASK, 2> : fm_sgd_ordered_ws_kernel<1, 2, TASK, 4>;
+    if (k == 4) return z2 ? fm_sgd_ordered_ws_kernel<1, 4, TASK, 2> : fm_sgd_ordered_ws_kernel<1, 4, TASK, 4>;
+    return z2 ? fm_sgd_ordered_ws_kernel<1, 8, TASK, 2> : fm_sgd_ordered_ws_kernel<1, 8, TASK, 4>;
+  }
+  if (k <= 1) return fm_sgd_ordered_ws_kernel<1, 1, TASK>;
+  if (k <= 2) return fm_sgd_ordered_ws_kernel<1, 2, TASK>;
+  if (k <= 4) return fm_sgd_ordered_ws_kernel<1, 4, TASK>;
+  if (k <= 8) return fm_sgd_ordered_ws_kernel<1, 8, TASK>;
+  if (k <= 16) {
+    *ncompute = 2 * ORD_SMAX;
+    return fm_sgd_ordered_ws_kernel<2, 8, TASK>;
+  }
+  if (k <= 32) {
+    *ncompute = 4 * ORD_SMAX;
+    return fm_sgd_ordered_ws_kernel<4, 8, TASK>;
+  }
   return nullptr;
 }
 
@@ -113,7 +159,14 @@ cudaError_t build_ordered_links(fmb200_ctx* c, DataSlot& d) {
   const uint64_t cap_e = d.cap_nnz + 16, cap_r = d.cap_rows + 520;
   if (!d.link) {
     if ((e = cudaMalloc(&d.link, cap_e * sizeof(uint32_t))) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&d.rowdep, cap_r * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&d.rowdep, (cap_r + 4) * sizeof(uint32_t))) != cudaSuccess) return e;  // + the shape word
+  }
+  d.ord_shape = d.rowdep + cap_r;
+  {
+    if ((e = cudaMemsetAsync(d.ord_shape, 0x03, sizeof(uint32_t), c->stream)) != cudaSuccess) return e;
+    ord_shape_kernel<<<grid_for(c, d.nnz + d.n_rows), 256, 0, c->stream>>>(d.val, d.nnz, d.row_ptr, d.n_rows,
+                                                                           d.max_row_nnz, d.ord_shape);
+    c->launches++;
   }
   if ((e = cudaMemsetAsync(d.link, 0xff, cap_e * sizeof(uint32_t), c->stream)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(d.rowdep, 0xff, cap_r * sizeof(uint32_t), c->stream)) != cudaSuccess) return e;
@@ -212,6 +265,7 @@ cudaError_t launch_sgd_ordered(fmb200_ctx* c, DataSlot& d, bool* handled) {
   a.target = d.target;
   a.link = d.link;
   a.rowdep = d.rowdep;
+  a.shape = d.ord_shape;
   a.n_rows = d.n_rows;
   a.n_tiles = (uint32_t)((d.n_rows + TR - 1) / TR);
   a.tile_rows = TR;
@@ -247,11 +301,22 @@ cudaError_t launch_sgd_ordered(fmb200_ctx* c, DataSlot& d, bool* handled) {
                                                       : pick_fast_kernel<1>(c->k, d.max_row_nnz);
     if (fast != nullptr) fn = fast;
   }
+  // the warp-specialised form is the default where it exists (variant 1 / 2 and explicit thread counts keep
+  // the single-role kernels: comparisons, tests)
+  if (c->tune_variant != 1 && c->tune_variant != 2 && !c->tune_threads) {
+    int ncompute = 0;
+    OrdFn ws = c->hp.task == FMB200_TASK_REGRESSION ? pick_ws_kernel<0>(c->k, d.max_row_nnz, &ncompute)
+                                                    : pick_ws_kernel<1>(c->k, d.max_row_nnz, &ncompute);
+    if (ws != nullptr) {
+      fn = ws;
+      threads = ncompute + ORD_HELPERS;
+    }
+  }
   e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   fn<<<1, threads, smem, c->stream>>>(a);
   c->launches++;
-  c->last_cfg = EpochConfig{GL, std::min(ORD_SMAX, threads / GL), TR, 1, threads, (int)smem, 0};
+  c->last_cfg = EpochConfig{GL, std::min(ORD_SMAX, (threads >= ORD_SMAX * GL ? ORD_SMAX * GL : threads) / GL), TR, 1, threads, (int)smem, 0};
   *handled = true;
   return cudaGetLastError();
 }

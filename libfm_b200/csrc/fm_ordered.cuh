@@ -56,9 +56,12 @@ constexpr int ORD_EL = ORD_SMAX / 32;
 constexpr int ORD_NBUF = 3;    // ring depth (CSR stages and record buffers)
 // [0,24) mbarriers | [32,40) run lengths | [40,48) first contradicted clamp guess, by iteration parity |
 // [64, +2048) sAB: per example (a_t, b_t) of its bias step w -> a_t w + b_t   (classification: sR scores | sM
-// multipliers) | [2112, +1032) sW: the bias each example of the run reads, sW[P] = the bias after the run
-constexpr int ORD_HDR_BYTES = 3200;
-constexpr int ORD_SW_OFF = 64 + 2 * ORD_SMAX * 8;
+// multipliers) | [2112, +1032) sW: [0, 8) the bias at the start of each chain segment, [ORD_SMAX] the bias after the run
+// | [3200, +2048) sPre: per example the affine map from its segment's start to the bias it reads
+constexpr int ORD_HDR_BYTES = 5376;
+constexpr int ORD_SW_OFF = 64 + 2 * ORD_SMAX * 8;  // sW[0..8): the bias at the start of each segment; sW[ORD_SMAX]: after the run
+constexpr int ORD_SPRE_OFF = 3200;
+constexpr int ORD_SEGS = 8;  // segments of the bias chain (lanes of warp 0 composing in parallel)
 constexpr int ORD_MAX_THREADS = 1024;
 
 struct OrderedArgs {
@@ -69,6 +72,7 @@ struct OrderedArgs {
   const uint32_t* link;    // [nnz]: e - (previous entry with the same feature), ORD_NONE if none
   const uint32_t* rowdep;  // [n_rows]: r - (nearest earlier row sharing a feature); 0 = the row
                            // names a feature twice; ORD_NONE if none
+  const uint32_t* shape;   // one word: bit 0 = every value is 1, bit 1 = every row has exactly max_row_nnz entries
   uint64_t n_rows;
   uint32_t n_tiles;
   int tile_rows;      // TR
@@ -258,12 +262,13 @@ __device__ __forceinline__ void ord_store(double* p, const double (&v)[KF], int 
 // The bias chain of one run, regression.  The step  w0' = w0 - lr((clamp(w0 + R_t) - y_t) + reg0 w0)
 // (fm_learn_sgd_element.h:58-62, fm_sgd.h:34-37) is affine in w0 once the example's clamp state (inside / at
 // min / at max) is fixed: w0' = a_t w0 + b_t.  Every example's own thread GUESSES its state from the bias at
-// the start of the run and publishes (a_t, b_t); ONE thread then walks  w <- fma(a_t, w, b_t)  -- one
-// dependent DFMA per example (8 cycles on B200; the Kogge-Stone scan this replaces spent 270 dependent
-// instructions, ~2 700 cycles, per run: profiles/r02_ordered_v5_ncu_summary.md) -- and leaves in sW[t] the bias
-// example t reads.  The examples' threads then check their guess against that bias in parallel; the first
-// contradicted one corrects its pair and the chain is walked again from there (a consistent assignment IS the
-// sequential answer, by induction over t; every pass finalises at least one more example).
+// the start of the run and publishes (a_t, b_t); warp 0 then walks  w <- fma(a_t, w, b_t)  -- one dependent
+// DFMA per example (8 cycles on B200), cut into segments that are composed in parallel (ord_bias_chain); the
+// Kogge-Stone scan over shuffles this replaces spent 270 dependent instructions, ~2 700 cycles, per run
+// (profiles/r02_ordered_v5_ncu_summary.md).  The examples' threads then check their guess against the bias they
+// actually read, in parallel; the first contradicted one corrects its pair and the chain is walked again from
+// there (a consistent assignment IS the sequential answer, by induction over t; every pass finalises at least
+// one more example).
 struct OrdBias {
   double lr, lo, hi, a_mid, a_out;
   bool inverted;
@@ -271,25 +276,48 @@ struct OrdBias {
 __device__ __forceinline__ double2 ord_bias_pair(const OrdBias& c, int st, double R, double y) {
   return make_double2(st == 0 ? c.a_mid : c.a_out, -c.lr * ((st == 0 ? R : (st == 1 ? c.lo : c.hi)) - y));
 }
-__device__ __forceinline__ void ord_bias_chain(const double2* sAB, double* sW, int from, int P, double w) {
-  int t = from;
-  for (; t + 4 <= P; t += 4) {  // the loads do not depend on the chain: issued ahead of it
-    const double2 p0 = sAB[t], p1 = sAB[t + 1], p2 = sAB[t + 2], p3 = sAB[t + 3];
-    sW[t] = w;
-    w = fma(p0.x, w, p0.y);
-    sW[t + 1] = w;
-    w = fma(p1.x, w, p1.y);
-    sW[t + 2] = w;
-    w = fma(p2.x, w, p2.y);
-    sW[t + 3] = w;
-    w = fma(p3.x, w, p3.y);
+// The chain of one run, walked by warp 0.  The run is cut into up to ORD_SEGS segments of `1 << sh` examples;
+// lane s composes the affine maps of segment s (two independent DFMA chains: 8 cycles per example, all segments
+// at once) and leaves in sPre[t] the map from the segment's start to the bias example t reads; the bias is then
+// threaded through the segment totals (one DFMA per segment) into sW[s].  Example t reads
+//   fma(sPre[t].x, sW[t >> sh], sPre[t].y).
+// Critical path ~ 8 (P / 8 + 8) cycles instead of 8 P.
+// A re-walk behind a contradicted guess (from > 0, rare) is serial: sPre[t] = (0, bias) for t >= from.
+__device__ __forceinline__ void ord_bias_chain(const double2* sAB, double2* sPre, double* sW, int from, int P, int sh,
+                                               double w0, int lane) {
+  if (from == 0) {
+    const int seg = 1 << sh;
+    const int nseg = (P + seg - 1) >> sh;
+    double A = 1.0, B = 0.0;
+    if (lane < nseg) {
+      const int t0 = lane << sh, t1 = min(P, t0 + seg);
+      for (int t = t0; t < t1; t++) {
+        const double2 ab = sAB[t];
+        sPre[t] = make_double2(A, B);
+        B = fma(ab.x, B, ab.y);  // w -> ab.x (A w + B) + ab.y
+        A = ab.x * A;
+      }
+    }
+    double w = w0;
+#pragma unroll
+    for (int q = 0; q < ORD_SEGS; q++) {  // lane q holds segment q's total
+      const double Aq = __shfl_sync(0xffffffffu, A, q), Bq = __shfl_sync(0xffffffffu, B, q);
+      if (q < nseg) {
+        if (lane == 0) sW[q] = w;
+        w = fma(Aq, w, Bq);
+      }
+    }
+    if (lane == 0) sW[ORD_SMAX] = w;
+  } else if (lane == 0) {
+    double w = fma(sPre[from - 1].x, sW[(from - 1) >> sh], sPre[from - 1].y);  // the bias example from-1 read ...
+    w = fma(sAB[from - 1].x, w, sAB[from - 1].y);                             // ... and left (its pair is corrected)
+    for (int t = from; t < P; t++) {
+      const double2 ab = sAB[t];
+      sPre[t] = make_double2(0.0, w);
+      w = fma(ab.x, w, ab.y);
+    }
+    sW[ORD_SMAX] = w;
   }
-  for (; t < P; t++) {
-    const double2 p0 = sAB[t];
-    sW[t] = w;
-    w = fma(p0.x, w, p0.y);
-  }
-  sW[P] = w;
 }
 
 // barrier over one role's threads: the whole CTA (0), or a named barrier over the role (WS)
@@ -339,8 +367,15 @@ __device__ __forceinline__ OrdConsts ord_consts(const OrderedArgs& a) {
 // length of the tile's first run.  Every thread carries the bias w0 (the clamp guesses start from it).
 template <int GL, int KF, int TASK, int ZF, bool WS>
 __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned char* smem, const OrdConsts& cc,
-                                              uint32_t T, int tid, int nthreads, double& w0, uint32_t& it) {
+                                              uint32_t T, int tid, int nthreads, double& w0, uint32_t& it,
+                                              bool onehot) {
   const int lane = tid & 31, warp = tid >> 5;
+  // the one-hot two-field shape (ratings data: every row is exactly user:1 item:1): with x = 1 and two
+  // entries a, b the score is  w_a + w_b + sum_f v_af v_bf  (1/2 ((a+b)^2 - a^2 - b^2) = ab) and the
+  // gradient of v_af is mult v_bf  (sum_f - v_af = v_bf)  -- 10 fp64 operations per example instead of 64 for
+  // the score, 52 instead of ~100 for the update; fp64 instruction issue is what phase A of a run spends its
+  // time on (profiles/r02_ordered_v6_ncu_summary.md)
+  const bool oh = (ZF == 2) && onehot;
   const int gl = tid % GL;   // lane inside the example's group
   const int grp = tid / GL;  // example slot inside a run
   const int smax = min(ORD_SMAX, nthreads / GL);
@@ -350,6 +385,7 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
   double* sM = sR + ORD_SMAX;
   double2* sAB = reinterpret_cast<double2*>(smem + 64);
   double* sW = reinterpret_cast<double*>(smem + ORD_SW_OFF);
+  double2* sPre = reinterpret_cast<double2*>(smem + ORD_SPRE_OFF);
   const int dwarp = nthreads > 32 ? 1 : 0;  // the warp that searches the next run
   const int k = cc.k, kw = cc.kw;
   const bool k0 = cc.k0, k1 = cc.k1;
@@ -364,6 +400,7 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
   const uint64_t r0 = (uint64_t)T * a.tile_rows;
   const int nrows = (int)min((uint64_t)a.tile_rows, a.n_rows - r0);
   const uint64_t ab = s.rp[0] & ~3ull;
+  const uint32_t j00 = (uint32_t)(s.rp[0] - ab);  // tile-relative index of the tile's first entry (even for width 2)
   const uint32_t rec = ord_rec_base(a, T);
 
   int t0 = 0;
@@ -379,7 +416,7 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
 #pragma unroll
     for (int q = 0; q < KF; q++) sum[q] = 0.0;
     double Rloc = 0.0;
-    if (act) {
+    if (act && !oh) {
       jb = (uint32_t)(s.rp[r] - ab);
       je = (uint32_t)(s.rp[r + 1] - ab);
       rowdup = s.rd[r] == 0u;
@@ -388,7 +425,42 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
     double fv[ZR][KF], fw[ZR], fx[ZR];  // fast path: the row's records, weights and values
     uint32_t fid[ZR];
     const bool fast = (ZF > 0) && (s.rd[t0] != 0u);  // uniform: a row naming a feature twice runs alone
-    if (fast) {
+    if (act && oh && !fast) {  // (that row takes the general path: it wants its offsets)
+      jb = (uint32_t)(s.rp[r] - ab);
+      je = (uint32_t)(s.rp[r + 1] - ab);
+      rowdup = s.rd[r] == 0u;
+    }
+    if (fast && oh) {
+      if (act) {  // fixed width: no offsets to read
+        jb = j00 + 2u * (uint32_t)r;
+        je = jb + 2u;
+      }
+      if (act && !(a.debug & 8)) {
+        const uint2 so = *reinterpret_cast<const uint2*>(s.src + jb);
+        const uint2 ids = *reinterpret_cast<const uint2*>(s.col + jb);
+        fid[0] = ids.x;
+        fid[1] = ids.y;
+        const double* ra = reinterpret_cast<const double*>(smem + so.x);
+        const double* rb = reinterpret_cast<const double*>(smem + so.y);
+#pragma unroll
+        for (int q = 0; q < KF; q += 2) {
+          const double2 ta = *reinterpret_cast<const double2*>(ra + q), tb = *reinterpret_cast<const double2*>(rb + q);
+          fv[0][q] = ta.x;
+          fv[0][q + 1] = ta.y;
+          fv[1][q] = tb.x;
+          fv[1][q + 1] = tb.y;
+        }
+        fw[0] = k1 ? ra[kw + (ids.x & 1u)] : 0.0;
+        fw[1] = k1 ? rb[kw + (ids.y & 1u)] : 0.0;
+        double r0 = fw[0], r1 = fw[1];  // two accumulators: half the dependent chain
+#pragma unroll
+        for (int q = 0; q < KF; q += 2) {
+          r0 = fma(fv[0][q], fv[1][q], r0);
+          r1 = fma(fv[0][q + 1], fv[1][q + 1], r1);
+        }
+        Rloc = r0 + r1;
+      }
+    } else if (fast) {
       if (act && !(a.debug & 8)) {
         const uint32_t cnt = je - jb;
 #pragma unroll
@@ -462,7 +534,25 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
 
     // ---- fm_SGD (fm_sgd.h:38-50) for the lane's example with multiplier `mult`: result into the own ring slot
     auto sgd_update = [&](double mult) {
-      if (fast) {
+      if (fast && oh) {
+        if (act && !(a.debug & 4)) {
+          double* oa = reinterpret_cast<double*>(smem + rec + jb * recb);
+          double* ob = oa + a.rs;
+#pragma unroll
+          for (int q = 0; q < KF; q += 2) {
+            // fm_sgd.h:44-48 with x = 1: grad of v_af = sum_f - v_af = v_bf
+            const double a0 = fv[0][q], a1 = fv[0][q + 1], b0 = fv[1][q], b1 = fv[1][q + 1];
+            *reinterpret_cast<double2*>(oa + q) =
+                make_double2(fma(-lr, fma(regv, a0, mult * b0), a0), fma(-lr, fma(regv, a1, mult * b1), a1));
+            *reinterpret_cast<double2*>(ob + q) =
+                make_double2(fma(-lr, fma(regv, b0, mult * a0), b0), fma(-lr, fma(regv, b1, mult * a1), b1));
+          }
+          if (k1) {
+            oa[kw + (fid[0] & 1u)] = fma(-lr, fma(regw, fw[0], mult), fw[0]);
+            ob[kw + (fid[1] & 1u)] = fma(-lr, fma(regw, fw[1], mult), fw[1]);
+          }
+        }
+      } else if (fast) {
         if (act && !(a.debug & 4)) {
           const uint32_t cnt = je - jb;
 #pragma unroll
@@ -522,17 +612,19 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
     if (k0 && TASK == 0) {
       // ---- regression: the bias chain (see ord_bias_chain) ----------------------------------------------
       constexpr bool SPEC = ZF > 0;  // (a ZF kernel's general-path runs are single rows: never redone)
+      const int sh = P <= 32 ? 2 : (P <= 64 ? 3 : 4);  // segment length 4 / 8 / 16: at most ORD_SEGS segments
       const double y = act ? (double)s.tg[r] : 0.0;
       int st = ord_state(w0 + Rloc, lo, hi, inverted);  // guess: the bias at the start of the run
       if (act && gl == 0) sAB[grp] = ord_bias_pair(bias, st, Rloc, y);
       ord_group_sync<WS>(1, nthreads);
       int from = 0;  // examples below `from` are final
       for (;;) {
-        if (tid == 0) {
+        if (warp == 0) {
           if (a.debug & 2) {
-            for (int t = 0; t <= P; t++) sW[t] = 0.0;
+            for (int t = lane; t < P; t += 32) sPre[t] = make_double2(0.0, 0.0);
+            if (lane == 0) sW[ORD_SMAX] = 0.0;
           } else {
-            ord_bias_chain(sAB, sW, from, P, from == 0 ? w0 : sW[from]);
+            ord_bias_chain(sAB, sPre, sW, from, P, sh, w0, lane);
           }
         }
         if (from == 0 && warp == dwarp) {  // the next run's length: warp 1 searches while thread 0 walks the chain
@@ -546,7 +638,8 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
         double mult = 0.0;
         bool pending = false;
         if (act && grp >= from) {
-          const double wt = sW[grp];
+          const double2 pre = sPre[grp];
+          const double wt = fma(pre.x, sW[grp >> sh], pre.y);
           const double p = wt + Rloc;
           const int ns = (a.debug & 2) ? st : ord_state(p, lo, hi, inverted);
           if (ns != st) {  // the guess is contradicted: correct the pair; everything behind it is walked again
@@ -570,12 +663,10 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
         it++;
         if (!SPEC && pending && grp <= bad) sgd_update(mult);
         if (bad >= P) break;
-        from = bad + 1;
-        if (tid == 0) sW[from] = fma(sAB[bad].x, sW[bad], sAB[bad].y);  // thread 0 restarts the chain here
-        // (no barrier needed: only thread 0 reads sW[from] before the next one)
+        from = bad + 1;  // (example `bad` read the right bias: its own result is final, its pair is corrected)
       }
       if (!SPEC) ord_group_sync<WS>(1, nthreads);  // the general path's ring slots are final
-      w0 = sW[P];  // every thread: the next run's guess
+      w0 = sW[ORD_SMAX];  // every thread: the next run's guess
     } else if (k0) {
       // ---- classification: the chain walked serially by warp 0 (fm_learn_sgd_element.h:63-64) ----
       if (act && gl == 0) sR[grp] = Rloc;
@@ -589,7 +680,7 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
           if (lane == (t & 31)) sM[t] = m;
           wc -= lr * (m + reg0 * wc);
         }
-        if (lane == 0) sW[P] = wc;
+        if (lane == 0) sW[ORD_SMAX] = wc;
       }
       if (warp == dwarp) {
         const int Pn = (t0n < nrows) ? ord_detect(s, t0n, nrows, smax, lane) : 1;
@@ -598,7 +689,7 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
       ord_group_sync<WS>(1, nthreads);
       sgd_update(act ? sM[grp] : 0.0);
       ord_group_sync<WS>(1, nthreads);
-      w0 = sW[P];
+      w0 = sW[ORD_SMAX];
     } else {
       double mult = 0.0;
       if (act) {
@@ -710,6 +801,7 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
   const OrdConsts cc = ord_consts(a);
   double w0 = cc.k0 ? *a.w0 : 0.0;  // every thread follows the bias (the clamp guesses start from it)
   uint32_t it = 0;                   // passes of the bias chain so far (parity selects the flag word)
+  const bool onehot = (ZF == 2) && ((*a.shape & 3u) == 3u);
   const uint32_t NT = a.n_tiles;
   const int TR = a.tile_rows;
 
@@ -753,10 +845,105 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
       if (lane == 0) sP[0] = P0;
     }
     __syncthreads();  // ... everyone's fetches; src[] of tile T; the first run length
-    ord_tile_runs<GL, KF, TASK, ZF, false>(a, smem, cc, T, tid, nthreads, w0, it);
+    ord_tile_runs<GL, KF, TASK, ZF, false>(a, smem, cc, T, tid, nthreads, w0, it, onehot);
     ord_writeback<false>(a, smem, cc, T, tid, nthreads);
     __syncthreads();  // stage T%3 is read above and refilled by the TMA issue at the top of tile T+1
   }
+  if (tid == 0 && cc.k0) *a.w0 = w0;
+}
+
+// ---- driver 2: warp-specialised.  The first `ncompute` threads walk the runs of tile T; the remaining
+// (helper) threads meanwhile write tile T-1's final records back to global memory and then fetch tile T+1's
+// records.  The v5 capture (profiles/r02_ordered_v5_ncu_summary.md) had the write-back loop at 19% and the
+// fetch issue at ~5% of all stall samples with every thread doing everything in sequence; both are LSU work a
+// single SM issues at about one 16-byte request per cycle, and neither is on the dependency chain.
+//
+// Order of the global traffic is the single-role driver's: the fetch of tile T+1 is issued behind tile T-1's
+// write-back (same helper threads, a helper barrier in between), so what it may miss is what tiles T and T+1
+// write -- exactly the entries ord_prep forwards from the ring.  Tile T-1's CSR stage is read by its
+// write-back, so the TMA refill of that stage (tile T+2) is issued behind it.
+template <int GL, int KF, int TASK, int ZF = 0>
+__device__ __forceinline__ void ordered_epoch_body_ws(const OrderedArgs& a, unsigned char* smem, int ncompute) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+  const int nhelp = nthreads - ncompute, htid = tid - ncompute;
+  const bool helper = tid >= ncompute;
+  const int smax = min(ORD_SMAX, ncompute / GL);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  int* sP = reinterpret_cast<int*>(smem + 32);
+
+  if (tid == 0) {
+    for (int i = 0; i < ORD_NBUF; i++) mbar_init(bars + i, 1);
+    fence_mbar_init();
+    reinterpret_cast<int*>(smem + 40)[0] = 0x7fffffff;
+    reinterpret_cast<int*>(smem + 40)[1] = 0x7fffffff;
+  }
+  for (uint32_t t = 0; t < (uint32_t)ORD_NBUF; t++) {
+    unsigned char* sup = ord_stage(a, smem, t).sup;
+    for (uint32_t j = tid; j < a.tile_cap; j += nthreads) sup[j] = 0;
+  }
+  __syncthreads();
+
+  const OrdConsts cc = ord_consts(a);
+  double w0 = cc.k0 ? *a.w0 : 0.0;
+  uint32_t it = 0;
+  const bool onehot = (ZF == 2) && ((*a.shape & 3u) == 3u);
+  const uint32_t NT = a.n_tiles;
+  const int TR = a.tile_rows;
+
+  // producer state (helper thread 0): entry range of the next tile to stage, fetched a tile ahead
+  uint64_t policy = 0, nb = 0, ne = 0;
+  if (htid == 0) {
+    policy = policy_evict_first();
+    for (uint32_t t = 0; t < 2 && t < NT; t++) {
+      const uint64_t r0 = (uint64_t)t * TR, r1 = min(r0 + TR, a.n_rows);
+      ord_issue_csr(a, smem, bars, t, a.row_ptr[r0], a.row_ptr[r1], policy);
+    }
+    if (2 < NT) {
+      const uint64_t r0 = 2ull * TR, r1 = min(r0 + TR, a.n_rows);
+      nb = a.row_ptr[r0];
+      ne = a.row_ptr[r1];
+    }
+  }
+  mbar_wait(bars + 0, 0);
+  ord_prep(a, smem, 0, tid, nthreads);  // the first tile's records: everybody fetches
+  cp_async_commit();
+  cp_async_wait_0();
+  __syncthreads();
+
+  for (uint32_t T = 0; T < NT; T++) {
+    if (helper) {
+      if (T > 0) {
+        ord_writeback<true>(a, smem, cc, T - 1, htid, nhelp);
+        named_bar_sync(2, nhelp);  // the stores are issued (and sup[] is clear) before anything below
+      }
+      if (htid == 0 && T + 2 < NT) {  // stage (T+2)%3 held tile T-1, whose write-back just read it
+        ord_issue_csr(a, smem, bars, T + 2, nb, ne, policy);
+        if (T + 3 < NT) {
+          const uint64_t r0 = (uint64_t)(T + 3) * TR, r1 = min(r0 + TR, a.n_rows);
+          nb = a.row_ptr[r0];
+          ne = a.row_ptr[r1];
+        }
+      }
+      if (T + 1 < NT) {
+        mbar_wait(bars + (T + 1) % ORD_NBUF, ((T + 1) / ORD_NBUF) & 1);
+        ord_prep(a, smem, T + 1, htid, nhelp);
+      }
+      cp_async_commit();
+      cp_async_wait_0();
+    } else {
+      mbar_wait(bars + T % ORD_NBUF, (T / ORD_NBUF) & 1);  // (complete since a tile ago; acquires the TMA's writes)
+      if (warp == 0) {
+        const OrdStage s = ord_stage(a, smem, T);
+        const int nrows = (int)min((uint64_t)TR, a.n_rows - (uint64_t)T * TR);
+        const int P0 = ord_detect(s, 0, nrows, smax, lane);
+        if (lane == 0) sP[0] = P0;
+      }
+      named_bar_sync(1, ncompute);
+      ord_tile_runs<GL, KF, TASK, ZF, true>(a, smem, cc, T, tid, ncompute, w0, it, onehot);
+    }
+    __syncthreads();  // tile T's slots are final, tile T+1's records have landed, tile T-1 is written back
+  }
+  if (NT > 0) ord_writeback<false>(a, smem, cc, NT - 1, tid, nthreads);
   if (tid == 0 && cc.k0) *a.w0 = w0;
 }
 

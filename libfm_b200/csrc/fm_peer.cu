@@ -286,6 +286,22 @@ __global__ void fm_peer_barrier_kernel(const PeerArgs a) {
   }
 }
 
+// Load every kernel of the exchange NOW (called when peers are attached).  With CUDA's lazy module loading
+// the first launch of a kernel may have to synchronise the context; if that happens while an exchange kernel
+// of this process is already spinning on a peer's flag -- and the peer's kernel is the one still to be
+// launched -- the process deadlocks (seen with two contexts in one process: sliced combine running, the
+// barrier kernel behind it never launched before).
+cudaError_t peer_preload_kernels() {
+  cudaFuncAttributes fa;
+  cudaError_t e;
+  if ((e = cudaFuncGetAttributes(&fa, fm_peer_mean_kernel)) != cudaSuccess) return e;
+  if ((e = cudaFuncGetAttributes(&fa, fm_peer_meanfield_kernel)) != cudaSuccess) return e;
+  if ((e = cudaFuncGetAttributes(&fa, fm_peer_meanfield_sliced_kernel)) != cudaSuccess) return e;
+  if ((e = cudaFuncGetAttributes(&fa, fm_peer_capture_kernel)) != cudaSuccess) return e;
+  if ((e = cudaFuncGetAttributes(&fa, fm_peer_counts_kernel)) != cudaSuccess) return e;
+  return cudaFuncGetAttributes(&fa, fm_peer_barrier_kernel);
+}
+
 cudaError_t launch_peer_barrier(fmb200_ctx* c) {
   PeerArgs a;
   for (int q = 0; q < c->peer_world; q++) a.flags[q] = reinterpret_cast<unsigned int*>(c->peer_base[q]);

@@ -113,11 +113,15 @@ __device__ __forceinline__ void rowlane_tile(const HogwildArgs& a, const uint64_
 #pragma unroll
   for (int e = 0; e < Z; ++e) {
     if (GP == 2) {
-      const uint32_t pid = __shfl_xor_sync(0xffffffffu, id[e], 1);
-      const uint32_t idA = odd ? pid : id[e];  // row of the even lane
-      const uint32_t idB = odd ? id[e] : pid;  // row of the odd lane
-      const float4 la = ld_cg_f4(V4 + (size_t)idA * 2 + odd);
-      const float4 lb = ld_cg_f4(V4 + (size_t)idB * 2 + odd);
+      // a missing entry (ragged rows) fetches nothing: an unconditional gather of feature 0's sector would add
+      // L2 loads on a line the rows that really contain feature 0 are reducing into
+      const uint32_t gid = (e < cnt) ? id[e] : 0xffffffffu;
+      const uint32_t pid = __shfl_xor_sync(0xffffffffu, gid, 1);
+      const uint32_t idA = odd ? pid : gid;  // row of the even lane
+      const uint32_t idB = odd ? gid : pid;  // row of the odd lane
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 la = idA != 0xffffffffu ? ld_cg_f4(V4 + (size_t)idA * 2 + odd) : zero4;
+      const float4 lb = idB != 0xffffffffu ? ld_cg_f4(V4 + (size_t)idB * 2 + odd) : zero4;
       const float4 send = odd ? la : lb;
       float4 recv;
       recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
@@ -129,7 +133,7 @@ __device__ __forceinline__ void rowlane_tile(const HogwildArgs& a, const uint64_
       vr[e].v[0] = lo.x; vr[e].v[1] = lo.y; vr[e].v[2] = lo.z; vr[e].v[3] = lo.w;
       vr[e].v[4] = hi.x; vr[e].v[5] = hi.y; vr[e].v[6] = hi.z; vr[e].v[7] = hi.w;
     } else {
-      const float4 l = ld_cg_f4(V4 + (size_t)id[e]);
+      const float4 l = (e < cnt) ? ld_cg_f4(V4 + (size_t)id[e]) : make_float4(0.f, 0.f, 0.f, 0.f);
       vr[e].v[0] = l.x; vr[e].v[1] = l.y; vr[e].v[2] = l.z; vr[e].v[3] = l.w;
     }
     wv[e] = (use_w && e < cnt) ? ld_cg_f(a.w + (size_t)id[e] * a.ws) : 0.f;

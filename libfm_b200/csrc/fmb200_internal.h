@@ -33,6 +33,7 @@ struct DataSlot {
   // feature, per-row distance to the nearest earlier row sharing a feature; built lazily
   uint32_t* link = nullptr;
   uint32_t* rowdep = nullptr;
+  uint32_t* ord_shape = nullptr;  // behind rowdep: bit 0 = all values 1, bit 1 = all rows max_row_nnz long
   bool links_ready = false;
   void* ord_scratch = nullptr;  // scratch of the index build (kept for re-uploads of moderate size)
   size_t ord_scratch_bytes = 0;
@@ -157,6 +158,7 @@ cudaError_t launch_scale_p32(fmb200_ctx* c, float factor);
 // fm_peer.cu: one-shot all-reduce (mean) of the packed fp32 state over peer memory
 cudaError_t launch_peer_mean(fmb200_ctx* c);
 cudaError_t launch_peer_barrier(fmb200_ctx* c);
+cudaError_t peer_preload_kernels();  // defeat lazy loading before any exchange kernel can spin
 // mean-field combine theta = theta0 + gamma_i * sum_g (theta_g - theta0) (see fm_peer.cu)
 cudaError_t launch_peer_meanfield(fmb200_ctx* c);
 cudaError_t peer_before_epoch(fmb200_ctx* c, const DataSlot& d);

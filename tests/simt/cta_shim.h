@@ -46,6 +46,7 @@ extern thread_local Dim tid;
 extern Dim bdim;
 extern pthread_barrier_t cta_barrier;
 extern pthread_barrier_t warp_barrier[kMaxWarps];
+extern pthread_barrier_t named_barrier[4];
 extern uint64_t xchg[kMaxWarps][32];
 
 inline int warp() { return (int)(tid.x >> 5); }
@@ -133,7 +134,8 @@ inline void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* 
 inline void cp_async_16(void* dst, const void* src) { memcpy(dst, src, 16); }
 inline void cp_async_commit() {}
 inline void cp_async_wait_1() {}
-// the single-role driver never takes the named-barrier branch (WS == false)
-inline void named_bar_sync(int, int) { __builtin_trap(); }
+inline void cp_async_wait_0() {}
+// bar.sync id, n: the host driver initialises named_barrier[id] for n threads before the launch
+inline void named_bar_sync(int id, int) { pthread_barrier_wait(&simt::named_barrier[id]); }
 
 }  // namespace fmb

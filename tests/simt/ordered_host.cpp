@@ -19,6 +19,7 @@ thread_local Dim tid;
 Dim bdim;
 pthread_barrier_t cta_barrier;
 pthread_barrier_t warp_barrier[kMaxWarps];
+pthread_barrier_t named_barrier[4];
 uint64_t xchg[kMaxWarps][32];
 }  // namespace simt
 
@@ -58,6 +59,7 @@ struct Case {
   int TR;          // forced tile rows
   int warps;
   double lr;
+  int helper_warps = 0;  // > 0: the warp-specialised driver
 };
 
 struct Csr {
@@ -114,37 +116,49 @@ void build_links(const Csr& d, uint32_t n_feat, std::vector<uint32_t>& link, std
     }
 }
 
+// helper_warps > 0 runs the warp-specialised driver: `nthreads` compute threads + 32 * helper_warps helpers
 template <int GL, int KF, int ZF = 0>
-void run_threads(const fmb::OrderedArgs& a, unsigned char* smem, int task, int nthreads) {
+void run_threads(const fmb::OrderedArgs& a, unsigned char* smem, int task, int nthreads, int helper_warps = 0) {
+  const int ncompute = nthreads;
+  nthreads += 32 * helper_warps;
   simt::bdim.x = (unsigned)nthreads;
   pthread_barrier_init(&simt::cta_barrier, nullptr, nthreads);
+  pthread_barrier_init(&simt::named_barrier[1], nullptr, ncompute);
+  if (helper_warps) pthread_barrier_init(&simt::named_barrier[2], nullptr, 32 * helper_warps);
   for (int w = 0; w < nthreads / 32; w++) pthread_barrier_init(&simt::warp_barrier[w], nullptr, 32);
   std::vector<std::thread> th;
   for (int t = 0; t < nthreads; t++)
     th.emplace_back([&, t]() {
       simt::tid.x = (unsigned)t;
-      if (task == 0) fmb::ordered_epoch_body<GL, KF, 0, ZF>(a, smem);
-      else fmb::ordered_epoch_body<GL, KF, 1, ZF>(a, smem);
+      if (helper_warps) {
+        if (task == 0) fmb::ordered_epoch_body_ws<GL, KF, 0, ZF>(a, smem, ncompute);
+        else fmb::ordered_epoch_body_ws<GL, KF, 1, ZF>(a, smem, ncompute);
+      } else {
+        if (task == 0) fmb::ordered_epoch_body<GL, KF, 0, ZF>(a, smem);
+        else fmb::ordered_epoch_body<GL, KF, 1, ZF>(a, smem);
+      }
     });
   for (auto& x : th) x.join();
   pthread_barrier_destroy(&simt::cta_barrier);
+  pthread_barrier_destroy(&simt::named_barrier[1]);
+  if (helper_warps) pthread_barrier_destroy(&simt::named_barrier[2]);
   for (int w = 0; w < nthreads / 32; w++) pthread_barrier_destroy(&simt::warp_barrier[w]);
 }
 
-void dispatch(int k, const fmb::OrderedArgs& a, unsigned char* smem, int task, int nthreads, int max_nnz) {
+void dispatch(int k, const fmb::OrderedArgs& a, unsigned char* smem, int task, int nthreads, int max_nnz, int hw) {
   // the register-resident fast path where the launcher would pick it (fm_ordered.cu::pick_fast_kernel)
-  if (k == 8 && max_nnz >= 1 && max_nnz <= 2) return run_threads<1, 8, 2>(a, smem, task, nthreads);
-  if (k == 8 && max_nnz >= 1 && max_nnz <= 4) return run_threads<1, 8, 4>(a, smem, task, nthreads);
-  if (k == 4 && max_nnz >= 1 && max_nnz <= 4) return run_threads<1, 4, 4>(a, smem, task, nthreads);
-  if (k <= 1) run_threads<1, 1>(a, smem, task, nthreads);
-  else if (k <= 2) run_threads<1, 2>(a, smem, task, nthreads);
-  else if (k <= 4) run_threads<1, 4>(a, smem, task, nthreads);
-  else if (k <= 8) run_threads<1, 8>(a, smem, task, nthreads);
-  else if (k <= 16) run_threads<2, 8>(a, smem, task, nthreads);
-  else if (k <= 32) run_threads<4, 8>(a, smem, task, nthreads);
-  else if (k <= 64) run_threads<8, 8>(a, smem, task, nthreads);
-  else if (k <= 128) run_threads<16, 8>(a, smem, task, nthreads);
-  else run_threads<32, 8>(a, smem, task, nthreads);
+  if (k == 8 && max_nnz >= 1 && max_nnz <= 2) return run_threads<1, 8, 2>(a, smem, task, nthreads, hw);
+  if (k == 8 && max_nnz >= 1 && max_nnz <= 4) return run_threads<1, 8, 4>(a, smem, task, nthreads, hw);
+  if (k == 4 && max_nnz >= 1 && max_nnz <= 4) return run_threads<1, 4, 4>(a, smem, task, nthreads, hw);
+  if (k <= 1) run_threads<1, 1>(a, smem, task, nthreads, hw);
+  else if (k <= 2) run_threads<1, 2>(a, smem, task, nthreads, hw);
+  else if (k <= 4) run_threads<1, 4>(a, smem, task, nthreads, hw);
+  else if (k <= 8) run_threads<1, 8>(a, smem, task, nthreads, hw);
+  else if (k <= 16) run_threads<2, 8>(a, smem, task, nthreads, hw);
+  else if (k <= 32) run_threads<4, 8>(a, smem, task, nthreads, hw);
+  else if (k <= 64) run_threads<8, 8>(a, smem, task, nthreads, hw);
+  else if (k <= 128) run_threads<16, 8>(a, smem, task, nthreads, hw);
+  else run_threads<32, 8>(a, smem, task, nthreads, hw);
 }
 
 bool run_case(const Case& c) {
@@ -211,6 +225,16 @@ bool run_case(const Case& c) {
   a.target = tg.data();
   a.link = lk.data();
   a.rowdep = rd.data();
+  uint32_t shape = 3u;  // what fm_ordered.cu::ord_shape_kernel computes
+  {
+    uint64_t mx = 0;
+    for (uint64_t i = 0; i < N; i++) mx = std::max<uint64_t>(mx, d.row_ptr[i + 1] - d.row_ptr[i]);
+    for (uint64_t i = 0; i < N; i++)
+      if (d.row_ptr[i + 1] - d.row_ptr[i] != mx) shape &= ~2u;
+    for (float x : d.val)
+      if (x != 1.f) shape &= ~1u;
+  }
+  a.shape = &shape;
   a.n_rows = N;
   a.n_tiles = (uint32_t)((N + TR - 1) / TR);
   a.tile_rows = TR;
@@ -237,7 +261,7 @@ bool run_case(const Case& c) {
   for (uint64_t i = 0; i < N; i++) max_nnz = std::max<int>(max_nnz, (int)(d.row_ptr[i + 1] - d.row_ptr[i]));
   const int epochs = 2;
   for (int ep = 0; ep < epochs; ep++) {
-    if (N > 0) dispatch(k, a, smem, c.task, c.warps * 32, max_nnz);
+    if (N > 0) dispatch(k, a, smem, c.task, c.warps * 32, max_nnz, c.helper_warps);
     fmo_sgd_epoch(n, k, c.k0, c.k1, &ow0, ow.data(), ov.data(), c.lr, c.regs[0], c.regs[1], c.regs[2], c.task,
                   a.min_target, a.max_target, N, d.row_ptr.data(), d.col.data(), d.val.data(), d.target.data());
   }
@@ -251,8 +275,8 @@ bool run_case(const Case& c) {
   for (int f = 0; f < k; f++)
     for (uint32_t i = 0; i < n; i++) cmp(st[off_v + (size_t)i * k + f], ov[(size_t)f * n + i]);
   const bool ok = worst <= 1e-10;
-  printf("%-28s rows=%-6llu k=%-3d TR=%-3d warps=%d tiles=%u  worst rel err %.3g  %s\n", c.name,
-         (unsigned long long)N, k, TR, c.warps, a.n_tiles, worst, ok ? "ok" : "FAIL");
+  printf("%-28s rows=%-6llu k=%-3d TR=%-3d warps=%d+%d tiles=%u  worst rel err %.3g  %s\n", c.name,
+         (unsigned long long)N, k, TR, c.warps, c.helper_warps, a.n_tiles, worst, ok ? "ok" : "FAIL");
   return ok;
 }
 
@@ -275,6 +299,13 @@ int main(int argc, char** argv) {
       {"k0_linear_only", 1000, 200, 0, 1, 1, 0, {0, 0, 0}, 3, 0, 32, 1, 0.02},
       {"single_row_tiles", 300, 100, 8, 1, 1, 0, {0, 0, 0}, 5, 3, 1, 2, 0.02},
       {"tiny", 5, 6, 8, 1, 1, 0, {0, 0, 0}, 0, 0, 32, 2, 0.02},
+      // the warp-specialised driver (helper warps write tile T-1 back and fetch tile T+1 while tile T runs)
+      {"ws_c2_like", 3000, 1000, 8, 1, 1, 0, {0, 0, 0}, 0, 0, 64, 4, 0.02, 2},
+      {"ws_small_tiles_hot", 1500, 60, 8, 1, 1, 0, {0, 0, 0}, 0, 0, 8, 2, 0.02, 1},
+      {"ws_ragged_dups_k3", 1500, 300, 3, 1, 1, 0, {0.01, 0.02, 0.03}, 4, 5, 16, 2, 0.02, 2},
+      {"ws_k16_classification", 800, 600, 16, 1, 1, 1, {0, 0, 0.01}, 12, 9, 8, 2, 0.02, 1},
+      {"ws_single_row_tiles", 300, 100, 8, 1, 1, 0, {0, 0, 0}, 5, 3, 1, 2, 0.02, 1},
+      {"ws_tiny", 5, 6, 8, 1, 1, 0, {0, 0, 0}, 0, 0, 32, 2, 0.02, 1},
   };
   if (quick) cases.resize(3);
   bool all = true;
