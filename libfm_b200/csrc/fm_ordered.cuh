@@ -50,6 +50,18 @@
 
 namespace fmb {
 
+// phase timing (development aid): one thread per role adds the cycles since its previous mark to a slot
+#ifdef FMB_SIMT_HOST
+#define ORD_PROF(cond, slot)
+#else
+#define ORD_PROF(cond, slot)                      \
+  if (a.prof != nullptr && (cond)) {              \
+    const long long now_ = clock64();             \
+    a.prof[slot] += (unsigned long long)(now_ - tprof); \
+    tprof = now_;                                 \
+  }
+#endif
+
 constexpr uint32_t ORD_NONE = 0xffffffffu;
 constexpr int ORD_SMAX = 128;  // examples per run: ORD_EL per lane in the bias scan
 constexpr int ORD_EL = ORD_SMAX / 32;
@@ -87,6 +99,7 @@ struct OrderedArgs {
   double lr, reg0, regw, regv, min_target, max_target;
   uint32_t csr_bytes;  // one CSR stage
   uint32_t rec_bytes;  // one record buffer = tile_cap * rs * 8
+  unsigned long long* prof;  // phase timing (development aid): 16 clock64 accumulators, or null
   int debug;           // timing experiments only (results become wrong): 1 = no write-back to global,
                        // 2 = no bias scan (multiplier 0), 4 = no fm_SGD phase, 8 = no score phase
 };
@@ -180,24 +193,39 @@ __device__ __forceinline__ void ord_prep(const OrderedArgs& a, unsigned char* sm
   const uint32_t recb = (uint32_t)a.rs * 8u;
   const int k = a.k, kw = a.kw;
   // (s.sup[] is all zero here: zeroed at kernel start and re-zeroed by the write-back that read it)
-  for (uint32_t j = j0 + tid; j < j1; j += nthreads) {
-    const uint32_t L = s.link[j];
-    const uint64_t e = ab + j;
-    uint32_t src = rec + j * recb;
-    if (L != ORD_NONE && (uint64_t)L <= e - E0p) {  // previous writer is inside the window
-      if (L <= j - j0) {  // this tile: that entry's value never needs to reach global memory
-        src = rec + (j - L) * recb;
-        s.sup[j - L] = 1;
-      } else src = recp + (uint32_t)((e - L) - abp) * recb;                 // the previous tile
-    } else {
-      const uint32_t id = s.col[j];
-      const uint32_t vo = (k & 1) ? (id & 1u) : 0u;
-      const double* gv = a.v + (size_t)id * k - vo;
-      unsigned char* dst = smem + src;
-      for (int c = 0; c < kw; c += 2) cp_async_16(dst + c * 8, gv + c);
-      if (a.use_w) cp_async_16(dst + kw * 8, a.w + (id & ~1u));
+  // Four entries per thread at a time: their link / id loads are issued together, then the decisions, then
+  // the fetches -- one dependent load chain per batch instead of one per entry.
+  constexpr int PU = 4;
+  for (uint32_t jbase = j0 + tid; jbase < j1; jbase += PU * nthreads) {
+    uint32_t L[PU], id[PU];
+    bool in[PU];
+#pragma unroll
+    for (int u = 0; u < PU; u++) {
+      const uint32_t j = jbase + u * nthreads;
+      in[u] = j < j1;
+      L[u] = in[u] ? s.link[j] : ORD_NONE;
+      id[u] = in[u] ? s.col[j] : 0u;
     }
-    s.src[j] = src;
+#pragma unroll
+    for (int u = 0; u < PU; u++) {
+      if (!in[u]) continue;
+      const uint32_t j = jbase + u * nthreads;
+      const uint64_t e = ab + j;
+      uint32_t src = rec + j * recb;
+      if (L[u] != ORD_NONE && (uint64_t)L[u] <= e - E0p) {  // previous writer is inside the window
+        if (L[u] <= j - j0) {  // this tile: that entry's value never needs to reach global memory
+          src = rec + (j - L[u]) * recb;
+          s.sup[j - L[u]] = 1;
+        } else src = recp + (uint32_t)((e - L[u]) - abp) * recb;                 // the previous tile
+      } else {
+        const uint32_t vo = (k & 1) ? (id[u] & 1u) : 0u;
+        const double* gv = a.v + (size_t)id[u] * k - vo;
+        unsigned char* dst = smem + src;
+        for (int c = 0; c < kw; c += 2) cp_async_16(dst + c * 8, gv + c);
+        if (a.use_w) cp_async_16(dst + kw * 8, a.w + (id[u] & ~1u));
+      }
+      s.src[j] = src;
+    }
   }
 }
 
@@ -283,29 +311,40 @@ __device__ __forceinline__ double2 ord_bias_pair(const OrdBias& c, int st, doubl
 //   fma(sPre[t].x, sW[t >> sh], sPre[t].y).
 // Critical path ~ 8 (P / 8 + 8) cycles instead of 8 P.
 // A re-walk behind a contradicted guess (from > 0, rare) is serial: sPre[t] = (0, bias) for t >= from.
+template <int SEG>
+__device__ __forceinline__ void ord_bias_compose(const double2* sAB, double2* sPre, int t0, int P, double& A, double& B) {
+  // the segment's pairs first (independent loads), then the two dependent chains, the stores trailing
+  double2 ab[SEG];
+#pragma unroll
+  for (int e = 0; e < SEG; e++) ab[e] = (t0 + e < P) ? sAB[t0 + e] : make_double2(1.0, 0.0);
+#pragma unroll
+  for (int e = 0; e < SEG; e++) {
+    if (t0 + e < P) sPre[t0 + e] = make_double2(A, B);
+    B = fma(ab[e].x, B, ab[e].y);  // w -> ab.x (A w + B) + ab.y
+    A = ab[e].x * A;
+  }
+}
 __device__ __forceinline__ void ord_bias_chain(const double2* sAB, double2* sPre, double* sW, int from, int P, int sh,
                                                double w0, int lane) {
   if (from == 0) {
-    const int seg = 1 << sh;
-    const int nseg = (P + seg - 1) >> sh;
-    double A = 1.0, B = 0.0;
-    if (lane < nseg) {
-      const int t0 = lane << sh, t1 = min(P, t0 + seg);
-      for (int t = t0; t < t1; t++) {
-        const double2 ab = sAB[t];
-        sPre[t] = make_double2(A, B);
-        B = fma(ab.x, B, ab.y);  // w -> ab.x (A w + B) + ab.y
-        A = ab.x * A;
-      }
+    double A = 1.0, B = 0.0;  // lanes without a segment keep the identity
+    const int t0 = lane << sh;
+    if (t0 < P) {
+      if (sh == 2) ord_bias_compose<4>(sAB, sPre, t0, P, A, B);
+      else if (sh == 3) ord_bias_compose<8>(sAB, sPre, t0, P, A, B);
+      else ord_bias_compose<16>(sAB, sPre, t0, P, A, B);
+    }
+    double Aq[ORD_SEGS], Bq[ORD_SEGS];
+#pragma unroll
+    for (int q = 0; q < ORD_SEGS; q++) {  // lane q holds segment q's total
+      Aq[q] = __shfl_sync(0xffffffffu, A, q);
+      Bq[q] = __shfl_sync(0xffffffffu, B, q);
     }
     double w = w0;
 #pragma unroll
-    for (int q = 0; q < ORD_SEGS; q++) {  // lane q holds segment q's total
-      const double Aq = __shfl_sync(0xffffffffu, A, q), Bq = __shfl_sync(0xffffffffu, B, q);
-      if (q < nseg) {
-        if (lane == 0) sW[q] = w;
-        w = fma(Aq, w, Bq);
-      }
+    for (int q = 0; q < ORD_SEGS; q++) {  // every lane threads the bias through the totals; lane q keeps step q
+      if (lane == q) sW[q] = w;
+      w = fma(Aq[q], w, Bq[q]);  // (segments beyond the run are the identity: w stays exactly w)
     }
     if (lane == 0) sW[ORD_SMAX] = w;
   } else if (lane == 0) {
@@ -405,6 +444,8 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
 
   int t0 = 0;
   int pi = 0;  // parity of the run inside the tile
+  long long tprof = 0;
+  ORD_PROF(tid == 0, 15);  // (resets the mark; slot 15 collects what lies between tiles)
   while (t0 < nrows) {
     const int P = sP[pi];
     // ---- scores of the run's examples: fm_model.h:105-127 with R_t = p_t - w0 ----------
@@ -616,7 +657,9 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
       const double y = act ? (double)s.tg[r] : 0.0;
       int st = ord_state(w0 + Rloc, lo, hi, inverted);  // guess: the bias at the start of the run
       if (act && gl == 0) sAB[grp] = ord_bias_pair(bias, st, Rloc, y);
+      ORD_PROF(tid == 0, 0);  // phase A: scores
       ord_group_sync<WS>(1, nthreads);
+      ORD_PROF(tid == 0, 1);  // ... waiting for the other warps' scores
       int from = 0;  // examples below `from` are final
       for (;;) {
         if (warp == 0) {
@@ -627,11 +670,13 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
             ord_bias_chain(sAB, sPre, sW, from, P, sh, w0, lane);
           }
         }
+        ORD_PROF(tid == 0, 2);  // the chain
         if (from == 0 && warp == dwarp) {  // the next run's length: warp 1 searches while thread 0 walks the chain
           const int Pn = (t0n < nrows) ? ord_detect(s, t0n, nrows, smax, lane) : 1;
           if (lane == 0) sP[pi ^ 1] = Pn;
         }
         ord_group_sync<WS>(1, nthreads);
+        ORD_PROF(tid == 0, 3);  // barrier behind the chain
         // the next pass' flag word: its last readers (after the previous pass' closing barrier) are past the
         // barrier above, its next writers come after the barrier below
         if (tid == 0) sBad[(it + 1) & 1] = 0x7fffffff;
@@ -658,7 +703,9 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
           if (SPEC) sgd_update(mult);
           else pending = true;
         }
+        ORD_PROF(tid == 0, 4);  // check + fm_SGD
         ord_group_sync<WS>(1, nthreads);  // ring slots, sAB corrections, the flag, the next run length
+        ORD_PROF(tid == 0, 5);  // closing barrier
         const int bad = sBad[it & 1];
         it++;
         if (!SPEC && pending && grp <= bad) sgd_update(mult);
@@ -740,21 +787,44 @@ __device__ __forceinline__ void ord_writeback(const OrderedArgs& a, unsigned cha
       const uint32_t pieces = (uint32_t)(kw / 2) + 1u;
       const uint32_t dj = (uint32_t)nthreads / pieces, dp = (uint32_t)nthreads % pieces;
       uint32_t j = j0 + (uint32_t)tid / pieces, pc = (uint32_t)tid % pieces;
+      // four pieces per thread in flight: the flag / id / record loads of all four are issued before the first
+      // store (one warp per scheduler: a dependent load -> store chain per piece cost ~7 cycles per
+      // instruction in the r02 v7 capture, and the compute warps waited for the helpers)
+      constexpr int WU = 4;
       while (j < j1) {
-        if (!s.sup[j]) {
-          const double* own = reinterpret_cast<const double*>(smem + rec + j * recb);
-          const uint32_t id = s.col[j];
-          if (pc < pieces - 1u) {
-            *reinterpret_cast<double2*>(a.v + (size_t)id * k + 2u * pc) = *reinterpret_cast<const double2*>(own + 2u * pc);
-          } else if (k1) {
-            a.w[id] = own[kw + (id & 1u)];
+        uint32_t jj[WU], pp[WU], idu[WU];
+        bool go[WU];
+        double2 vu[WU];
+#pragma unroll
+        for (int u = 0; u < WU; u++) {
+          jj[u] = j;
+          pp[u] = pc;
+          j += dj;
+          pc += dp;
+          if (pc >= pieces) {
+            pc -= pieces;
+            j++;
           }
         }
-        j += dj;
-        pc += dp;
-        if (pc >= pieces) {
-          pc -= pieces;
-          j++;
+#pragma unroll
+        for (int u = 0; u < WU; u++) go[u] = jj[u] < j1 && !s.sup[jj[u]] && (pp[u] < pieces - 1u || k1);
+#pragma unroll
+        for (int u = 0; u < WU; u++) {
+          idu[u] = 0u;
+          vu[u] = make_double2(0.0, 0.0);
+          if (go[u]) {
+            const double* own = reinterpret_cast<const double*>(smem + rec + jj[u] * recb);
+            idu[u] = s.col[jj[u]];
+            if (pp[u] < pieces - 1u) vu[u] = *reinterpret_cast<const double2*>(own + 2u * pp[u]);
+            else vu[u].x = own[kw + (idu[u] & 1u)];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < WU; u++) {
+          if (go[u]) {
+            if (pp[u] < pieces - 1u) *reinterpret_cast<double2*>(a.v + (size_t)idu[u] * k + 2u * pp[u]) = vu[u];
+            else a.w[idu[u]] = vu[u].x;
+          }
         }
       }
       ord_group_sync<WS>(2, nthreads);  // every piece of a record has read its flag
@@ -910,12 +980,15 @@ __device__ __forceinline__ void ordered_epoch_body_ws(const OrderedArgs& a, unsi
   cp_async_wait_0();
   __syncthreads();
 
+  long long tprof = 0;
+  ORD_PROF(tid == 0 || htid == 0, 15);
   for (uint32_t T = 0; T < NT; T++) {
     if (helper) {
       if (T > 0) {
         ord_writeback<true>(a, smem, cc, T - 1, htid, nhelp);
         named_bar_sync(2, nhelp);  // the stores are issued (and sup[] is clear) before anything below
       }
+      ORD_PROF(htid == 0, 8);  // write-back
       if (htid == 0 && T + 2 < NT) {  // stage (T+2)%3 held tile T-1, whose write-back just read it
         ord_issue_csr(a, smem, bars, T + 2, nb, ne, policy);
         if (T + 3 < NT) {
@@ -926,10 +999,13 @@ __device__ __forceinline__ void ordered_epoch_body_ws(const OrderedArgs& a, unsi
       }
       if (T + 1 < NT) {
         mbar_wait(bars + (T + 1) % ORD_NBUF, ((T + 1) / ORD_NBUF) & 1);
+        ORD_PROF(htid == 0, 9);  // CSR issue + wait
         ord_prep(a, smem, T + 1, htid, nhelp);
       }
+      ORD_PROF(htid == 0, 10);  // fetch issue
       cp_async_commit();
       cp_async_wait_0();
+      ORD_PROF(htid == 0, 11);  // fetch landing
     } else {
       mbar_wait(bars + T % ORD_NBUF, (T / ORD_NBUF) & 1);  // (complete since a tile ago; acquires the TMA's writes)
       if (warp == 0) {
@@ -939,9 +1015,13 @@ __device__ __forceinline__ void ordered_epoch_body_ws(const OrderedArgs& a, unsi
         if (lane == 0) sP[0] = P0;
       }
       named_bar_sync(1, ncompute);
+      ORD_PROF(tid == 0, 6);  // tile prologue (CSR acquire, first run length)
       ord_tile_runs<GL, KF, TASK, ZF, true>(a, smem, cc, T, tid, ncompute, w0, it, onehot);
+      ORD_PROF(tid == 0, 15);
     }
     __syncthreads();  // tile T's slots are final, tile T+1's records have landed, tile T-1 is written back
+    ORD_PROF(tid == 0, 7);     // compute side: waiting for the helpers
+    ORD_PROF(htid == 0, 12);   // helper side: waiting for the compute warps
   }
   if (NT > 0) ord_writeback<false>(a, smem, cc, NT - 1, tid, nthreads);
   if (tid == 0 && cc.k0) *a.w0 = w0;
