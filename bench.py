@@ -251,6 +251,10 @@ def static_traffic(key, rows):
 
 def kernel_name(cfg, mode):
     if mode == "ordered":
+        ncompute = cfg["lanes_per_row"] * cfg["slots"]
+        if cfg["block"] > ncompute:
+            return "fm_sgd_ordered_ws_kernel<GL=%d> (1 CTA: %d compute + %d helper threads)" % (
+                cfg["lanes_per_row"], ncompute, cfg["block"] - ncompute)
         return "fm_sgd_ordered_kernel<GL=%d> (1 CTA x %d threads)" % (cfg["lanes_per_row"], cfg["block"])
     if cfg["lanes_per_row"] == 1:
         return "fm_sgd_rowlane_kernel<GP=%d,Z=%d,DAMP=%d> (grid %d x %d)" % (
@@ -583,7 +587,8 @@ def run_gpu_arm(args):
         peak, _ = hbm_peak()
         o_ach = rows * (2 * K_FACTORS * 2 * 4) / (o_ms * 1e-3) / 1e9
         tol = {"mode": "ordered (FMB200_MODE_ORDERED: the reference's read/write order on w0/w/V; conflict-free "
-                       "runs of rows in parallel, bias chain by affine prefix scan; fp64 state)",
+                       "runs of rows in parallel, bias chain as one fp64 FMA per row over speculated clamp states; "
+                       "fp64 state)",
                "dtype": "f64", "value": rows / (o_ms * 1e-3), "unit": UNIT, "ms_per_step": o_ms, "steps": o_steps,
                "e2e": {"value": o_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": int((2 + n + n * K_FACTORS) * 8), "steps": n_e2e},

@@ -54,11 +54,11 @@ namespace fmb {
 #ifdef FMB_SIMT_HOST
 #define ORD_PROF(cond, slot)
 #else
-#define ORD_PROF(cond, slot)                      \
-  if (a.prof != nullptr && (cond)) {              \
-    const long long now_ = clock64();             \
-    a.prof[slot] += (unsigned long long)(now_ - tprof); \
-    tprof = now_;                                 \
+#define ORD_PROF(cond, slot)                                                                 \
+  if (a.prof != nullptr && (cond)) {                                                         \
+    const long long now_ = clock64();                                                        \
+    reinterpret_cast<unsigned long long*>(smem + ORD_PROF_OFF)[slot] += (unsigned long long)(now_ - tprof); \
+    tprof = now_;                                                                            \
   }
 #endif
 
@@ -70,10 +70,13 @@ constexpr int ORD_NBUF = 3;    // ring depth (CSR stages and record buffers)
 // [64, +2048) sAB: per example (a_t, b_t) of its bias step w -> a_t w + b_t   (classification: sR scores | sM
 // multipliers) | [2112, +1032) sW: [0, 8) the bias at the start of each chain segment, [ORD_SMAX] the bias after the run
 // | [3200, +2048) sPre: per example the affine map from its segment's start to the bias it reads
-constexpr int ORD_HDR_BYTES = 5376;
-constexpr int ORD_SW_OFF = 64 + 2 * ORD_SMAX * 8;  // sW[0..8): the bias at the start of each segment; sW[ORD_SMAX]: after the run
+// | [5248, +256) sTot: the chain segments' totals | [5504, +128) phase timers (development aid)
+constexpr int ORD_HDR_BYTES = 5632;
+constexpr int ORD_STOT_OFF = 5248;
+constexpr int ORD_PROF_OFF = 5504;
+constexpr int ORD_SW_OFF = 64 + 2 * ORD_SMAX * 8;  // sW[0..16): the bias at the start of each segment; sW[ORD_SMAX]: after the run
 constexpr int ORD_SPRE_OFF = 3200;
-constexpr int ORD_SEGS = 8;  // segments of the bias chain (lanes of warp 0 composing in parallel)
+constexpr int ORD_SEGS = 16;  // segments of the bias chain (lanes of warp 0 composing in parallel)
 constexpr int ORD_MAX_THREADS = 1024;
 
 struct OrderedArgs {
@@ -175,6 +178,7 @@ __device__ __forceinline__ void ord_issue_csr(const OrderedArgs& a, unsigned cha
 // after the barrier that closed tile-2: anything tile-2 or earlier wrote is visible to the
 // fetch; a feature last written by tile-1 or by this tile is forwarded from the writer's
 // ring slot instead (the fetched copy would be stale).
+template <int KC>  // KC > 0: kw == KC at compile time (the fetch unrolls); 0: runtime
 __device__ __forceinline__ void ord_prep(const OrderedArgs& a, unsigned char* smem, uint32_t tile, int tid,
                                          int nthreads) {
   const OrdStage s = ord_stage(a, smem, tile);
@@ -218,11 +222,18 @@ __device__ __forceinline__ void ord_prep(const OrderedArgs& a, unsigned char* sm
           s.sup[j - L[u]] = 1;
         } else src = recp + (uint32_t)((e - L[u]) - abp) * recb;                 // the previous tile
       } else {
-        const uint32_t vo = (k & 1) ? (id[u] & 1u) : 0u;
-        const double* gv = a.v + (size_t)id[u] * k - vo;
         unsigned char* dst = smem + src;
-        for (int c = 0; c < kw; c += 2) cp_async_16(dst + c * 8, gv + c);
-        if (a.use_w) cp_async_16(dst + kw * 8, a.w + (id[u] & ~1u));
+        if (KC > 0) {
+          const double* gv = a.v + (size_t)id[u] * KC;
+#pragma unroll
+          for (int c = 0; c < KC; c += 2) cp_async_16(dst + c * 8, gv + c);
+          if (a.use_w) cp_async_16(dst + KC * 8, a.w + (id[u] & ~1u));
+        } else {
+          const uint32_t vo = (k & 1) ? (id[u] & 1u) : 0u;
+          const double* gv = a.v + (size_t)id[u] * k - vo;
+          for (int c = 0; c < kw; c += 2) cp_async_16(dst + c * 8, gv + c);
+          if (a.use_w) cp_async_16(dst + kw * 8, a.w + (id[u] & ~1u));
+        }
       }
       s.src[j] = src;
     }
@@ -312,40 +323,43 @@ __device__ __forceinline__ double2 ord_bias_pair(const OrdBias& c, int st, doubl
 // Critical path ~ 8 (P / 8 + 8) cycles instead of 8 P.
 // A re-walk behind a contradicted guess (from > 0, rare) is serial: sPre[t] = (0, bias) for t >= from.
 template <int SEG>
-__device__ __forceinline__ void ord_bias_compose(const double2* sAB, double2* sPre, int t0, int P, double& A, double& B) {
-  // the segment's pairs first (independent loads), then the two dependent chains, the stores trailing
+__device__ __forceinline__ void ord_bias_compose(const double2* sAB, double2* sPre, int t0, double& A, double& B) {
+  // the segment's pairs first (independent loads), then the two dependent chains, the stores trailing.
+  // No bounds: slots behind the run hold the identity (1, 0) and sPre has room for every slot.
   double2 ab[SEG];
 #pragma unroll
-  for (int e = 0; e < SEG; e++) ab[e] = (t0 + e < P) ? sAB[t0 + e] : make_double2(1.0, 0.0);
+  for (int e = 0; e < SEG; e++) ab[e] = sAB[t0 + e];
 #pragma unroll
   for (int e = 0; e < SEG; e++) {
-    if (t0 + e < P) sPre[t0 + e] = make_double2(A, B);
+    sPre[t0 + e] = make_double2(A, B);
     B = fma(ab[e].x, B, ab[e].y);  // w -> ab.x (A w + B) + ab.y
     A = ab[e].x * A;
   }
 }
-__device__ __forceinline__ void ord_bias_chain(const double2* sAB, double2* sPre, double* sW, int from, int P, int sh,
-                                               double w0, int lane) {
+// Executed by the whole of warp 0.  sh = log2(segment length): 1 (P <= 32), 2 (P <= 64), 3.
+__device__ __forceinline__ void ord_bias_chain(const double2* sAB, double2* sPre, double* sW, double2* sTot, int from,
+                                               int P, int sh, double w0, int lane) {
   if (from == 0) {
-    double A = 1.0, B = 0.0;  // lanes without a segment keep the identity
-    const int t0 = lane << sh;
-    if (t0 < P) {
-      if (sh == 2) ord_bias_compose<4>(sAB, sPre, t0, P, A, B);
-      else if (sh == 3) ord_bias_compose<8>(sAB, sPre, t0, P, A, B);
-      else ord_bias_compose<16>(sAB, sPre, t0, P, A, B);
+    double A = 1.0, B = 0.0;
+    if (lane < ORD_SEGS) {
+      const int t0 = lane << sh;
+      if (sh == 1) ord_bias_compose<2>(sAB, sPre, t0, A, B);
+      else if (sh == 2) ord_bias_compose<4>(sAB, sPre, t0, A, B);
+      else ord_bias_compose<8>(sAB, sPre, t0, A, B);
+      sTot[lane] = make_double2(A, B);
     }
-    double Aq[ORD_SEGS], Bq[ORD_SEGS];
+    __syncwarp();
+    // every lane threads the bias through the segment totals (broadcast reads); lane q keeps step q
+    double2 tot[ORD_SEGS];
 #pragma unroll
-    for (int q = 0; q < ORD_SEGS; q++) {  // lane q holds segment q's total
-      Aq[q] = __shfl_sync(0xffffffffu, A, q);
-      Bq[q] = __shfl_sync(0xffffffffu, B, q);
-    }
-    double w = w0;
+    for (int q = 0; q < ORD_SEGS; q++) tot[q] = sTot[q];
+    double w = w0, mine = w0;
 #pragma unroll
-    for (int q = 0; q < ORD_SEGS; q++) {  // every lane threads the bias through the totals; lane q keeps step q
-      if (lane == q) sW[q] = w;
-      w = fma(Aq[q], w, Bq[q]);  // (segments beyond the run are the identity: w stays exactly w)
+    for (int q = 0; q < ORD_SEGS; q++) {
+      mine = (lane == q) ? w : mine;
+      w = fma(tot[q].x, w, tot[q].y);  // (segments behind the run are the identity: w stays exactly w)
     }
+    if (lane < ORD_SEGS) sW[lane] = mine;
     if (lane == 0) sW[ORD_SMAX] = w;
   } else if (lane == 0) {
     double w = fma(sPre[from - 1].x, sW[(from - 1) >> sh], sPre[from - 1].y);  // the bias example from-1 read ...
@@ -425,6 +439,7 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
   double2* sAB = reinterpret_cast<double2*>(smem + 64);
   double* sW = reinterpret_cast<double*>(smem + ORD_SW_OFF);
   double2* sPre = reinterpret_cast<double2*>(smem + ORD_SPRE_OFF);
+  double2* sTot = reinterpret_cast<double2*>(smem + ORD_STOT_OFF);
   const int dwarp = nthreads > 32 ? 1 : 0;  // the warp that searches the next run
   const int k = cc.k, kw = cc.kw;
   const bool k0 = cc.k0, k1 = cc.k1;
@@ -453,9 +468,7 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
     const int r = t0 + grp;
     uint32_t jb = 0, je = 0;
     bool rowdup = false;
-    double sum[KF];
-#pragma unroll
-    for (int q = 0; q < KF; q++) sum[q] = 0.0;
+    double sum[KF];  // (zeroed by the paths that use it: the one-hot path does not)
     double Rloc = 0.0;
     if (act && !oh) {
       jb = (uint32_t)(s.rp[r] - ab);
@@ -502,6 +515,8 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
         Rloc = r0 + r1;
       }
     } else if (fast) {
+#pragma unroll
+      for (int q = 0; q < KF; q++) sum[q] = 0.0;
       if (act && !(a.debug & 8)) {
         const uint32_t cnt = je - jb;
 #pragma unroll
@@ -543,7 +558,11 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
 #pragma unroll
         for (int q = 0; q < KF; q++) Rloc += 0.5 * (sum[q] * sum[q] - ssq[q]);
       }
-    } else if (act && !(a.debug & 8)) {
+    } else {
+#pragma unroll
+      for (int q = 0; q < KF; q++) sum[q] = 0.0;
+    }
+    if (!fast && act && !(a.debug & 8)) {
       double ssq[KF];
 #pragma unroll
       for (int q = 0; q < KF; q++) ssq[q] = 0.0;
@@ -653,10 +672,13 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
     if (k0 && TASK == 0) {
       // ---- regression: the bias chain (see ord_bias_chain) ----------------------------------------------
       constexpr bool SPEC = ZF > 0;  // (a ZF kernel's general-path runs are single rows: never redone)
-      const int sh = P <= 32 ? 2 : (P <= 64 ? 3 : 4);  // segment length 4 / 8 / 16: at most ORD_SEGS segments
+      const int sh = P <= 32 ? 1 : (P <= 64 ? 2 : 3);  // segment length 2 / 4 / 8: at most ORD_SEGS segments
       const double y = act ? (double)s.tg[r] : 0.0;
       int st = ord_state(w0 + Rloc, lo, hi, inverted);  // guess: the bias at the start of the run
-      if (act && gl == 0) sAB[grp] = ord_bias_pair(bias, st, Rloc, y);
+      // (slots behind the run hold the identity: the chain composes whole segments without bounds)
+      if (gl == 0)
+        for (int g = grp; g < ORD_SMAX; g += nthreads / GL)
+          sAB[g] = (g == grp && act) ? ord_bias_pair(bias, st, Rloc, y) : make_double2(1.0, 0.0);
       ORD_PROF(tid == 0, 0);  // phase A: scores
       ord_group_sync<WS>(1, nthreads);
       ORD_PROF(tid == 0, 1);  // ... waiting for the other warps' scores
@@ -667,7 +689,7 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
             for (int t = lane; t < P; t += 32) sPre[t] = make_double2(0.0, 0.0);
             if (lane == 0) sW[ORD_SMAX] = 0.0;
           } else {
-            ord_bias_chain(sAB, sPre, sW, from, P, sh, w0, lane);
+            ord_bias_chain(sAB, sPre, sW, sTot, from, P, sh, w0, lane);
           }
         }
         ORD_PROF(tid == 0, 2);  // the chain
@@ -763,7 +785,7 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
 // Write-back of tile T by `nthreads` threads (tid in [0, nthreads)): the tile's FINAL records go to global
 // memory in one pass.  Per-update stores made every run's barrier wait behind them (r02 ncu); an entry
 // whose feature is rewritten later in this tile (sup) never needs to leave the SM.  Also re-zeroes sup[].
-template <bool WS>
+template <bool WS, int KC>
 __device__ __forceinline__ void ord_writeback(const OrderedArgs& a, unsigned char* smem, const OrdConsts& cc,
                                               uint32_t T, int tid, int nthreads) {
   const int k = cc.k, kw = cc.kw;
@@ -782,48 +804,38 @@ __device__ __forceinline__ void ord_writeback(const OrderedArgs& a, unsigned cha
   if (!(a.debug & 1)) {
     const uint32_t j0 = (uint32_t)(s.rp[0] - ab), j1 = (uint32_t)(s.rp[nrows] - ab);
     if ((k & 1) == 0) {
-      // consecutive threads write consecutive 16-byte pieces (kw/2 factor pairs + the linear weight) of
-      // consecutive records: every lane busy, rows coalesced; (record, piece) advance without a division
-      const uint32_t pieces = (uint32_t)(kw / 2) + 1u;
-      const uint32_t dj = (uint32_t)nthreads / pieces, dp = (uint32_t)nthreads % pieces;
-      uint32_t j = j0 + (uint32_t)tid / pieces, pc = (uint32_t)tid % pieces;
-      // four pieces per thread in flight: the flag / id / record loads of all four are issued before the first
-      // store (one warp per scheduler: a dependent load -> store chain per piece cost ~7 cycles per
-      // instruction in the r02 v7 capture, and the compute warps waited for the helpers)
+      // One entry per thread, four entries in flight: flags and ids first, then the records, then the stores.
+      // (An earlier form spread the 16-byte pieces of a record over consecutive lanes -- fuller sectors per
+      // store instruction, but ~60 instructions per piece of index arithmetic on warps that run one per
+      // scheduler: the r02 v8 capture had the write-back at 8 500 cycles per 256-row tile.)
       constexpr int WU = 4;
-      while (j < j1) {
-        uint32_t jj[WU], pp[WU], idu[WU];
+      for (uint32_t jb_ = j0 + tid; jb_ < j1; jb_ += WU * nthreads) {
         bool go[WU];
-        double2 vu[WU];
+        uint32_t idu[WU];
 #pragma unroll
         for (int u = 0; u < WU; u++) {
-          jj[u] = j;
-          pp[u] = pc;
-          j += dj;
-          pc += dp;
-          if (pc >= pieces) {
-            pc -= pieces;
-            j++;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < WU; u++) go[u] = jj[u] < j1 && !s.sup[jj[u]] && (pp[u] < pieces - 1u || k1);
-#pragma unroll
-        for (int u = 0; u < WU; u++) {
-          idu[u] = 0u;
-          vu[u] = make_double2(0.0, 0.0);
-          if (go[u]) {
-            const double* own = reinterpret_cast<const double*>(smem + rec + jj[u] * recb);
-            idu[u] = s.col[jj[u]];
-            if (pp[u] < pieces - 1u) vu[u] = *reinterpret_cast<const double2*>(own + 2u * pp[u]);
-            else vu[u].x = own[kw + (idu[u] & 1u)];
-          }
+          const uint32_t j = jb_ + u * nthreads;
+          go[u] = j < j1 && !s.sup[j];
+          idu[u] = go[u] ? s.col[j] : 0u;
         }
 #pragma unroll
         for (int u = 0; u < WU; u++) {
-          if (go[u]) {
-            if (pp[u] < pieces - 1u) *reinterpret_cast<double2*>(a.v + (size_t)idu[u] * k + 2u * pp[u]) = vu[u];
-            else a.w[idu[u]] = vu[u].x;
+          if (!go[u]) continue;
+          const uint32_t j = jb_ + u * nthreads;
+          const double* own = reinterpret_cast<const double*>(smem + rec + j * recb);
+          double* gv = a.v + (size_t)idu[u] * k;
+          if (KC > 0) {
+            double2 t[KC / 2 > 0 ? KC / 2 : 1];
+#pragma unroll
+            for (int c = 0; c < KC / 2; c++) t[c] = *reinterpret_cast<const double2*>(own + 2 * c);
+            const double wv = own[KC + (idu[u] & 1u)];
+#pragma unroll
+            for (int c = 0; c < KC / 2; c++) *reinterpret_cast<double2*>(gv + 2 * c) = t[c];
+            if (k1) a.w[idu[u]] = wv;
+          } else {
+            for (int c = 0; c < kw; c += 2)
+              *reinterpret_cast<double2*>(gv + c) = *reinterpret_cast<const double2*>(own + c);
+            if (k1) a.w[idu[u]] = own[kw + (idu[u] & 1u)];
           }
         }
       }
@@ -851,6 +863,7 @@ __device__ __forceinline__ void ord_writeback(const OrderedArgs& a, unsigned cha
 // ---- driver 1: every thread does everything, phases separated by CTA barriers ------------------------
 template <int GL, int KF, int TASK, int ZF = 0>
 __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigned char* smem) {
+  constexpr int KC = ZF > 0 ? KF : 0;  // the fast kernels run with k == KF (even): fetch and write-back unroll
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
   const int smax = min(ORD_SMAX, nthreads / GL);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -862,6 +875,7 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
     reinterpret_cast<int*>(smem + 40)[0] = 0x7fffffff;
     reinterpret_cast<int*>(smem + 40)[1] = 0x7fffffff;
   }
+  if (tid < 16) reinterpret_cast<unsigned long long*>(smem + ORD_PROF_OFF)[tid] = 0ull;
   for (uint32_t t = 0; t < (uint32_t)ORD_NBUF; t++) {
     unsigned char* sup = ord_stage(a, smem, t).sup;
     for (uint32_t j = tid; j < a.tile_cap; j += nthreads) sup[j] = 0;
@@ -890,7 +904,7 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
     }
   }
   mbar_wait(bars + 0, 0);
-  ord_prep(a, smem, 0, tid, nthreads);
+  ord_prep<KC>(a, smem, 0, tid, nthreads);
   cp_async_commit();
 
   for (uint32_t T = 0; T < NT; T++) {
@@ -904,7 +918,7 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
     }
     if (T + 1 < NT) {
       mbar_wait(bars + (T + 1) % ORD_NBUF, ((T + 1) / ORD_NBUF) & 1);
-      ord_prep(a, smem, T + 1, tid, nthreads);
+      ord_prep<KC>(a, smem, T + 1, tid, nthreads);
     }
     cp_async_commit();
     cp_async_wait_1();  // this thread's fetches for tile T have landed
@@ -916,10 +930,11 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
     }
     __syncthreads();  // ... everyone's fetches; src[] of tile T; the first run length
     ord_tile_runs<GL, KF, TASK, ZF, false>(a, smem, cc, T, tid, nthreads, w0, it, onehot);
-    ord_writeback<false>(a, smem, cc, T, tid, nthreads);
+    ord_writeback<false, KC>(a, smem, cc, T, tid, nthreads);
     __syncthreads();  // stage T%3 is read above and refilled by the TMA issue at the top of tile T+1
   }
   if (tid == 0 && cc.k0) *a.w0 = w0;
+  if (a.prof != nullptr && tid < 16) a.prof[tid] = reinterpret_cast<unsigned long long*>(smem + ORD_PROF_OFF)[tid];
 }
 
 // ---- driver 2: warp-specialised.  The first `ncompute` threads walk the runs of tile T; the remaining
@@ -934,6 +949,7 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
 // write-back, so the TMA refill of that stage (tile T+2) is issued behind it.
 template <int GL, int KF, int TASK, int ZF = 0>
 __device__ __forceinline__ void ordered_epoch_body_ws(const OrderedArgs& a, unsigned char* smem, int ncompute) {
+  constexpr int KC = ZF > 0 ? KF : 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
   const int nhelp = nthreads - ncompute, htid = tid - ncompute;
   const bool helper = tid >= ncompute;
@@ -947,6 +963,7 @@ __device__ __forceinline__ void ordered_epoch_body_ws(const OrderedArgs& a, unsi
     reinterpret_cast<int*>(smem + 40)[0] = 0x7fffffff;
     reinterpret_cast<int*>(smem + 40)[1] = 0x7fffffff;
   }
+  if (tid < 16) reinterpret_cast<unsigned long long*>(smem + ORD_PROF_OFF)[tid] = 0ull;
   for (uint32_t t = 0; t < (uint32_t)ORD_NBUF; t++) {
     unsigned char* sup = ord_stage(a, smem, t).sup;
     for (uint32_t j = tid; j < a.tile_cap; j += nthreads) sup[j] = 0;
@@ -975,7 +992,7 @@ __device__ __forceinline__ void ordered_epoch_body_ws(const OrderedArgs& a, unsi
     }
   }
   mbar_wait(bars + 0, 0);
-  ord_prep(a, smem, 0, tid, nthreads);  // the first tile's records: everybody fetches
+  ord_prep<KC>(a, smem, 0, tid, nthreads);  // the first tile's records: everybody fetches
   cp_async_commit();
   cp_async_wait_0();
   __syncthreads();
@@ -985,7 +1002,7 @@ __device__ __forceinline__ void ordered_epoch_body_ws(const OrderedArgs& a, unsi
   for (uint32_t T = 0; T < NT; T++) {
     if (helper) {
       if (T > 0) {
-        ord_writeback<true>(a, smem, cc, T - 1, htid, nhelp);
+        ord_writeback<true, KC>(a, smem, cc, T - 1, htid, nhelp);
         named_bar_sync(2, nhelp);  // the stores are issued (and sup[] is clear) before anything below
       }
       ORD_PROF(htid == 0, 8);  // write-back
@@ -1000,7 +1017,7 @@ __device__ __forceinline__ void ordered_epoch_body_ws(const OrderedArgs& a, unsi
       if (T + 1 < NT) {
         mbar_wait(bars + (T + 1) % ORD_NBUF, ((T + 1) / ORD_NBUF) & 1);
         ORD_PROF(htid == 0, 9);  // CSR issue + wait
-        ord_prep(a, smem, T + 1, htid, nhelp);
+        ord_prep<KC>(a, smem, T + 1, htid, nhelp);
       }
       ORD_PROF(htid == 0, 10);  // fetch issue
       cp_async_commit();
@@ -1023,8 +1040,9 @@ __device__ __forceinline__ void ordered_epoch_body_ws(const OrderedArgs& a, unsi
     ORD_PROF(tid == 0, 7);     // compute side: waiting for the helpers
     ORD_PROF(htid == 0, 12);   // helper side: waiting for the compute warps
   }
-  if (NT > 0) ord_writeback<false>(a, smem, cc, NT - 1, tid, nthreads);
+  if (NT > 0) ord_writeback<false, KC>(a, smem, cc, NT - 1, tid, nthreads);
   if (tid == 0 && cc.k0) *a.w0 = w0;
+  if (a.prof != nullptr && tid < 16) a.prof[tid] = reinterpret_cast<unsigned long long*>(smem + ORD_PROF_OFF)[tid];
 }
 
 }  // namespace fmb
