@@ -343,6 +343,101 @@ def extra_c4(device, rows, passes=5):
                          "note": "the step is bound by the 8 B/case read-back over PCIe, not by HBM"}}
 
 
+def extra_c5(world, rank, local_rank, dist, torch, flush, rows_total, steps=3):
+    """BASELINE config C5: SGD k=128 on a 100M-row synthetic CSR (n = 1M features, 39 one-hot fields, -task c)
+    row-sharded across the ranks; per epoch ONE exchange of the 516 MB packed state over NVLink peer memory
+    (the sliced mean-field combine: reduce-scatter + all-gather in one kernel, fm_peer.cu).  Every rank
+    generates and uploads its own shard; device-timed with CUDA events, max over ranks."""
+    import ctypes as C
+    import numpy as np
+    from libfm_b200 import FmLearnSgdElement, FmModel, MODE_HOGWILD
+    k, n, z = 128, 1_000_000, 39
+    rows = rows_total // world
+    ok, l, err = 1, None, ""
+    try:
+        r = np.random.default_rng(1000 + rank)
+        per = n // z
+        ids = r.integers(0, per, size=(rows, z), dtype=np.uint32)
+        ids += (np.arange(z, dtype=np.uint32) * np.uint32(per))[None, :]
+        tgt = np.where(r.integers(0, 2, size=rows) > 0, 1.0, -1.0).astype(np.float32)
+        fm = FmModel(n, k)
+        fm.init_stdev = 0.01
+        fm.init_numpy(42)  # identical replicas
+        l = FmLearnSgdElement(fm, device=local_rank, mode=MODE_HOGWILD)
+        l.task, l.learn_rate, l.min_target, l.max_target = 1, LEARN_RATE, -1.0, 1.0
+        l.push_hparams()
+        P = lambda a, t: a.ctypes.data_as(C.POINTER(t))  # noqa: E731
+        if l.lib.fmb200_upload_onehot(l._ctx, 0, rows, z, P(ids, C.c_uint32), P(tgt, C.c_float)) != 0:
+            raise RuntimeError(l.lib.fmb200_last_error().decode())
+        del ids, tgt
+        h = C.create_string_buffer(64)
+        if l.lib.fmb200_peer_export(l._ctx, h) != 0:
+            raise RuntimeError(l.lib.fmb200_last_error().decode())
+    except Exception as exc:  # a rank that cannot set up must not leave the others spinning in the exchange
+        ok, err = 0, repr(exc)
+    flag = torch.tensor([ok], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        if l is not None:
+            l.close()
+        return {"error": "setup failed on at least one rank" + (": " + err if err else "")}
+    handles = [None] * world
+    dist.all_gather_object(handles, h.raw)
+    ok = 1 if l.lib.fmb200_peer_attach_ipc(l._ctx, world, rank, b"".join(handles)) == 0 else 0
+    flag = torch.tensor([ok], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        l.close()
+        return {"error": "peer attach failed"}
+    lib, ctx = l.lib, l._ctx
+    stream = torch.cuda.ExternalStream(l.stream(), device=local_rank)
+
+    def step():
+        if lib.fmb200_sgd_epoch_async(ctx, 0) != 0 or lib.fmb200_allreduce_meanfield(ctx) != 0:
+            raise RuntimeError(lib.fmb200_last_error().decode())
+
+    launches0 = l.kernel_launches()
+    with torch.cuda.stream(stream):
+        step()  # warm-up (first-epoch bias ramp, lazy loading)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        ep = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        for i, (a, b) in enumerate(ev):
+            flush.zero_()
+            if lib.fmb200_peer_barrier(ctx) != 0:
+                raise RuntimeError(lib.fmb200_last_error().decode())
+            a.record(stream)
+            if lib.fmb200_sgd_epoch_async(ctx, 0) != 0:
+                raise RuntimeError(lib.fmb200_last_error().decode())
+            ep[i].record(stream)
+            if lib.fmb200_allreduce_meanfield(ctx) != 0:
+                raise RuntimeError(lib.fmb200_last_error().decode())
+            b.record(stream)
+        torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    ms_epoch = sum(a.elapsed_time(e) for (a, _), e in zip(ev, ep)) / steps
+    t = torch.tensor([ms, ms_epoch], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_epoch = float(t[0].item()), float(t[1].item())
+    launches = (l.kernel_launches() - launches0) // (steps + 1)
+    cfg = l.epoch_config()
+    _, n_floats = l.params_device()
+    l.close()
+    peak, peak_src = hbm_peak()
+    bpe = 2 * k * z * 4
+    achieved = rows * bpe / (ms_epoch * 1e-3) / 1e9  # per GPU, the epoch kernel alone
+    return {"workload": "C5: SGD k=128, %d-row synthetic CSR (1M features, 39 nnz/row) row-sharded over %d GPUs, "
+                        "-task c, Hogwild, one sliced mean-field exchange of the packed state per epoch" % (rows * world, world),
+            "rows_per_gpu": rows, "k": k, "nnz_per_row": z, "value": world * rows / (ms * 1e-3), "unit": UNIT,
+            "ms_per_step": ms, "ms_epoch_kernel": ms_epoch, "ms_exchange": ms - ms_epoch, "steps": steps,
+            "state_bytes_per_gpu": int(n_floats * 4), "gpu_launches_per_step": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_example": bpe,
+                         "scope": "per GPU, epoch kernel", "kernel": kernel_name(cfg, "hogwild")},
+            "kernel_geometry": cfg}
+
+
 # --------------------------------------------------------------------------
 # the GPU arm
 # --------------------------------------------------------------------------
@@ -573,6 +668,14 @@ def run_gpu_arm(args):
                             "note": "statistical parity only (HOGWILD inside a shard, one combine per epoch)"}
         del full, te, shard
 
+    # ---- N == 8 (or --c5): BASELINE config C5, 100 M rows of k = 128 sharded over the ranks -------------
+    c5 = None
+    if world > 1 and collective == "p2p" and (args.c5 or (world == 8 and not args.no_extras)):
+        try:
+            c5 = extra_c5(world, rank, local_rank, dist, torch, flush, args.c5_rows)
+        except Exception as exc:
+            c5 = {"error": repr(exc)}
+
     # ---- the tolerance mode: the same workload, sequentially consistent (N == 1) -------------
     tol = None
     if world == 1 and not args.no_tolerance_mode:
@@ -667,7 +770,7 @@ def run_gpu_arm(args):
         "parity": parity,
         "parity_multi_gpu": parity_multi,
         "tolerance_mode": tol,
-        "extra": extra,
+        "extra": dict(extra, **({"c5": c5} if c5 is not None else {})),
         "timed_region_wall_s": wall,
     }
     print(json.dumps(line), flush=True)
@@ -688,6 +791,8 @@ def main():
     ap.add_argument("--no-tolerance-mode", action="store_true")
     ap.add_argument("--c3-rows", type=int, default=10_000_000)
     ap.add_argument("--c4-rows", type=int, default=10_000_054)
+    ap.add_argument("--c5", action="store_true", help="run BASELINE config C5 at any N > 1 (default: only at N = 8)")
+    ap.add_argument("--c5-rows", type=int, default=100_000_000, help="total rows of C5 over all ranks")
     ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--exchange", default="meanfield", choices=["meanfield", "mean"])
     args = ap.parse_args()

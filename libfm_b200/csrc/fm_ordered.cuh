@@ -74,9 +74,9 @@ constexpr int ORD_NBUF = 3;    // ring depth (CSR stages and record buffers)
 constexpr int ORD_HDR_BYTES = 5632;
 constexpr int ORD_STOT_OFF = 5248;
 constexpr int ORD_PROF_OFF = 5504;
-constexpr int ORD_SW_OFF = 64 + 2 * ORD_SMAX * 8;  // sW[0..16): the bias at the start of each segment; sW[ORD_SMAX]: after the run
+constexpr int ORD_SW_OFF = 64 + 2 * ORD_SMAX * 8;  // sW[0..8): the bias at the start of each segment; sW[ORD_SMAX]: after the run
 constexpr int ORD_SPRE_OFF = 3200;
-constexpr int ORD_SEGS = 16;  // segments of the bias chain (lanes of warp 0 composing in parallel)
+constexpr int ORD_SEGS = 8;  // segments of the bias chain (lanes of warp 0 composing in parallel)
 constexpr int ORD_MAX_THREADS = 1024;
 
 struct OrderedArgs {
@@ -336,30 +336,31 @@ __device__ __forceinline__ void ord_bias_compose(const double2* sAB, double2* sP
     A = ab[e].x * A;
   }
 }
-// Executed by the whole of warp 0.  sh = log2(segment length): 1 (P <= 32), 2 (P <= 64), 3.
+// Executed by the whole of warp 0.  sh = log2(segment length): 2 (P <= 32), 3 (P <= 64), 4.
 __device__ __forceinline__ void ord_bias_chain(const double2* sAB, double2* sPre, double* sW, double2* sTot, int from,
                                                int P, int sh, double w0, int lane) {
   if (from == 0) {
-    double A = 1.0, B = 0.0;
+    double A = 1.0, B = 0.0;  // lanes without a segment keep the identity
     if (lane < ORD_SEGS) {
       const int t0 = lane << sh;
-      if (sh == 1) ord_bias_compose<2>(sAB, sPre, t0, A, B);
-      else if (sh == 2) ord_bias_compose<4>(sAB, sPre, t0, A, B);
-      else ord_bias_compose<8>(sAB, sPre, t0, A, B);
-      sTot[lane] = make_double2(A, B);
+      if (sh == 2) ord_bias_compose<4>(sAB, sPre, t0, A, B);
+      else if (sh == 3) ord_bias_compose<8>(sAB, sPre, t0, A, B);
+      else ord_bias_compose<16>(sAB, sPre, t0, A, B);
     }
-    __syncwarp();
-    // every lane threads the bias through the segment totals (broadcast reads); lane q keeps step q
-    double2 tot[ORD_SEGS];
-#pragma unroll
-    for (int q = 0; q < ORD_SEGS; q++) tot[q] = sTot[q];
-    double w = w0, mine = w0;
+    // the totals first (independent shuffles), then every lane threads the bias through them; lane q keeps step q
+    // (measured against a shared-memory exchange with 16 segments, r02 call K: the shuffles are faster)
+    double Aq[ORD_SEGS], Bq[ORD_SEGS];
 #pragma unroll
     for (int q = 0; q < ORD_SEGS; q++) {
-      mine = (lane == q) ? w : mine;
-      w = fma(tot[q].x, w, tot[q].y);  // (segments behind the run are the identity: w stays exactly w)
+      Aq[q] = __shfl_sync(0xffffffffu, A, q);
+      Bq[q] = __shfl_sync(0xffffffffu, B, q);
     }
-    if (lane < ORD_SEGS) sW[lane] = mine;
+    double w = w0;
+#pragma unroll
+    for (int q = 0; q < ORD_SEGS; q++) {
+      if (lane == q) sW[q] = w;
+      w = fma(Aq[q], w, Bq[q]);  // (segments behind the run are the identity: w stays exactly w)
+    }
     if (lane == 0) sW[ORD_SMAX] = w;
   } else if (lane == 0) {
     double w = fma(sPre[from - 1].x, sW[(from - 1) >> sh], sPre[from - 1].y);  // the bias example from-1 read ...
@@ -672,13 +673,12 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
     if (k0 && TASK == 0) {
       // ---- regression: the bias chain (see ord_bias_chain) ----------------------------------------------
       constexpr bool SPEC = ZF > 0;  // (a ZF kernel's general-path runs are single rows: never redone)
-      const int sh = P <= 32 ? 1 : (P <= 64 ? 2 : 3);  // segment length 2 / 4 / 8: at most ORD_SEGS segments
+      const int sh = P <= 32 ? 2 : (P <= 64 ? 3 : 4);  // segment length 4 / 8 / 16: at most ORD_SEGS segments
       const double y = act ? (double)s.tg[r] : 0.0;
       int st = ord_state(w0 + Rloc, lo, hi, inverted);  // guess: the bias at the start of the run
       // (slots behind the run hold the identity: the chain composes whole segments without bounds)
-      if (gl == 0)
-        for (int g = grp; g < ORD_SMAX; g += nthreads / GL)
-          sAB[g] = (g == grp && act) ? ord_bias_pair(bias, st, Rloc, y) : make_double2(1.0, 0.0);
+      // (sAB starts as all identity; a slot is dirtied only by its own thread group, which writes it every run)
+      if (gl == 0 && grp < ORD_SMAX) sAB[grp] = act ? ord_bias_pair(bias, st, Rloc, y) : make_double2(1.0, 0.0);
       ORD_PROF(tid == 0, 0);  // phase A: scores
       ord_group_sync<WS>(1, nthreads);
       ORD_PROF(tid == 0, 1);  // ... waiting for the other warps' scores
@@ -876,6 +876,7 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
     reinterpret_cast<int*>(smem + 40)[1] = 0x7fffffff;
   }
   if (tid < 16) reinterpret_cast<unsigned long long*>(smem + ORD_PROF_OFF)[tid] = 0ull;
+  for (int g = tid; g < ORD_SMAX; g += nthreads) reinterpret_cast<double2*>(smem + 64)[g] = make_double2(1.0, 0.0);
   for (uint32_t t = 0; t < (uint32_t)ORD_NBUF; t++) {
     unsigned char* sup = ord_stage(a, smem, t).sup;
     for (uint32_t j = tid; j < a.tile_cap; j += nthreads) sup[j] = 0;
@@ -964,6 +965,7 @@ __device__ __forceinline__ void ordered_epoch_body_ws(const OrderedArgs& a, unsi
     reinterpret_cast<int*>(smem + 40)[1] = 0x7fffffff;
   }
   if (tid < 16) reinterpret_cast<unsigned long long*>(smem + ORD_PROF_OFF)[tid] = 0ull;
+  for (int g = tid; g < ORD_SMAX; g += nthreads) reinterpret_cast<double2*>(smem + 64)[g] = make_double2(1.0, 0.0);
   for (uint32_t t = 0; t < (uint32_t)ORD_NBUF; t++) {
     unsigned char* sup = ord_stage(a, smem, t).sup;
     for (uint32_t j = tid; j < a.tile_cap; j += nthreads) sup[j] = 0;
