@@ -96,6 +96,28 @@ def test_cli_hogwild_tracks_reference(c1_files):
     assert abs(a[0] - b[0]) < 0.05 and abs(a[1] - b[1]) < 0.05, (a, b)
 
 
+def _gpu_count():
+    r = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True)
+    return sum(1 for l in r.stdout.splitlines() if l.startswith("GPU ")) if r.returncode == 0 else 0
+
+
+def test_cli_two_gpus_row_sharded(c1_files):
+    """bin/libFM -gpus 2: the rows are cut into two shards, one context per GPU in ONE process, one exchange of
+    w0|w|V per epoch over peer memory (fm_peer.cu).  Runs only where two GPUs are visible."""
+    _need()
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    base = ["-task", "r", "-train", "train.libfm", "-test", "test.libfm", "-method", "sgd",
+            "-iter", "8", "-learn_rate", "0.01", "-seed", "42"]
+    ref = _run(REF_CLI, base, c1_files)
+    ours = _run(CLI, base + ["-gpus", "2"], c1_files)
+    assert ours.returncode == 0, ours.stderr
+    val = lambda l: [float(t.split("=")[1]) for t in l.split("\t") if t.startswith(("Train", "Test"))]  # noqa: E731
+    a, b = val(_iters(ours.stdout)[-1]), val(_iters(ref.stdout)[-1])
+    print("\n[cli -gpus 2] final Train/Test %s vs the reference's single stream %s" % (a, b))
+    assert abs(a[0] - b[0]) < 0.08 and abs(a[1] - b[1]) < 0.08, (a, b)
+
+
 def test_cli_load_model_roundtrip(c1_files):
     _need()
     base = ["-task", "r", "-train", "train.libfm", "-test", "test.libfm", "-method", "sgd",

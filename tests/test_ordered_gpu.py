@@ -98,6 +98,15 @@ def _shape(case):
     elif case == "no_bias":
         tr = synth.two_field(30_000, 800, 500, seed=8)
         k0, k1 = 0, 0
+    elif case == "two_field_real_values":
+        # two entries per row but values != 1: the register-resident path WITHOUT the one-hot shortcut
+        tr = synth.two_field(60_000, 1500, 900, seed=12, planted_k=4)
+        tr.val[:] = (0.5 + np.random.default_rng(3).random(tr.val.shape[0])).astype(np.float32)
+        regs = (0.0, 0.01, 0.02)
+    elif case == "one_hot_regularised":
+        # the one-hot two-field path with all three regularisers and a user id that is also an item id's twin
+        tr = synth.two_field(60_000, 1200, 800, seed=13, planted_k=4)
+        regs = (0.02, 0.01, 0.03)
     elif case == "tiny":
         tr = synth.two_field(5, 3, 3, seed=1)
     elif case == "k3_reg":
@@ -119,7 +128,8 @@ def _shape(case):
 
 
 @pytest.mark.parametrize("case", ["tiny", "c2_shape", "zipf", "ragged", "dups", "classification", "no_bias",
-                                  "k3_reg", "k16_c4_shape", "k64_fields", "k128_long"])
+                                  "k3_reg", "k16_c4_shape", "k64_fields", "k128_long", "two_field_real_values",
+                                  "one_hot_regularised"])
 def test_ordered_matches_sequential_oracle(case, built_lib):
     tr, task, k, k0, k1, regs, lr = _shape(case)
     n = tr.num_feature
