@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfmb200.so")
+# FMB200_LIB: an alternative build of the same ABI (A/B timing of kernel variants; development aid)
+LIB_PATH = os.environ.get("FMB200_LIB") or os.path.join(_HERE, "lib", "libfmb200.so")
 
 # every symbol include/fmb200.h declares, with (restype, argtypes)
 _u64p = C.POINTER(C.c_uint64)
