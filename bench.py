@@ -253,7 +253,7 @@ def kernel_name(cfg, mode):
     if mode == "ordered":
         ncompute = cfg["lanes_per_row"] * cfg["slots"]
         if cfg["block"] > ncompute:
-            return "fm_sgd_ordered_ws_kernel<GL=%d> (1 CTA: %d compute + %d helper threads)" % (
+            return "fm_sgd_ordered_ws_kernel<GL=%d> (1 CTA: %d compute threads + %d parked / helper threads)" % (
                 cfg["lanes_per_row"], ncompute, cfg["block"] - ncompute)
         return "fm_sgd_ordered_kernel<GL=%d> (1 CTA x %d threads)" % (cfg["lanes_per_row"], cfg["block"])
     if cfg["lanes_per_row"] == 1:

@@ -72,12 +72,19 @@ __global__ void __launch_bounds__((ORD_SMAX * GL < 256 ? 256 : (ORD_SMAX * GL < 
   ordered_epoch_body<GL, KF, TASK, ZF>(a, ord_smem);
 }
 
-// warp-specialised form: ORD_SMAX * GL compute threads + ORD_HELPERS helper threads (write-back, fetch)
-constexpr int ORD_HELPERS = 128;
+// warp-specialised form: ORD_SMAX * GL compute threads, ORD_PARKED threads that leave after the set-up and
+// ORD_HELPERS helper threads (write-back, fetch).  ONE helper warp: every further helper warp slowed the epoch
+// by ~5% although the helpers idle most of the time -- their bursts of shared-memory / LSU traffic delay the
+// compute warps' loads (r02 calls M, N, the same build on one box, C2-shaped 200 000 rows: 1 / 2 / 3 / 4 helper
+// warps = 6.30 / 6.64-6.74 / 6.92 / 7.33 ms; which schedulers the helpers sit on matters little).  The parked
+// threads keep the helper warp's index a multiple of 4 apart from compute warp 3.
+constexpr int ORD_PARKED = 96;
+constexpr int ORD_HELPERS = 32;
 template <int GL, int KF, int TASK, int ZF = 0>
-__global__ void __launch_bounds__(ORD_SMAX * GL + ORD_HELPERS, 1) fm_sgd_ordered_ws_kernel(const OrderedArgs a) {
+__global__ void __launch_bounds__(ORD_SMAX * GL + ORD_PARKED + ORD_HELPERS, 1)
+    fm_sgd_ordered_ws_kernel(const OrderedArgs a) {
   extern __shared__ __align__(128) unsigned char ord_smem[];
-  ordered_epoch_body_ws<GL, KF, TASK, ZF>(a, ord_smem, ORD_SMAX * GL);
+  ordered_epoch_body_ws<GL, KF, TASK, ZF>(a, ord_smem, ORD_SMAX * GL, ORD_PARKED);
 }
 
 using OrdFn = void (*)(const OrderedArgs);
@@ -317,7 +324,7 @@ cudaError_t launch_sgd_ordered(fmb200_ctx* c, DataSlot& d, bool* handled) {
                                                     : pick_ws_kernel<1>(c->k, d.max_row_nnz, &ncompute);
     if (ws != nullptr) {
       fn = ws;
-      threads = ncompute + ORD_HELPERS;
+      threads = ncompute + ORD_PARKED + ORD_HELPERS;
     }
   }
   e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -949,11 +949,16 @@ __device__ __forceinline__ void ordered_epoch_body(const OrderedArgs& a, unsigne
 // write -- exactly the entries ord_prep forwards from the ring.  Tile T-1's CSR stage is read by its
 // write-back, so the TMA refill of that stage (tile T+2) is issued behind it.
 template <int GL, int KF, int TASK, int ZF = 0>
-__device__ __forceinline__ void ordered_epoch_body_ws(const OrderedArgs& a, unsigned char* smem, int ncompute) {
+__device__ __forceinline__ void ordered_epoch_body_ws(const OrderedArgs& a, unsigned char* smem, int ncompute,
+                                                      int nparked) {
   constexpr int KC = ZF > 0 ? KF : 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
-  const int nhelp = nthreads - ncompute, htid = tid - ncompute;
-  const bool helper = tid >= ncompute;
+  // Threads [ncompute, ncompute + nparked) leave after the set-up (warp w runs on scheduler w % 4: they choose
+  // which compute warps the helpers share a scheduler with; measured to matter little, see fm_ordered.cu).
+  const int hstart = ncompute + nparked;
+  const int nhelp = nthreads - hstart, htid = tid - hstart;
+  const bool helper = tid >= hstart;
+  const int nlive = nthreads - nparked, ltid = helper ? tid - nparked : tid;
   const int smax = min(ORD_SMAX, ncompute / GL);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   int* sP = reinterpret_cast<int*>(smem + 32);
@@ -993,8 +998,9 @@ __device__ __forceinline__ void ordered_epoch_body_ws(const OrderedArgs& a, unsi
       ne = a.row_ptr[r1];
     }
   }
+  if (tid >= ncompute && tid < hstart) return;  // parked (barriers below count the threads still running)
   mbar_wait(bars + 0, 0);
-  ord_prep<KC>(a, smem, 0, tid, nthreads);  // the first tile's records: everybody fetches
+  ord_prep<KC>(a, smem, 0, ltid, nlive);  // the first tile's records: everybody fetches
   cp_async_commit();
   cp_async_wait_0();
   __syncthreads();
@@ -1042,7 +1048,7 @@ __device__ __forceinline__ void ordered_epoch_body_ws(const OrderedArgs& a, unsi
     ORD_PROF(tid == 0, 7);     // compute side: waiting for the helpers
     ORD_PROF(htid == 0, 12);   // helper side: waiting for the compute warps
   }
-  if (NT > 0) ord_writeback<false, KC>(a, smem, cc, NT - 1, tid, nthreads);
+  if (NT > 0) ord_writeback<false, KC>(a, smem, cc, NT - 1, ltid, nlive);
   if (tid == 0 && cc.k0) *a.w0 = w0;
   if (a.prof != nullptr && tid < 16) a.prof[tid] = reinterpret_cast<unsigned long long*>(smem + ORD_PROF_OFF)[tid];
 }

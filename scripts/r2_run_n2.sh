@@ -4,6 +4,8 @@
 set -u
 mkdir -p gpurun_out
 nvidia-smi -L
+timeout 60 python scripts/prof_ordered.py 200000 0 132 2>&1 | cut -c1-420 | tee gpurun_out/r2_ordered_v11.txt
+timeout 60 python scripts/prof_ordered.py 1000209 0 0 2>&1 | cut -c1-120 | tee -a gpurun_out/r2_ordered_v11.txt
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
   bench.py --gpus 2 --steps 30 --warmup 5 --c5 --c5-rows 25000000 > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err
 echo "bench n2 rc=$?"; tail -n 3 gpurun_out/r2_bench_n2.err

@@ -131,8 +131,8 @@ void run_threads(const fmb::OrderedArgs& a, unsigned char* smem, int task, int n
     th.emplace_back([&, t]() {
       simt::tid.x = (unsigned)t;
       if (helper_warps) {
-        if (task == 0) fmb::ordered_epoch_body_ws<GL, KF, 0, ZF>(a, smem, ncompute);
-        else fmb::ordered_epoch_body_ws<GL, KF, 1, ZF>(a, smem, ncompute);
+        if (task == 0) fmb::ordered_epoch_body_ws<GL, KF, 0, ZF>(a, smem, ncompute, 0);
+        else fmb::ordered_epoch_body_ws<GL, KF, 1, ZF>(a, smem, ncompute, 0);
       } else {
         if (task == 0) fmb::ordered_epoch_body<GL, KF, 0, ZF>(a, smem);
         else fmb::ordered_epoch_body<GL, KF, 1, ZF>(a, smem);
