@@ -13,6 +13,7 @@ run() {  # n port extra...
 run 8 29521 > gpurun_out/r2_bench_n8.json 2> gpurun_out/r2_bench_n8.err; echo "n8 rc=$?"; tail -n 2 gpurun_out/r2_bench_n8.err
 run 4 29522 > gpurun_out/r2_bench_n4.json 2> gpurun_out/r2_bench_n4.err; echo "n4 rc=$?"
 run 8 29524 --collective nccl --no-parity --no-extras > gpurun_out/r2_bench_n8_nccl.json 2> gpurun_out/r2_bench_n8_nccl.err; echo "n8 nccl rc=$?"
+timeout 300 python -m pytest tests/test_cli_gpu.py -m gpu -q -s -k "two_gpus" 2>&1 | tail -n 4
 python - <<'PY'
 import json
 for f in ("n8", "n4", "n8_nccl"):

@@ -181,8 +181,10 @@ def test_rmse_trajectory_tracks_oracle_on_learnable_data(built_lib):
         print("[hogwild 200k] epoch %d  gpu train %.5f test %.5f | oracle train %.5f test %.5f" % (e, g_tr, g_te, o_tr, o_te))
     # the concurrent schedule lags the sequential one in the first epochs (one damped
     # Jacobi-like sweep vs 200k Gauss-Seidel steps) and converges to the same optimum
-    assert worst < 0.08, worst
-    assert gaps[-1] < 0.01 and gaps[-1] < gaps[0], gaps
+    # (r02 runs: 0.057 in epoch 0 -- this 200k-row set is smaller than the 113k-row window is comfortable with --
+    # and 0.003 after 6 epochs; the C2-size trajectory test below holds the tighter bars)
+    assert worst < 0.07, worst
+    assert gaps[-1] < 0.006 and gaps[-1] < gaps[0], gaps
     assert g_te < 1.0  # it learned: the no-signal RMSE of these ratings is ~1.17
     l.close()
 
