@@ -347,21 +347,27 @@ __device__ __forceinline__ void ord_bias_chain(const double2* sAB, double2* sPre
       else if (sh == 3) ord_bias_compose<8>(sAB, sPre, t0, A, B);
       else ord_bias_compose<16>(sAB, sPre, t0, A, B);
     }
-    // the totals first (independent shuffles), then every lane threads the bias through them; lane q keeps step q
-    // (measured against a shared-memory exchange with 16 segments, r02 call K: the shuffles are faster)
-    double Aq[ORD_SEGS], Bq[ORD_SEGS];
+    // Inclusive scan of the 8 segment totals over the first 8 lanes (3 Kogge-Stone steps: maps compose as
+    // (A2,B2) o (A1,B1) = (A2 A1, A2 B1 + B2)), then lane s applies "everything before segment s" to the run's
+    // starting bias.  28 instructions where threading the bias through 8 fetched totals took ~60; this warp's
+    // instruction count IS the run's critical path.
 #pragma unroll
-    for (int q = 0; q < ORD_SEGS; q++) {
-      Aq[q] = __shfl_sync(0xffffffffu, A, q);
-      Bq[q] = __shfl_sync(0xffffffffu, B, q);
+    for (int o = 1; o < ORD_SEGS; o <<= 1) {
+      const double Ap = __shfl_up_sync(0xffffffffu, A, o), Bp = __shfl_up_sync(0xffffffffu, B, o);
+      if (lane >= o) {  // (lanes >= ORD_SEGS carry the identity through and are never read)
+        B = fma(A, Bp, B);
+        A = A * Ap;
+      }
     }
-    double w = w0;
-#pragma unroll
-    for (int q = 0; q < ORD_SEGS; q++) {
-      if (lane == q) sW[q] = w;
-      w = fma(Aq[q], w, Bq[q]);  // (segments behind the run are the identity: w stays exactly w)
+    // exclusive prefix = the inclusive one of the lane below
+    double Ae = __shfl_up_sync(0xffffffffu, A, 1), Be = __shfl_up_sync(0xffffffffu, B, 1);
+    if (lane == 0) {
+      Ae = 1.0;
+      Be = 0.0;
     }
-    if (lane == 0) sW[ORD_SMAX] = w;
+    if (lane < ORD_SEGS) sW[lane] = fma(Ae, w0, Be);
+    const double w = fma(A, w0, B);  // lane ORD_SEGS - 1: the bias after the run
+    if (lane == ORD_SEGS - 1) sW[ORD_SMAX] = w;
   } else if (lane == 0) {
     double w = fma(sPre[from - 1].x, sW[(from - 1) >> sh], sPre[from - 1].y);  // the bias example from-1 read ...
     w = fma(sAB[from - 1].x, w, sAB[from - 1].y);                             // ... and left (its pair is corrected)
@@ -599,14 +605,24 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
         if (act && !(a.debug & 4)) {
           double* oa = reinterpret_cast<double*>(smem + rec + jb * recb);
           double* ob = oa + a.rs;
+          // fm_sgd.h:44-48 with x = 1: grad of v_af = sum_f - v_af = v_bf
+          if (regv == 0.0) {  // (uniform) no regularisation: one FMA per factor, v - (lr mult) v_other
+            const double lm = -lr * mult;
 #pragma unroll
-          for (int q = 0; q < KF; q += 2) {
-            // fm_sgd.h:44-48 with x = 1: grad of v_af = sum_f - v_af = v_bf
-            const double a0 = fv[0][q], a1 = fv[0][q + 1], b0 = fv[1][q], b1 = fv[1][q + 1];
-            *reinterpret_cast<double2*>(oa + q) =
-                make_double2(fma(-lr, fma(regv, a0, mult * b0), a0), fma(-lr, fma(regv, a1, mult * b1), a1));
-            *reinterpret_cast<double2*>(ob + q) =
-                make_double2(fma(-lr, fma(regv, b0, mult * a0), b0), fma(-lr, fma(regv, b1, mult * a1), b1));
+            for (int q = 0; q < KF; q += 2) {
+              const double a0 = fv[0][q], a1 = fv[0][q + 1], b0 = fv[1][q], b1 = fv[1][q + 1];
+              *reinterpret_cast<double2*>(oa + q) = make_double2(fma(lm, b0, a0), fma(lm, b1, a1));
+              *reinterpret_cast<double2*>(ob + q) = make_double2(fma(lm, a0, b0), fma(lm, a1, b1));
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < KF; q += 2) {
+              const double a0 = fv[0][q], a1 = fv[0][q + 1], b0 = fv[1][q], b1 = fv[1][q + 1];
+              *reinterpret_cast<double2*>(oa + q) =
+                  make_double2(fma(-lr, fma(regv, a0, mult * b0), a0), fma(-lr, fma(regv, a1, mult * b1), a1));
+              *reinterpret_cast<double2*>(ob + q) =
+                  make_double2(fma(-lr, fma(regv, b0, mult * a0), b0), fma(-lr, fma(regv, b1, mult * a1), b1));
+            }
           }
           if (k1) {
             oa[kw + (fid[0] & 1u)] = fma(-lr, fma(regw, fw[0], mult), fw[0]);

@@ -93,6 +93,7 @@ struct MeanFieldArgs {
   PeerArgs p;
   float4* base_local;              // theta0 in, theta out
   const float* cnt[FMB200_MAX_PEERS];
+  float* cntm;                     // local: the features' mean count per shard (fm_peer_counts_mean_kernel)
   const float* part_in;            // [n_part] partial sums of |V|^2 of theta0
   float* part_out;                 // [gridDim.x]
   int n_part;
@@ -111,8 +112,7 @@ __device__ __forceinline__ float mf_gamma(float u, float G) {
 
 // header of both mean-field kernels: the leading barrier, h_V from the previous exchange's partials
 // (fixed order: identical in every block of every rank), the bias' gamma.  Returns (hv, g0).
-__device__ __forceinline__ void mf_prologue(const MeanFieldArgs& a, float* s_red, float* hv_out, float* g0_out) {
-  const PeerArgs& p = a.p;
+__device__ __forceinline__ void mf_barrier(const PeerArgs& p) {
   if (blockIdx.x == 0 && threadIdx.x < p.world) st_release_sys(p.flags[threadIdx.x] + p.rank, p.seq);
   if (threadIdx.x < p.world) {
     const unsigned int* mine = p.flags[p.rank] + threadIdx.x;
@@ -120,6 +120,26 @@ __device__ __forceinline__ void mf_prologue(const MeanFieldArgs& a, float* s_red
     }
   }
   __syncthreads();
+}
+
+// First kernel of a mean-field exchange: the cross-GPU barrier, then every feature's mean count per shard into a
+// LOCAL table.  The combine kernels read that table; fetching the G counts per state element from the peers
+// again (16 peer loads per k = 8 factor row at G = 8, as many as the state itself) made the C2 exchange 65 us at
+// N = 8 (r02 8-GPU run).
+__global__ void __launch_bounds__(256) fm_peer_counts_mean_kernel(const MeanFieldArgs a) {
+  const PeerArgs& p = a.p;
+  mf_barrier(p);
+  const float G = (float)p.world;
+  for (uint64_t f = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; f < a.n; f += (uint64_t)gridDim.x * blockDim.x) {
+    float c = 0.f;
+    for (int q = 0; q < p.world; q++) c += __ldcv(a.cnt[q] + f);
+    a.cntm[f] = c / G;
+  }
+}
+
+// (the barrier has been passed by fm_peer_counts_mean_kernel, in front of this kernel in the stream)
+__device__ __forceinline__ void mf_prologue(const MeanFieldArgs& a, float* s_red, float* hv_out, float* g0_out) {
+  const PeerArgs& p = a.p;
   const float G = (float)p.world;
   float acc = 0.f;
   for (int i = threadIdx.x; i < a.n_part; i += 256) acc += a.part_in[i];
@@ -163,20 +183,12 @@ __device__ __forceinline__ float4 mf_combine(const MeanFieldArgs& a, uint64_t i,
       const uint64_t rel = e0 + j - a.off_w;
       const uint64_t f = rel / a.ws;
       g[j] = 0.f;
-      if (rel % a.ws == 0 && f < a.n) {
-        float c = 0.f;
-        for (int q = 0; q < p.world; q++) c += __ldcv(a.cnt[q] + f);
-        g[j] = mf_gamma(a.lr * (1.f + a.regw) * (c / G), G);
-      }
+      if (rel % a.ws == 0 && f < a.n) g[j] = mf_gamma(a.lr * (1.f + a.regw) * a.cntm[f], G);
     }
   } else {
     const uint64_t f = (e0 - a.off_v) / a.kp;  // kp is a multiple of 4: one row per float4
     float gv = 0.f;
-    if (f < a.n) {
-      float c = 0.f;
-      for (int q = 0; q < p.world; q++) c += __ldcv(a.cnt[q] + f);
-      gv = mf_gamma(a.lr * (hv + a.regv) * (c / G), G);
-    }
+    if (f < a.n) gv = mf_gamma(a.lr * (hv + a.regv) * a.cntm[f], G);
     g[0] = g[1] = g[2] = g[3] = gv;
   }
   float4 o;
@@ -297,6 +309,7 @@ cudaError_t peer_preload_kernels() {
   if ((e = cudaFuncGetAttributes(&fa, fm_peer_mean_kernel)) != cudaSuccess) return e;
   if ((e = cudaFuncGetAttributes(&fa, fm_peer_meanfield_kernel)) != cudaSuccess) return e;
   if ((e = cudaFuncGetAttributes(&fa, fm_peer_meanfield_sliced_kernel)) != cudaSuccess) return e;
+  if ((e = cudaFuncGetAttributes(&fa, fm_peer_counts_mean_kernel)) != cudaSuccess) return e;
   if ((e = cudaFuncGetAttributes(&fa, fm_peer_capture_kernel)) != cudaSuccess) return e;
   if ((e = cudaFuncGetAttributes(&fa, fm_peer_counts_kernel)) != cudaSuccess) return e;
   return cudaFuncGetAttributes(&fa, fm_peer_barrier_kernel);
@@ -360,6 +373,7 @@ cudaError_t launch_peer_meanfield(fmb200_ctx* c) {
   a.p.inv_world = 1.f / (float)c->peer_world;
   a.base_local = reinterpret_cast<float4*>(c->comm_base + extra);
   float* part = reinterpret_cast<float*>(c->comm_base + extra + c->comm_buf_bytes) + c->comm_cnt_floats;
+  a.cntm = part + 2 * (size_t)FMB_PEER_PART;
   a.part_in = part + (size_t)c->peer_part_cur * FMB_PEER_PART;
   a.part_out = part + (size_t)(c->peer_part_cur ^ 1) * FMB_PEER_PART;
   a.n_part = c->peer_n_part;
@@ -372,7 +386,12 @@ cudaError_t launch_peer_meanfield(fmb200_ctx* c) {
   a.reg0 = (float)c->hp.reg0;
   a.regw = (float)c->hp.regw;
   a.regv = (float)c->hp.regv;
-  // small state: one-shot (one barrier); large state: sliced (1/G of the reads; + a trailing barrier)
+  {  // the barrier + the local table of mean counts
+    const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>((c->n + 255) / 256, (uint32_t)c->sm_count));
+    fm_peer_counts_mean_kernel<<<grid, 256, 0, c->stream>>>(a);
+    c->launches++;
+  }
+  // small state: one-shot; large state: sliced (1/G of the reads; + a trailing barrier)
   bool sliced = a.p.n_vec * 16ull >= (8ull << 20);
   if (c->tune_variant == 8) sliced = true;
   if (c->tune_variant == 9) sliced = false;

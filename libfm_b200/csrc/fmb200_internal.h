@@ -113,7 +113,7 @@ struct fmb200_ctx {
   // peer-memory parameter averaging (fm_peer.cu).  comm block = [flags | buf0 | buf1]
   unsigned char* comm_base = nullptr;
   size_t comm_hdr = 1024, comm_buf_bytes = 0;
-  // behind the two state buffers: theta0 (comm_buf_bytes) | counts (comm_cnt_floats) | |V|^2 partials (2 x FMB_PEER_PART)
+  // behind the two state buffers: theta0 (comm_buf_bytes) | counts (comm_cnt_floats) | |V|^2 partials (2 x FMB_PEER_PART) | mean counts (comm_cnt_floats)
   size_t comm_cnt_floats = 0;
   bool peer_base_valid = false;  // theta0 holds the state the running epoch started from
   bool hogwild_fresh = true;     // no HOGWILD epoch has run since the state was last set (bias ramp)
