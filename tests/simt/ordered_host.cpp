@@ -285,26 +285,26 @@ bool run_case(const Case& c) {
 int main(int argc, char** argv) {
   const bool quick = argc > 1 && !strcmp(argv[1], "--quick");
   std::vector<Case> cases = {
-      {"c2_like", 3000, 1000, 8, 1, 1, 0, {0, 0, 0}, 0, 0, 64, 4, 0.02},
-      {"c2_like_small_tiles", 1500, 300, 8, 1, 1, 0, {0, 0, 0}, 0, 0, 8, 2, 0.02},
-      {"hot_features", 1500, 40, 8, 1, 1, 0, {0, 0, 0}, 0, 0, 32, 2, 0.02},
-      {"ragged_real_values", 1500, 400, 8, 1, 1, 0, {0, 0, 0}, 4, 0, 32, 2, 0.02},
-      {"dups_in_row", 1500, 300, 8, 1, 1, 0, {0.01, 0.02, 0.03}, 4, 5, 16, 2, 0.02},
-      {"classification", 1500, 500, 8, 1, 1, 1, {0, 0, 0}, 0, 0, 32, 2, 0.05},
-      {"no_bias_no_linear", 1500, 500, 8, 0, 0, 0, {0, 0, 0}, 0, 0, 32, 2, 0.02},
-      {"k3_odd_reg", 1500, 401, 3, 1, 1, 0, {0.01, 0.02, 0.03}, 4, 7, 32, 2, 0.02},
-      {"k16_longer_rows", 800, 600, 16, 1, 1, 0, {0, 0, 0.01}, 12, 9, 8, 2, 0.01},
-      {"k40_two_per_lane", 400, 300, 40, 1, 1, 1, {0, 0, 0}, 6, 0, 4, 2, 0.02},
-      {"k1", 1000, 200, 1, 1, 1, 0, {0, 0, 0}, 3, 4, 32, 1, 0.02},
-      {"k0_linear_only", 1000, 200, 0, 1, 1, 0, {0, 0, 0}, 3, 0, 32, 1, 0.02},
-      {"single_row_tiles", 300, 100, 8, 1, 1, 0, {0, 0, 0}, 5, 3, 1, 2, 0.02},
+      {"c2_like", 1200, 1000, 8, 1, 1, 0, {0, 0, 0}, 0, 0, 64, 4, 0.02},
+      {"c2_like_small_tiles", 700, 300, 8, 1, 1, 0, {0, 0, 0}, 0, 0, 8, 2, 0.02},
+      {"hot_features", 700, 40, 8, 1, 1, 0, {0, 0, 0}, 0, 0, 32, 2, 0.02},
+      {"ragged_real_values", 700, 400, 8, 1, 1, 0, {0, 0, 0}, 4, 0, 32, 2, 0.02},
+      {"dups_in_row", 700, 300, 8, 1, 1, 0, {0.01, 0.02, 0.03}, 4, 5, 16, 2, 0.02},
+      {"classification", 700, 500, 8, 1, 1, 1, {0, 0, 0}, 0, 0, 32, 2, 0.05},
+      {"no_bias_no_linear", 700, 500, 8, 0, 0, 0, {0, 0, 0}, 0, 0, 32, 2, 0.02},
+      {"k3_odd_reg", 700, 401, 3, 1, 1, 0, {0.01, 0.02, 0.03}, 4, 7, 32, 2, 0.02},
+      {"k16_longer_rows", 500, 600, 16, 1, 1, 0, {0, 0, 0.01}, 12, 9, 8, 2, 0.01},
+      {"k40_two_per_lane", 300, 300, 40, 1, 1, 1, {0, 0, 0}, 6, 0, 4, 2, 0.02},
+      {"k1", 600, 200, 1, 1, 1, 0, {0, 0, 0}, 3, 4, 32, 1, 0.02},
+      {"k0_linear_only", 600, 200, 0, 1, 1, 0, {0, 0, 0}, 3, 0, 32, 1, 0.02},
+      {"single_row_tiles", 200, 100, 8, 1, 1, 0, {0, 0, 0}, 5, 3, 1, 2, 0.02},
       {"tiny", 5, 6, 8, 1, 1, 0, {0, 0, 0}, 0, 0, 32, 2, 0.02},
       // the warp-specialised driver (helper warps write tile T-1 back and fetch tile T+1 while tile T runs)
-      {"ws_c2_like", 3000, 1000, 8, 1, 1, 0, {0, 0, 0}, 0, 0, 64, 4, 0.02, 2},
-      {"ws_small_tiles_hot", 1500, 60, 8, 1, 1, 0, {0, 0, 0}, 0, 0, 8, 2, 0.02, 1},
-      {"ws_ragged_dups_k3", 1500, 300, 3, 1, 1, 0, {0.01, 0.02, 0.03}, 4, 5, 16, 2, 0.02, 2},
-      {"ws_k16_classification", 800, 600, 16, 1, 1, 1, {0, 0, 0.01}, 12, 9, 8, 2, 0.02, 1},
-      {"ws_single_row_tiles", 300, 100, 8, 1, 1, 0, {0, 0, 0}, 5, 3, 1, 2, 0.02, 1},
+      {"ws_c2_like", 1200, 1000, 8, 1, 1, 0, {0, 0, 0}, 0, 0, 64, 4, 0.02, 2},
+      {"ws_small_tiles_hot", 700, 60, 8, 1, 1, 0, {0, 0, 0}, 0, 0, 8, 2, 0.02, 1},
+      {"ws_ragged_dups_k3", 700, 300, 3, 1, 1, 0, {0.01, 0.02, 0.03}, 4, 5, 16, 2, 0.02, 2},
+      {"ws_k16_classification", 500, 600, 16, 1, 1, 1, {0, 0, 0.01}, 12, 9, 8, 2, 0.02, 1},
+      {"ws_single_row_tiles", 200, 100, 8, 1, 1, 0, {0, 0, 0}, 5, 3, 1, 2, 0.02, 1},
       {"ws_tiny", 5, 6, 8, 1, 1, 0, {0, 0, 0}, 0, 0, 32, 2, 0.02, 1},
   };
   if (quick) cases.resize(3);
