@@ -103,6 +103,7 @@ int upload_begin(fmb200_ctx* c, int slot, uint64_t n_rows, uint64_t nnz, cudaStr
   }
   s.present = false;
   s.links_ready = false;
+  s.upload_gen = ++c->upload_counter;
   s.n_rows = n_rows;
   s.nnz = nnz;
   return 0;
@@ -243,7 +244,7 @@ static int create_resources(fmb200_ctx* c, int device, const cudaDeviceProp& pro
   c->p64.n_doubles = c->p64.off_v + (uint64_t)n_attr * num_factor + 2;
   c->comm_buf_bytes = (c->p32.n_floats * sizeof(float) + 255) & ~(size_t)255;
   c->comm_cnt_floats = ((size_t)n_attr + 63) & ~(size_t)63;
-  const size_t comm_total = c->comm_hdr + 3 * c->comm_buf_bytes + (2 * c->comm_cnt_floats + 2 * (size_t)fmb::FMB_PEER_PART) * sizeof(float);
+  const size_t comm_total = c->comm_hdr + 3 * c->comm_buf_bytes + (3 * c->comm_cnt_floats + 2 * (size_t)fmb::FMB_PEER_PART) * sizeof(float);
   CK(cudaMalloc(&c->comm_base, comm_total));
   CK(cudaMemsetAsync(c->comm_base, 0, comm_total, c->stream));
   c->p32.base = reinterpret_cast<float*>(c->comm_base + c->comm_hdr);

@@ -153,7 +153,7 @@ __device__ __forceinline__ void mf_prologue(const MeanFieldArgs& a, float* s_red
   __syncthreads();
   // rows per shard (header words [64, 64+world)), averaged
   float rows = 0.f;
-  for (int q = 0; q < p.world; q++) rows += (float)__ldcv(p.flags[q] + 64 + q);
+  for (int q = 0; q < p.world; q++) rows += (float)__ldcv(p.flags[q] + 64 + 16 * (p.seq & 1u) + q);
   rows /= G;
   *g0_out = mf_gamma(a.lr * (1.f + a.reg0) * rows, G);
 }
@@ -331,13 +331,21 @@ static int peer_grid(const fmb200_ctx* c, uint64_t n_vec) {
 }
 
 // called in front of a HOGWILD epoch when peers are attached: theta0 and the shard's counts
+// Where rank-local things live behind the two state buffers of the comm block:
+//   theta0 (comm_buf_bytes) | counts, parity 0 | |V|^2 partials (2 x FMB_PEER_PART) | mean counts | counts, parity 1
+// The published counts (and the row count word in the header) are double-buffered by the parity of the exchange
+// that will read them: a slow peer may still be reading exchange e's table while this rank already prepares e+1.
+static float* peer_cnt_ptr(const fmb200_ctx* c, unsigned char* base, unsigned parity) {
+  float* cnt0 = reinterpret_cast<float*>(base + c->comm_hdr + 3 * c->comm_buf_bytes);
+  return parity ? cnt0 + 2 * c->comm_cnt_floats + 2 * (size_t)FMB_PEER_PART : cnt0;
+}
+
 cudaError_t peer_before_epoch(fmb200_ctx* c, const DataSlot& d) {
   if (c->peer_world <= 1) return cudaSuccess;
   const uint64_t n_vec = (c->p32.n_floats + 3) / 4;
   unsigned char* extra = c->comm_base + c->comm_hdr + 2 * c->comm_buf_bytes;
   float4* base = reinterpret_cast<float4*>(extra);
-  float* cnt = reinterpret_cast<float*>(extra + c->comm_buf_bytes);
-  float* part = cnt + c->comm_cnt_floats;
+  float* part = reinterpret_cast<float*>(extra + c->comm_buf_bytes) + c->comm_cnt_floats;
   if (!c->peer_base_valid) {
     const int grid = peer_grid(c, n_vec);
     fm_peer_capture_kernel<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(c->p32.base), base, n_vec,
@@ -346,12 +354,16 @@ cudaError_t peer_before_epoch(fmb200_ctx* c, const DataSlot& d) {
     c->peer_base_valid = true;
     c->launches++;
   }
-  if (c->n > 0 && d.feat_cnt != nullptr) {
+  // the shard's counts for the exchange behind this epoch, into the table of that exchange's parity -- unless
+  // that table already holds this very upload (every upload of a context has its own generation number)
+  const unsigned parity = (c->peer_seq + 1u) & 1u;
+  if (c->n > 0 && d.feat_cnt != nullptr && c->peer_cnt_stamp[parity] != d.upload_gen) {
     const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>((c->n + 255) / 256, 64));
-    fm_peer_counts_kernel<<<grid, 256, 0, c->stream>>>(d.feat_cnt, cnt, c->n,
-                                                       reinterpret_cast<unsigned int*>(c->comm_base) + 64 + c->peer_rank,
-                                                       (unsigned int)d.n_rows);
+    fm_peer_counts_kernel<<<grid, 256, 0, c->stream>>>(
+        d.feat_cnt, peer_cnt_ptr(c, c->comm_base, parity), c->n,
+        reinterpret_cast<unsigned int*>(c->comm_base) + 64 + 16 * parity + c->peer_rank, (unsigned int)d.n_rows);
     c->launches++;
+    c->peer_cnt_stamp[parity] = d.upload_gen;
   }
   return cudaGetLastError();
 }
@@ -363,7 +375,7 @@ cudaError_t launch_peer_meanfield(fmb200_ctx* c) {
   for (int q = 0; q < c->peer_world; q++) {
     a.p.flags[q] = reinterpret_cast<unsigned int*>(c->peer_base[q]);
     a.p.cur[q] = reinterpret_cast<const float4*>(c->peer_base[q] + c->comm_hdr + (size_t)cur * c->comm_buf_bytes);
-    a.cnt[q] = reinterpret_cast<const float*>(c->peer_base[q] + extra + c->comm_buf_bytes);
+    a.cnt[q] = peer_cnt_ptr(c, c->peer_base[q], (c->peer_seq + 1u) & 1u);
   }
   a.p.next_local = reinterpret_cast<float4*>(c->comm_base + c->comm_hdr + (size_t)(cur ^ 1) * c->comm_buf_bytes);
   a.p.world = c->peer_world;

@@ -25,6 +25,7 @@ struct DataSlot {
   unsigned int* h_flag = nullptr;  // pinned mirror
   cudaEvent_t ready = nullptr;     // recorded behind the upload's last operation
   bool pending = false;            // an upload is enqueued and not yet collected
+  uint64_t upload_gen = 0;         // unique per upload of a context (fmb200_ctx::upload_counter)
   uint32_t max_feat_cnt = 0;
   // worst-case 4-element-aligned nnz span of any tile of 2^(5+i) rows
   // (i = 0..4 -> 32, 64, 128, 256, 512 rows); sizes the smem staging buffers
@@ -113,7 +114,7 @@ struct fmb200_ctx {
   // peer-memory parameter averaging (fm_peer.cu).  comm block = [flags | buf0 | buf1]
   unsigned char* comm_base = nullptr;
   size_t comm_hdr = 1024, comm_buf_bytes = 0;
-  // behind the two state buffers: theta0 (comm_buf_bytes) | counts (comm_cnt_floats) | |V|^2 partials (2 x FMB_PEER_PART) | mean counts (comm_cnt_floats)
+  // behind the two state buffers: theta0 (comm_buf_bytes) | counts (comm_cnt_floats) | |V|^2 partials (2 x FMB_PEER_PART) | mean counts | counts of the other parity
   size_t comm_cnt_floats = 0;
   bool peer_base_valid = false;  // theta0 holds the state the running epoch started from
   bool hogwild_fresh = true;     // no HOGWILD epoch has run since the state was last set (bias ramp)
@@ -122,6 +123,9 @@ struct fmb200_ctx {
   bool peer_ipc[FMB200_MAX_PEERS] = {false};
   int peer_world = 1, peer_rank = 0, peer_cur = 0;
   unsigned int peer_seq = 0, peer_bar_seq = 0;
+  // which counts the comm block currently publishes (fm_peer.cu::peer_before_epoch)
+  uint64_t peer_cnt_stamp[2] = {0, 0};  // upload generation held by the table of each parity (0 = none)
+  uint64_t upload_counter = 0;          // generations handed out to uploads
   // SGDA state (fm_learn_sgd_element_adapt_reg.h): stored gradients, per-group regularisation
   double *sgda_grad_w = nullptr, *sgda_grad_v = nullptr, *sgda_reg_w = nullptr, *sgda_reg_v = nullptr;
   uint32_t* sgda_group = nullptr;
