@@ -17,28 +17,31 @@
 //   (2) the bias: w0 is read and rewritten by every example (fm_model.h:107-109,
 //       fm_sgd.h:34-37), but only through  p_t = w0_t + R_t,  R_t = sum_i w_i x_i +
 //       1/2 sum_f (sum_f^2 - sumsq_f)  independent of w0.  For regression the step
-//       w0' = w0 - lr((clamp(w0+R_t) - y_t) + reg0 w0) is piecewise AFFINE in w0: each
-//       warp solves the whole run with one affine prefix scan (Kogge-Stone over shuffles,
-//       2 examples per lane), guessing every example's clamp state (inside / at min / at
-//       max) from the run's initial w0 and re-scanning while any guess is contradicted --
-//       a consistent assignment is the sequential answer (induction over t), and at least
-//       one more prefix element is final per pass.  Classification (logistic multiplier)
+//       w0' = w0 - lr((clamp(w0+R_t) - y_t) + reg0 w0) is AFFINE in w0 once the example's
+//       clamp state (inside / at min / at max) is fixed.  Every example's thread guesses its
+//       state from the bias at the start of the run and publishes (a_t, b_t); warp 0 walks
+//       w <- fma(a_t, w, b_t), cut into 8 segments composed in parallel (ord_bias_chain);
+//       the examples' threads check their guess against the bias they actually read, and
+//       the chain is re-walked behind the first contradicted one -- a consistent assignment
+//       IS the sequential answer (induction over t).  Classification (logistic multiplier)
 //       walks the chain serially from shared memory.
-//   (3) memory latency: one CTA owns the epoch (there is ONE chain).  Rows are cut into
-//       TILES; while tile T is processed the CSR of tile T+2 arrives by TMA bulk copies
-//       (cp.async.bulk + mbarrier) and the w / V records of tile T+1 arrive by cp.async
-//       (L2 -> shared, 16 B) into a 3-deep ring of record buffers.  A record fetched that
-//       early is stale if its feature is written by tile T or T+1 itself; exactly those
+//   (3) memory: one CTA owns the epoch (there is ONE chain), warp-specialised where the
+//       thread budget allows (ordered_epoch_body_ws): compute warps walk the runs of tile T
+//       while a helper warp writes tile T-1's final records back to global memory and
+//       fetches tile T+1's records (cp.async, L2 -> shared, 16 B) into a 3-deep ring; the CSR
+//       of tile T+2 arrives by TMA bulk copies (cp.async.bulk + mbarrier).  A record fetched
+//       that early is stale if its feature is written by tile T or T+1 itself; exactly those
 //       entries (known from `link`) skip the fetch and read the record FORWARDED in shared
-//       memory: every fm_SGD result lands in the writer's own ring slot, and the tile's final
-//       records are written back to global memory in one pass at the end of the tile.
+//       memory: every fm_SGD result lands in the writer's own ring slot.
 //
 // Thread mapping: GL lanes per example, each owning KF <= 8 CONSECUTIVE factors (k <= 8: one
 // lane per example, no cross-lane reduction at all), at most min(ORD_SMAX, 1024 / GL) examples
-// per run, blockDim = that many examples x GL.  The bias scan and the search for the next
-// run's length are done by warp 0 alone and published through shared memory: the r02 ncu capture
-// of the first version (every warp scanning redundantly, 8 lanes per example) showed an
-// ISSUE-bound kernel -- 204 warp instructions per row, 40% of them the 16 redundant scans.
+// per run.  ZF > 0 kernels (k in {2,4,8}, rows of <= ZF entries) keep a row's records in
+// registers from the score to the update; the one-hot two-field shape has its own formulas.
+//
+// The mode is bound by LATENCY: with one warp per scheduler every dependent instruction costs
+// 4-8 cycles, and a run is score -> chain -> check + update with three barriers.  What the
+// round-2 measurements say about each structure tried is in DESIGN.md section 3.2.
 //
 // This header is also compiled for the host (tests/simt/: FMB_SIMT_HOST) and run thread
 // for thread against the sequential oracle.
@@ -70,9 +73,8 @@ constexpr int ORD_NBUF = 3;    // ring depth (CSR stages and record buffers)
 // [64, +2048) sAB: per example (a_t, b_t) of its bias step w -> a_t w + b_t   (classification: sR scores | sM
 // multipliers) | [2112, +1032) sW: [0, 8) the bias at the start of each chain segment, [ORD_SMAX] the bias after the run
 // | [3200, +2048) sPre: per example the affine map from its segment's start to the bias it reads
-// | [5248, +256) sTot: the chain segments' totals | [5504, +128) phase timers (development aid)
+// | [5248, +256) spare | [5504, +128) phase timers (development aid)
 constexpr int ORD_HDR_BYTES = 5632;
-constexpr int ORD_STOT_OFF = 5248;
 constexpr int ORD_PROF_OFF = 5504;
 constexpr int ORD_SW_OFF = 64 + 2 * ORD_SMAX * 8;  // sW[0..8): the bias at the start of each segment; sW[ORD_SMAX]: after the run
 constexpr int ORD_SPRE_OFF = 3200;
@@ -337,8 +339,8 @@ __device__ __forceinline__ void ord_bias_compose(const double2* sAB, double2* sP
   }
 }
 // Executed by the whole of warp 0.  sh = log2(segment length): 2 (P <= 32), 3 (P <= 64), 4.
-__device__ __forceinline__ void ord_bias_chain(const double2* sAB, double2* sPre, double* sW, double2* sTot, int from,
-                                               int P, int sh, double w0, int lane) {
+__device__ __forceinline__ void ord_bias_chain(const double2* sAB, double2* sPre, double* sW, int from, int P, int sh,
+                                               double w0, int lane) {
   if (from == 0) {
     double A = 1.0, B = 0.0;  // lanes without a segment keep the identity
     if (lane < ORD_SEGS) {
@@ -446,7 +448,6 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
   double2* sAB = reinterpret_cast<double2*>(smem + 64);
   double* sW = reinterpret_cast<double*>(smem + ORD_SW_OFF);
   double2* sPre = reinterpret_cast<double2*>(smem + ORD_SPRE_OFF);
-  double2* sTot = reinterpret_cast<double2*>(smem + ORD_STOT_OFF);
   const int dwarp = nthreads > 32 ? 1 : 0;  // the warp that searches the next run
   const int k = cc.k, kw = cc.kw;
   const bool k0 = cc.k0, k1 = cc.k1;
@@ -705,7 +706,7 @@ __device__ __forceinline__ void ord_tile_runs(const OrderedArgs& a, unsigned cha
             for (int t = lane; t < P; t += 32) sPre[t] = make_double2(0.0, 0.0);
             if (lane == 0) sW[ORD_SMAX] = 0.0;
           } else {
-            ord_bias_chain(sAB, sPre, sW, sTot, from, P, sh, w0, lane);
+            ord_bias_chain(sAB, sPre, sW, from, P, sh, w0, lane);
           }
         }
         ORD_PROF(tid == 0, 2);  // the chain
