@@ -55,12 +55,20 @@ __global__ void __launch_bounds__(256) fm_peer_mean_kernel(const PeerArgs a) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < a.n_vec;
        i += (uint64_t)gridDim.x * blockDim.x) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int q = 0; q < a.world; q++) {
-      const float4 v = __ldcv(a.cur[q] + i);  // never from a stale L1 line
-      s.x += v.x;
-      s.y += v.y;
-      s.z += v.z;
-      s.w += v.w;
+    for (int q0 = 0; q0 < a.world; q0 += 8) {  // 8 independent peer loads at a time, summed in rank order
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        v[u] = (q0 + u < a.world) ? __ldcv(a.cur[q0 + u] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        if (q0 + u < a.world) {
+          s.x += v[u].x;
+          s.y += v[u].y;
+          s.z += v[u].z;
+          s.w += v[u].w;
+        }
+      }
     }
     s.x *= a.inv_world;
     s.y *= a.inv_world;
@@ -132,7 +140,13 @@ __global__ void __launch_bounds__(256) fm_peer_counts_mean_kernel(const MeanFiel
   const float G = (float)p.world;
   for (uint64_t f = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; f < a.n; f += (uint64_t)gridDim.x * blockDim.x) {
     float c = 0.f;
-    for (int q = 0; q < p.world; q++) c += __ldcv(a.cnt[q] + f);
+    for (int q0 = 0; q0 < p.world; q0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = (q0 + u < p.world) ? __ldcv(a.cnt[q0 + u] + f) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; u++) c += v[u];  // (rank order; absent ranks add an exact 0)
+    }
     a.cntm[f] = c / G;
   }
 }
@@ -165,12 +179,22 @@ __device__ __forceinline__ float4 mf_combine(const MeanFieldArgs& a, uint64_t i,
   const float4 b4 = a.base_local[i];
   float b[4] = {b4.x, b4.y, b4.z, b4.w};
   float d[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int q = 0; q < p.world; q++) {
-    const float4 v = __ldcv(p.cur[q] + i);  // never from a stale L1 line
-    d[0] += v.x - b[0];
-    d[1] += v.y - b[1];
-    d[2] += v.z - b[2];
-    d[3] += v.w - b[3];
+  // the replicas' elements in batches of 8 INDEPENDENT peer loads (a loop over a runtime world size issues
+  // one NVLink round trip after the other: 8 x ~2 us per element at G = 8), summed in rank order
+  for (int q0 = 0; q0 < p.world; q0 += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      v[u] = (q0 + u < p.world) ? __ldcv(p.cur[q0 + u] + i) : b4;  // never from a stale L1 line
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      if (q0 + u < p.world) {
+        d[0] += v[u].x - b[0];
+        d[1] += v[u].y - b[1];
+        d[2] += v[u].z - b[2];
+        d[3] += v[u].w - b[3];
+      }
+    }
   }
   const uint64_t e0 = i * 4;
   float g[4];

@@ -6,10 +6,10 @@ run() { n=$1; port=$2; shift 2
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port \
     bench.py --gpus $n --steps 30 --warmup 5 "$@"; }
 run 8 29541 > gpurun_out/r2_bench_n8b.json 2> gpurun_out/r2_bench_n8b.err; echo "n8 rc=$?"; tail -n 2 gpurun_out/r2_bench_n8b.err
-run 4 29542 --no-parity > gpurun_out/r2_bench_n4b.json 2> gpurun_out/r2_bench_n4b.err; echo "n4 rc=$?"
+timeout 300 python -m pytest tests/test_hogwild_gpu.py tests/test_cli_gpu.py -m gpu -q -k "peer or two_gpus" 2>&1 | tail -n 2
 python - <<'PY'
 import json
-for f in ("n8b", "n4b"):
+for f in ("n8b",):
     try:
         d = json.loads(open("gpurun_out/r2_bench_%s.json" % f).read().strip().splitlines()[-1])
         print(f, "value %.4g ms %.4f e2e %.4g launches %d" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["gpu_launches"]))
