@@ -299,7 +299,13 @@ int main(int argc, char** argv) {
       {"k0_linear_only", 600, 200, 0, 1, 1, 0, {0, 0, 0}, 3, 0, 32, 1, 0.02},
       {"single_row_tiles", 200, 100, 8, 1, 1, 0, {0, 0, 0}, 5, 3, 1, 2, 0.02},
       {"tiny", 5, 6, 8, 1, 1, 0, {0, 0, 0}, 0, 0, 32, 2, 0.02},
+      // the bias chain under stress: big steps push scores across the clamps (contradicted guesses, re-walks)
+      {"oh_clamp_heavy", 700, 120, 8, 1, 1, 0, {0, 0, 0}, 0, 0, 32, 4, 0.3},
+      {"oh_regularised", 700, 300, 8, 1, 1, 0, {0.02, 0.01, 0.03}, 0, 0, 32, 4, 0.05},
+      {"k8_max2_real_clamps", 700, 200, 8, 1, 1, 0, {0, 0.01, 0.01}, 2, 0, 16, 2, 0.25},
+      {"k4_short_rows", 700, 200, 4, 1, 1, 0, {0, 0, 0.02}, 4, 6, 32, 2, 0.1},
       // the warp-specialised driver (helper warps write tile T-1 back and fetch tile T+1 while tile T runs)
+      {"ws_oh_clamp_heavy", 700, 120, 8, 1, 1, 0, {0, 0, 0}, 0, 0, 32, 4, 0.3, 1},
       {"ws_c2_like", 1200, 1000, 8, 1, 1, 0, {0, 0, 0}, 0, 0, 64, 4, 0.02, 2},
       {"ws_small_tiles_hot", 700, 60, 8, 1, 1, 0, {0, 0, 0}, 0, 0, 8, 2, 0.02, 1},
       {"ws_ragged_dups_k3", 700, 300, 3, 1, 1, 0, {0.01, 0.02, 0.03}, 4, 5, 16, 2, 0.02, 2},

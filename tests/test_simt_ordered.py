@@ -2,7 +2,8 @@
 through tests/simt/cta_shim.h and run as one OS thread per CUDA thread -- __syncthreads / warp
 collectives as pthread barriers, cp.async and TMA bulk copies performed at issue time (the most stale
 view the hardware may give), mbarriers as byte counters -- against the sequential oracle
-(oracle/fm_oracle.c) on 20 shapes (14 through the single-role driver, 6 through the warp-specialised one): tiles of 1..64 rows, 1..4 warps, k in {0,1,3,8,16,40}, repeated
+(oracle/fm_oracle.c) on 25 shapes (18 through the single-role driver, 7 through the warp-specialised one; four of them take big
+steps so that scores cross the clamps and the bias chain is re-walked): tiles of 1..64 rows, 1..4 warps, k in {0,1,3,8,16,40}, repeated
 features inside a row, hot features (runs of one row), classification, no bias.  The kernel
 re-associates sums, so the bar is 1e-10 relative on every parameter after two epochs.
 
@@ -37,4 +38,4 @@ def test_ordered_kernel_source_on_host_threads_matches_oracle():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stdout + r.stderr
     lines = [l for l in r.stdout.splitlines() if " ok" in l]
-    assert len(lines) == 20 and "ALL OK" in r.stdout, r.stdout
+    assert len(lines) == 25 and "ALL OK" in r.stdout, r.stdout
