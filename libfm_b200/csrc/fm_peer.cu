@@ -138,6 +138,17 @@ __global__ void __launch_bounds__(256) fm_peer_counts_mean_kernel(const MeanFiel
   const PeerArgs& p = a.p;
   mf_barrier(p);
   const float G = (float)p.world;
+  if (blockIdx.x == 0) {  // rows per shard (the peers' header words [64 + 16 parity + rank]), averaged in rank order
+    __shared__ unsigned int s_rows[FMB200_MAX_PEERS];
+    if ((int)threadIdx.x < p.world)
+      s_rows[threadIdx.x] = __ldcv(p.flags[threadIdx.x] + 64 + 16 * (p.seq & 1u) + threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float rows = 0.f;
+      for (int q = 0; q < p.world; q++) rows += (float)s_rows[q];
+      p.flags[p.rank][100 + (p.seq & 1u)] = __float_as_uint(rows / G);
+    }
+  }
   for (uint64_t f = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; f < a.n; f += (uint64_t)gridDim.x * blockDim.x) {
     float c = 0.f;
     for (int q0 = 0; q0 < p.world; q0 += 8) {
@@ -165,10 +176,9 @@ __device__ __forceinline__ void mf_prologue(const MeanFieldArgs& a, float* s_red
   }
   *hv_out = a.n ? s_red[0] / (float)a.n : 0.f;
   __syncthreads();
-  // rows per shard (header words [64, 64+world)), averaged
-  float rows = 0.f;
-  for (int q = 0; q < p.world; q++) rows += (float)__ldcv(p.flags[q] + 64 + 16 * (p.seq & 1u) + q);
-  rows /= G;
+  // mean rows per shard: left in the LOCAL header by fm_peer_counts_mean_kernel (a loop over the peers' words
+  // here was 8 NVLink round trips, one after the other, in every block's prologue at G = 8)
+  const float rows = __uint_as_float(__ldcv(p.flags[p.rank] + 100 + (p.seq & 1u)));
   *g0_out = mf_gamma(a.lr * (1.f + a.reg0) * rows, G);
 }
 
