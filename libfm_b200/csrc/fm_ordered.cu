@@ -266,7 +266,7 @@ cudaError_t launch_sgd_ordered(fmb200_ctx* c, DataSlot& d, bool* handled) {
   cudaError_t e = build_ordered_links(c, d);
   if (e != cudaSuccess) return e;
 
-  OrderedArgs a;
+  OrderedArgs a{};
   a.row_ptr = d.row_ptr;
   a.col = d.col;
   a.val = d.val;

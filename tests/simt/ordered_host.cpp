@@ -218,7 +218,7 @@ bool run_case(const Case& c) {
   unsigned char* smem = smem_raw.data();
   smem += (128 - ((uintptr_t)smem & 127)) & 127;
 
-  fmb::OrderedArgs a;
+  fmb::OrderedArgs a{};  // (zero: a.prof, the phase timers, must be null here)
   a.row_ptr = rp.data();
   a.col = col.data();
   a.val = val.data();
